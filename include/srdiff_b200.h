@@ -1,0 +1,163 @@
+/*
+ * srdiff_b200.h -- C ABI of libsrdiff_b200.so (sm_100a CUDA kernels for the SRDiff
+ * reverse-diffusion inference hot path).
+ *
+ * The reference (aryaman1802/dgm_img_super_resolution) has NO native/FFI layer: its
+ * boundary is the Python module API of srdiff/model.py.  This header is therefore the
+ * interface that the Python mirror of that API (dgm_img_super_resolution_b200/model.py)
+ * binds with ctypes; each entry point names the reference code whose arithmetic it
+ * replaces (file:line in /root/reference/srdiff/model.py).  INTEGRATION.md shows the
+ * binding a maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain pointers and sizes only; no torch types.  Device memory is owned by the caller.
+ *   - every function returns 0 on success, non-zero on failure; srd_last_error() gives the
+ *     message of the last failure on the calling thread.
+ *   - `stream` is a cudaStream_t passed as void*.  Launch functions never allocate, never
+ *     synchronise and never call back into the host, so they may be stream-captured into a
+ *     CUDA graph.
+ *   - Activations are "padded NHWC": [B][H+2][W+2][ct] elements (fp32 or bf16) whose 1-pixel
+ *     border ring holds either zeros (zero padding, RRDB convs :674-678,714-723 and the
+ *     transposed convs :487,759) or the reflected interior (nn.ReflectionPad2d(1) :444,498).
+ *     The producer of a buffer writes the ring (desc.border), consumers never pad.
+ */
+#ifndef SRDIFF_B200_H_
+#define SRDIFF_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SRD_MAX_SRC 3
+
+enum { SRD_F32 = 0, SRD_BF16 = 1 };                      /* activation element type            */
+enum { SRD_KERNEL_AUTO = 0, SRD_KERNEL_DIRECT = 1, SRD_KERNEL_TC = 2 };
+enum { SRD_ACT_NONE = 0, SRD_ACT_MISH = 1, SRD_ACT_LRELU02 = 2 };
+enum { SRD_BORDER_KEEP = 0, SRD_BORDER_REFLECT = 1 };
+
+/* One K-source of an implicit-GEMM convolution: channels [c_off, c_off+cin) of a padded NHWC
+ * buffer with `ct` channels per pixel.  Several sources = torch.cat(..., dim=1) that is never
+ * materialised (Unet skip concat :842, dense-block concats :686-689, cond concat :825). */
+typedef struct {
+  const void* ptr;
+  int32_t ct;
+  int32_t c_off;
+  int32_t cin;
+  int32_t reserved;
+} SrdSrc;
+
+/* Convolution descriptor.  Computes, for every output pixel p and channel n < N,
+ *   acc      = sum_{src, ky, kx, c} in_src[p*stride + (ky,kx)][c] * W[...][n]
+ *   v        = alpha * act(acc + bias[n]) + temb[b*temb_bstride + n]
+ *              + beta1 * res1[p][n] + beta2 * res2[p][n]
+ * and stores v (converted to the activation type) to out / out2 and/or to a planar fp32 NCHW
+ * tensor.  Covers: Block :442-447 (reflect 3x3 + Mish), ResnetBlock tail :476-480, Downsample
+ * :494-503 (stride 2), Upsample :483-491 and cond_proj :759-761 (ConvTranspose2d k=2S, stride S,
+ * pad S/2 run as S*S sub-pixel phases of 2x2 taps), res_conv / final 1x1 :471,800, and the RRDB
+ * convs :674-690,714-745 (zero padding, LeakyReLU 0.2, 0.2-scaled residuals). */
+typedef struct {
+  int32_t dtype;          /* SRD_F32 | SRD_BF16 : element type of src/res/out buffers            */
+  int32_t kernel;         /* SRD_KERNEL_*                                                        */
+  int32_t n_src;
+  int32_t B, H_in, W_in;  /* unpadded input dims shared by all sources                           */
+  SrdSrc src[SRD_MAX_SRC];
+  int32_t stride;         /* 1 | 2 (input stride of the conv)                                    */
+  int32_t nky, nkx;       /* taps per side: 3 (3x3), 2 (transposed-conv phase), 1 (1x1)          */
+  int32_t ky0, kx0;       /* first tap, padded coords, when up == 1 (0 for 3x3, 1 for 1x1)       */
+  int32_t up;             /* S: 1 = plain conv; 2|4 = ConvTranspose2d(k=2S, stride=S, pad=S/2)   */
+  int32_t N;              /* output channels                                                     */
+  const float* w_direct;  /* fp32 [up*up][K][N], K order (src, ky, kx, c)                        */
+  const void* w_tc;       /* bf16 [up*up][KB][Npad][64] K-blocks in order (src, chunk, kx, ky*)  */
+  const float* bias;      /* [N]                                                                 */
+  int32_t act;
+  float alpha;
+  const float* temb;      /* optional [*, N] added after the activation (:476)                   */
+  int32_t temb_bstride;   /* 0 = same row for every image, else elements between images          */
+  const void* res1; int32_t res1_ct, res1_coff; float beta1;
+  const void* res2; int32_t res2_ct, res2_coff; float beta2;
+  void* out;  int32_t out_ct,  out_coff;
+  void* out2; int32_t out2_ct, out2_coff;
+  int32_t H_out, W_out;   /* unpadded output dims (H_in*up for up>1, H_in/stride otherwise)      */
+  int32_t border;         /* SRD_BORDER_* : what the producer writes into out/out2's ring        */
+  float* planar;          /* optional fp32 NCHW [B][planar_c][H_out][W_out] destination          */
+  int32_t planar_c;
+  int32_t planar_clamp01; /* 1: planar = clamp(v,0,1)*2-1 (RRDBNet tail :744-745)                */
+  const float* head_w;    /* optional fused 1x1 head [planar_c][N] (final_conv.1 :800), tc only  */
+  const float* head_b;
+} SrdConvDesc;
+
+typedef struct SrdConvPlan SrdConvPlan;
+
+const char* srd_last_error(void);
+int srd_version(void);
+/* 1 if the tcgen05/TMA path can serve this descriptor (bf16, channel/stride alignment...). */
+int srd_conv_tc_supported(const SrdConvDesc* desc);
+/* Validates the descriptor, picks the kernel, encodes the TMA tensor maps. Host-only work. */
+int srd_conv_plan_create(const SrdConvDesc* desc, SrdConvPlan** out_plan);
+int srd_conv_plan_destroy(SrdConvPlan* plan);
+/* Which kernel the plan resolved to (SRD_KERNEL_DIRECT | SRD_KERNEL_TC). */
+int srd_conv_plan_kernel(const SrdConvPlan* plan);
+/* Launch.  `temb` overrides desc.temb when non-NULL (per-step row of the time table). */
+int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream);
+/* Non-zero after the tcgen05 pipeline watchdog fired (value = which wait timed out). */
+int srd_watchdog_flag(void);
+
+/* Time-embedding table: SinusoidalPosEmb :412-419 -> Unet.mlp :764-768 -> per-ResnetBlock
+ * Mish+Linear :464-467 for n_t time values at once.  out[n_t][S] with S = sum of Cout over
+ * blocks; w_blk [S][dim], b_blk [S] are the per-block Linear weights stacked; freqs[dim/2] =
+ * exp(-j*ln(1e4)/(dim/2-1)) exactly as :415-416 evaluates it (host-provided). */
+int srd_time_table(const float* t_values, int32_t n_t, int32_t dim, const float* freqs,
+                   const float* w0, const float* b0, const float* w2, const float* b2,
+                   const float* w_blk, const float* b_blk, int32_t S,
+                   float* out, void* stream);
+
+/* p_sample update :1054-1060 (+ predict_start_from_noise :968-972, clamp :986-987, q_posterior
+ * :974-981) as ONE vectorised elementwise kernel over [B][chw] fp32 tensors.
+ *   coef: [T][5] fp32 rows {sqrt_recip_ac, sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2,
+ *         post_log_variance_clipped};  t: [B] int32 timestep per image.
+ *   noise: fp32 [B][chw] or NULL -> in-kernel Philox4x32-10 + Box-Muller keyed by
+ *          (seed, step, image_offset + b, element).
+ *   x0_out optional.  img_out optional: res2img :1118-1125 fused,
+ *          img = clamp(x_prev)/res_rescale + img_lr_up (clamp iff clip_input).
+ *   nhwc_out optional: x_prev re-laid out as padded NHWC (ct channels, reflect ring) in
+ *          act_dtype for the next step's first conv. */
+typedef struct {
+  const float* x; const float* eps; const float* noise;
+  const float* coef; const int32_t* t;
+  int32_t B, C, H, W;
+  int32_t clip_denoised;
+  uint64_t seed; uint32_t step; uint32_t image_offset;
+  float* x_out; float* x0_out;
+  float* img_out; const float* img_lr_up; float res_rescale; int32_t clip_input;
+  void* nhwc_out; int32_t nhwc_ct; int32_t act_dtype;
+} SrdPSampleArgs;
+int srd_p_sample_step(const SrdPSampleArgs* args, void* stream);
+
+/* Standard-normal fill with the same Philox stream as srd_p_sample_step (x_T :1070). */
+int srd_randn(float* out, int32_t B, int32_t chw, uint64_t seed, uint32_t step,
+              uint32_t image_offset, void* stream);
+
+/* fp32 NCHW [B][C][H][W] -> padded NHWC [B][H+2][W+2][ct] (channels >= C zeroed),
+ * v = x*scale + shift ((x+1)/2 of RRDBNet.forward :729), ring = reflect | zero. */
+int srd_nchw_to_act(const float* x, int32_t B, int32_t C, int32_t H, int32_t W,
+                    float scale, float shift, void* out, int32_t ct, int32_t dtype,
+                    int32_t border, void* stream);
+/* padded NHWC channels [c_off, c_off+C) -> fp32 NCHW. */
+int srd_act_to_nchw(const void* act, int32_t ct, int32_t c_off, int32_t dtype,
+                    int32_t B, int32_t C, int32_t H, int32_t W, float* out, void* stream);
+/* F.interpolate(scale_factor=2, mode='nearest') :738-739 between padded NHWC buffers
+ * (same ct), zero ring. */
+int srd_upsample_nearest2x(const void* in, void* out, int32_t dtype, int32_t B, int32_t H,
+                           int32_t W, int32_t ct, void* stream);
+/* Mish :422-424 elementwise on fp32 (stand-alone module API). */
+int srd_mish_f32(const float* x, float* y, int64_t n, void* stream);
+/* res2img / img2res :1118-1134 elementwise on fp32. */
+int srd_res2img(const float* x, const float* img_lr_up, float* out, int64_t n,
+                float res_rescale, int32_t clip, int32_t inverse, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SRDIFF_B200_H_ */

@@ -1,0 +1,280 @@
+"""TEST INFRASTRUCTURE ONLY -- CPU oracle (fp32) for SRDiff reverse-diffusion inference.
+
+A functional restatement of the reference's hot path, written against a flat
+``state_dict`` (the key contract of SURVEY Appendix C) instead of nn.Modules.
+Every function cites the reference lines (``/root/reference/srdiff/model.py``) it
+follows.  Arithmetic is delegated to PyTorch's CPU ATen ops -- exactly the
+third-party dependency the reference itself uses (unpinned there; torch 2.11.0
+here) -- so, on the same inputs, this oracle reproduces the reference to fp32
+round-off (pinned by ``tests/test_oracle.py`` against the live reference when
+``/root/reference`` is present, and against the committed fixtures in
+``tests/golden`` generated from it by ``oracle/make_golden.py``).
+
+Parity status: the reference ships no tests / golden vectors of its own for this
+path, so the pin is "outputs of the reference itself run here".
+"""
+import math
+
+import numpy as np
+import torch
+import torch.nn.functional as F
+
+
+# ----------------------------------------------------------------------------- basics
+def mish(x):
+    """`Mish.forward` :422-424 -- x * tanh(softplus(x)) (torch softplus threshold 20)."""
+    return x * torch.tanh(F.softplus(x))
+
+
+def _conv(sd, key, x, stride=1, padding=0):
+    return F.conv2d(x, sd[key + ".weight"], sd[key + ".bias"], stride=stride, padding=padding)
+
+
+def _rpad(x):
+    """`nn.ReflectionPad2d(1)` :444,450,498."""
+    return F.pad(x, (1, 1, 1, 1), mode="reflect")
+
+
+# ----------------------------------------------------------------------------- schedule (row G)
+def cosine_betas(timesteps, s=0.008):
+    """`cosine_beta_schedule` :898-908 (note linspace(0, steps, steps))."""
+    steps = timesteps + 1
+    x = np.linspace(0, steps, steps)
+    ac = np.cos(((x / steps) + s) / (1 + s) * np.pi * 0.5) ** 2
+    ac = ac / ac[0]
+    betas = 1 - (ac[1:] / ac[:-1])
+    return np.clip(betas, a_min=0, a_max=0.999)
+
+
+def _warmup(beta_start, beta_end, T, frac):
+    betas = beta_end * np.ones(T, dtype=np.float64)
+    w = int(T * frac)
+    betas[:w] = np.linspace(beta_start, beta_end, w, dtype=np.float64)
+    return betas
+
+
+def named_betas(T, kind="linear", beta_start=0.0001, beta_end=0.02):
+    """`get_beta_schedule` :879-895."""
+    if kind == "quad":
+        return np.linspace(beta_start ** 0.5, beta_end ** 0.5, T, dtype=np.float64) ** 2
+    if kind == "linear":
+        return np.linspace(beta_start, beta_end, T, dtype=np.float64)
+    if kind == "warmup10":
+        return _warmup(beta_start, beta_end, T, 0.1)
+    if kind == "warmup50":
+        return _warmup(beta_start, beta_end, T, 0.5)
+    if kind == "const":
+        return beta_end * np.ones(T, dtype=np.float64)
+    if kind == "jsd":
+        return 1.0 / np.linspace(T, 1, T, dtype=np.float64)
+    raise NotImplementedError(kind)
+
+
+def make_schedule(timesteps, hp):
+    """The 12 fp32 buffers of `GaussianDiffusion.__init__` :921-959 (float64 math -> fp32)."""
+    if hp["beta_schedule"] == "cosine":
+        betas = cosine_betas(timesteps, s=hp["beta_s"])
+    elif hp["beta_schedule"] == "linear":
+        betas = named_betas(timesteps, beta_end=hp["beta_end"])
+        if hp["res"]:
+            betas[-1] = 0.999
+    else:
+        raise NotImplementedError(hp["beta_schedule"])
+    alphas = 1.0 - betas
+    ac = np.cumprod(alphas, axis=0)
+    ac_prev = np.append(1.0, ac[:-1])
+    pv = betas * (1.0 - ac_prev) / (1.0 - ac)
+    f32 = lambda a: torch.tensor(a, dtype=torch.float32)
+    return {
+        "betas": f32(betas),
+        "alphas_cumprod": f32(ac),
+        "alphas_cumprod_prev": f32(ac_prev),
+        "sqrt_alphas_cumprod": f32(np.sqrt(ac)),
+        "sqrt_one_minus_alphas_cumprod": f32(np.sqrt(1.0 - ac)),
+        "log_one_minus_alphas_cumprod": f32(np.log(1.0 - ac)),
+        "sqrt_recip_alphas_cumprod": f32(np.sqrt(1.0 / ac)),
+        "sqrt_recipm1_alphas_cumprod": f32(np.sqrt(1.0 / ac - 1)),
+        "posterior_variance": f32(pv),
+        "posterior_log_variance_clipped": f32(np.log(np.maximum(pv, 1e-20))),
+        "posterior_mean_coef1": f32(betas * np.sqrt(ac_prev) / (1.0 - ac)),
+        "posterior_mean_coef2": f32((1.0 - ac_prev) * np.sqrt(alphas) / (1.0 - ac)),
+    }
+
+
+# ----------------------------------------------------------------------------- RRDB encoder (row R)
+def _rdb5c(sd, p, x):
+    """`ResidualDenseBlock_5C.forward` :684-690."""
+    lr = lambda v: F.leaky_relu(v, 0.2)
+    x1 = lr(_conv(sd, p + "conv1", x, padding=1))
+    x2 = lr(_conv(sd, p + "conv2", torch.cat((x, x1), 1), padding=1))
+    x3 = lr(_conv(sd, p + "conv3", torch.cat((x, x1, x2), 1), padding=1))
+    x4 = lr(_conv(sd, p + "conv4", torch.cat((x, x1, x2, x3), 1), padding=1))
+    x5 = _conv(sd, p + "conv5", torch.cat((x, x1, x2, x3, x4), 1), padding=1)
+    return x5 * 0.2 + x
+
+
+def rrdb_forward(sd, x, hp, prefix="rrdb."):
+    """`RRDBNet.forward(x, get_fea=True)` :727-749 -> (out, feas[nb+1])."""
+    nb = 0
+    while (prefix + "RRDB_trunk.%d.RDB1.conv1.weight" % nb) in sd:
+        nb += 1
+    lr = lambda v: F.leaky_relu(v, 0.2)
+    feas = []
+    x = (x + 1) / 2
+    fea_first = fea = _conv(sd, prefix + "conv_first", x, padding=1)
+    for i in range(nb):
+        p = prefix + "RRDB_trunk.%d." % i
+        out = _rdb5c(sd, p + "RDB1.", fea)
+        out = _rdb5c(sd, p + "RDB2.", out)
+        out = _rdb5c(sd, p + "RDB3.", out)
+        fea = out * 0.2 + fea                       # `RRDB.forward` :702-706
+        feas.append(fea)
+    trunk = _conv(sd, prefix + "trunk_conv", fea, padding=1)
+    fea = fea_first + trunk
+    feas.append(fea)
+    up = lambda v: F.interpolate(v, scale_factor=2, mode="nearest")
+    fea = lr(_conv(sd, prefix + "upconv1", up(fea), padding=1))
+    fea = lr(_conv(sd, prefix + "upconv2", up(fea), padding=1))
+    if hp["sr_scale"] == 8:
+        fea = lr(_conv(sd, prefix + "upconv3", up(fea), padding=1))
+    fea_hr = _conv(sd, prefix + "HRconv", fea, padding=1)
+    out = _conv(sd, prefix + "conv_last", lr(fea_hr), padding=1)
+    out = out.clamp(0, 1) * 2 - 1
+    return out, feas
+
+
+# ----------------------------------------------------------------------------- Unet denoiser (row U)
+def time_embedding(sd, time, dim, prefix="denoise_fn."):
+    """`SinusoidalPosEmb` :412-419 followed by `Unet.mlp` :764-768."""
+    half = dim // 2
+    e = math.log(10000) / (half - 1)
+    e = torch.exp(torch.arange(half) * -e)
+    e = time[:, None] * e[None, :]
+    e = torch.cat((e.sin(), e.cos()), dim=-1)
+    h = F.linear(e, sd[prefix + "mlp.0.weight"], sd[prefix + "mlp.0.bias"])
+    return F.linear(mish(h), sd[prefix + "mlp.2.weight"], sd[prefix + "mlp.2.bias"])
+
+
+def _block(sd, p, x):
+    """`Block` (groups == 0 branch) :442-447,456-457: reflect-pad, conv3x3, Mish."""
+    return mish(_conv(sd, p + "block.1", _rpad(x)))
+
+
+def _resnet(sd, p, x, temb):
+    """`ResnetBlock.forward` :473-480 (temb added AFTER block1's Mish)."""
+    h = _block(sd, p + "block1.", x)
+    h = h + F.linear(mish(temb), sd[p + "mlp.1.weight"], sd[p + "mlp.1.bias"])[:, :, None, None]
+    h = _block(sd, p + "block2.", h)
+    if (p + "res_conv.weight") in sd:
+        return h + _conv(sd, p + "res_conv", x)
+    return h + x
+
+
+def unet_forward(sd, x, time, cond_feas, hp, prefix="denoise_fn.", taps=None):
+    """`Unet.forward` :820-847.  `cond_feas` is the RRDB feature list; `taps`, if a dict,
+    receives intermediate activations (test instrumentation only)."""
+    dim = sd[prefix + "mlp.2.weight"].shape[0]
+    n_levels = 0
+    while (prefix + "downs.%d.0.block1.block.1.weight" % n_levels) in sd:
+        n_levels += 1
+    temb = time_embedding(sd, time.float(), dim, prefix)
+    s = hp["sr_scale"]
+    cond = F.conv_transpose2d(torch.cat(cond_feas[2::3], 1), sd[prefix + "cond_proj.weight"],
+                              sd[prefix + "cond_proj.bias"], stride=s, padding=s // 2)
+    hs = []
+    for i in range(n_levels):
+        p = prefix + "downs.%d." % i
+        x = _resnet(sd, p + "0.", x, temb)
+        x = _resnet(sd, p + "1.", x, temb)
+        if i == 0:
+            x = x + cond
+        hs.append(x)
+        if i < n_levels - 1:                         # `Downsample` :494-503
+            x = _conv(sd, p + "2.conv.1", _rpad(x), stride=2)
+        if taps is not None:
+            taps["down%d" % i] = x
+    x = _resnet(sd, prefix + "mid_block1.", x, temb)
+    x = _resnet(sd, prefix + "mid_block2.", x, temb)
+    if taps is not None:
+        taps["mid"] = x
+    for j in range(n_levels - 1):                    # three Upsamples, h[0] never popped (Q5)
+        p = prefix + "ups.%d." % j
+        x = torch.cat((x, hs.pop()), dim=1)
+        x = _resnet(sd, p + "0.", x, temb)
+        x = _resnet(sd, p + "1.", x, temb)
+        x = F.conv_transpose2d(x, sd[p + "2.conv.0.weight"], sd[p + "2.conv.0.bias"],
+                               stride=2, padding=1)  # `Upsample` :483-491
+        if taps is not None:
+            taps["up%d" % j] = x
+    x = _block(sd, prefix + "final_conv.0.", x)
+    return _conv(sd, prefix + "final_conv.1", x)
+
+
+# ----------------------------------------------------------------------------- sampler (rows P, S, F)
+def _ext(a, t, ndim):
+    """`extract` :860-863."""
+    return a.gather(-1, t).reshape(t.shape[0], *((1,) * (ndim - 1)))
+
+
+def p_sample_update(sched, x, t, eps, noise, clip_denoised=True):
+    """The arithmetic of `p_sample` :1054-1060 given eps = Unet(x, t):
+    `predict_start_from_noise` :968-972, clamp :986-987, `q_posterior` :974-981."""
+    nd = x.dim()
+    x0 = _ext(sched["sqrt_recip_alphas_cumprod"], t, nd) * x - \
+        _ext(sched["sqrt_recipm1_alphas_cumprod"], t, nd) * eps
+    if clip_denoised:
+        x0 = x0.clamp(-1.0, 1.0)
+    mean = _ext(sched["posterior_mean_coef1"], t, nd) * x0 + \
+        _ext(sched["posterior_mean_coef2"], t, nd) * x
+    logvar = _ext(sched["posterior_log_variance_clipped"], t, nd)
+    mask = (1 - (t == 0).float()).reshape(x.shape[0], *((1,) * (nd - 1)))
+    return mean + mask * (0.5 * logvar).exp() * noise, x0
+
+
+def res2img(img, img_lr_up, hp, clip_input=None):
+    """`res2img` :1118-1125."""
+    if clip_input is None:
+        clip_input = hp["clip_input"]
+    if hp["res"]:
+        if clip_input:
+            img = img.clamp(-1, 1)
+        img = img / hp["res_rescale"] + img_lr_up
+    return img
+
+
+def sample(sd, sched, hp, img_lr, img_lr_up, noises, record=None):
+    """`GaussianDiffusion.sample` :1062-1091 with caller-provided noise.
+
+    ``noises`` is [T+1, B, 3, H, W]: noises[0] is x_T (the `torch.randn(shape)` at :1070),
+    noises[1 + k] the k-th per-step draw (step t = T-1-k; the t == 0 draw is multiplied by 0).
+    ``record`` (a dict) receives per-step eps and x lists.  Returns (img, rrdb_out).
+    """
+    T = sched["betas"].shape[0]
+    b = img_lr.shape[0]
+    x = noises[0].clone()
+    if hp["use_rrdb"]:
+        rrdb_out, cond = rrdb_forward(sd, img_lr, hp)
+    else:
+        raise NotImplementedError("use_rrdb=False is outside the hot path")
+    for k, i in enumerate(reversed(range(T))):
+        t = torch.full((b,), i, dtype=torch.long)
+        eps = unet_forward(sd, x, t, cond, hp)
+        x, x0 = p_sample_update(sched, x, t, eps, noises[1 + k])
+        if record is not None:
+            record.setdefault("eps", []).append(eps)
+            record.setdefault("x", []).append(x)
+            record.setdefault("x0", []).append(x0)
+    return res2img(x, img_lr_up, hp), rrdb_out
+
+
+# ----------------------------------------------------------------------------- helpers for tests / bench
+def rel_l2(a, b):
+    a = a.double().flatten()
+    b = b.double().flatten()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def psnr(a, b, peak=2.0):
+    """PSNR for images in [-1, 1] (peak-to-peak 2)."""
+    mse = float(((a.double() - b.double()) ** 2).mean())
+    return float("inf") if mse == 0 else 10.0 * math.log10(peak * peak / mse)
