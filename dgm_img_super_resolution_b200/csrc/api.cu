@@ -1,5 +1,6 @@
 // extern "C" boundary of libsrdiff_b200.so: error reporting and convolution plans.
 #include <string.h>
+#include <stddef.h>
 #include <cuda.h>
 #include <new>
 #include "epilogue.cuh"
@@ -88,6 +89,16 @@ extern "C" {
 const char* srd_last_error(void) { return g_err; }
 
 int srd_version(void) { return 100; }
+
+int srd_abi_sizeof(int32_t which) {
+  switch (which) {
+    case 0: return (int)sizeof(SrdConvDesc);
+    case 1: return (int)sizeof(SrdPSampleArgs);
+    case 2: return (int)offsetof(SrdConvDesc, head_b);
+    case 3: return (int)offsetof(SrdPSampleArgs, act_dtype);
+    default: return -1;
+  }
+}
 
 int srd_conv_tc_supported(const SrdConvDesc* desc) {
   if (!desc) return 0;

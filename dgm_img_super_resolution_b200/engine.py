@@ -1,0 +1,659 @@
+"""Host-side engine: weight repacking, activation arena, layer programs and CUDA-graph capture.
+
+PyTorch is used here only for device memory (torch.empty/zeros), streams, CUDA-graph capture
+and one-time weight re-layout; every per-image / per-step FLOP runs in libsrdiff_b200.so
+(see include/srdiff_b200.h).  Reference line numbers refer to /root/reference/srdiff/model.py.
+"""
+import ctypes as C
+import math
+
+import torch
+
+from . import _lib as L
+
+PRECISIONS = ("bf16", "fp32", "bf16_direct")
+
+
+def _ceil(a, b):
+    return (a + b - 1) // b
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _require_cuda(t, what):
+    if not t.is_cuda:
+        raise L.SrdError(
+            "%s is on '%s': dgm_img_super_resolution_b200 runs only on CUDA (sm_100a); there is no CPU "
+            "fallback. Move the module and its inputs to the GPU." % (what, t.device))
+
+
+class Precision:
+    def __init__(self, name):
+        if name not in PRECISIONS:
+            raise ValueError("precision must be one of %s" % (PRECISIONS,))
+        self.name = name
+        self.dtype = L.F32 if name == "fp32" else L.BF16
+        self.torch_dtype = torch.float32 if name == "fp32" else torch.bfloat16
+        self.kernel = L.KERNEL_AUTO if name == "bf16" else L.KERNEL_DIRECT
+
+
+# --------------------------------------------------------------------------------------------
+# activations: padded NHWC
+# --------------------------------------------------------------------------------------------
+class Act:
+    """[B][H+2][W+2][ct] buffer; ring zero-initialised (consumers that need zero padding rely on it)."""
+
+    def __init__(self, B, H, W, ct, prec, device):
+        self.B, self.H, self.W, self.ct = B, H, W, ct
+        self.t = torch.zeros((B, H + 2, W + 2, ct), dtype=prec.torch_dtype, device=device)
+
+    @property
+    def ptr(self):
+        return self.t.data_ptr()
+
+
+# --------------------------------------------------------------------------------------------
+# weight packing (one-time re-layout; see include/srdiff_b200.h for the layouts)
+# --------------------------------------------------------------------------------------------
+def _pack_conv(weight, src_cins, stride):
+    """nn.Conv2d weight [O][I][kh][kw] -> (w_direct fp32 [1][K][O], w_tc bf16 [KB][Npad][64])."""
+    O, I, kh, kw = weight.shape
+    assert sum(src_cins) == I, (src_cins, I)
+    npad = _ceil(O, 16) * 16
+    w = weight.detach().float()
+    parts, blocks, a = [], [], 0
+    ky_order = [0, 2, 1] if stride == 2 else list(range(kh))
+    for cin in src_cins:
+        ws = w[:, a:a + cin]
+        parts.append(ws.permute(2, 3, 1, 0).reshape(kh * kw * cin, O))
+        nch = _ceil(cin, 64)
+        blk = torch.zeros((nch, kw, len(ky_order), npad, 64), dtype=torch.float32, device=w.device)
+        for ch in range(nch):
+            c0, c1 = ch * 64, min(cin, ch * 64 + 64)
+            for kx in range(kw):
+                for j, ky in enumerate(ky_order):
+                    blk[ch, kx, j, :O, :c1 - c0] = ws[:, c0:c1, ky, kx]
+        blocks.append(blk.reshape(-1, npad, 64))
+        a += cin
+    w_direct = torch.cat(parts, 0).contiguous()[None].contiguous()
+    w_tc = torch.cat(blocks, 0).to(torch.bfloat16).contiguous()
+    return w_direct, w_tc
+
+
+def _pack_convT(weight, src_cins, S):
+    """nn.ConvTranspose2d(k=2S, stride=S, pad=S/2) weight [I][O][2S][2S] -> per sub-pixel phase
+    (r, s) a 2x2-tap conv: out[y*S+r] += in[y+dy] * w[ky], ky = r + S/2 - dy*S (dy in {-1,0} for
+    r < S/2, {0,1} otherwise).  SURVEY 7.4 tap tables."""
+    I, O, k, _ = weight.shape
+    assert k == 2 * S and sum(src_cins) == I
+    npad = _ceil(O, 16) * 16
+    w = weight.detach().float()
+    directs, tcs = [], []
+    for r in range(S):
+        ky0 = 1 if r >= S // 2 else 0
+        kys = [r + S // 2 - (ky0 + d - 1) * S for d in range(2)]
+        for s in range(S):
+            kx0 = 1 if s >= S // 2 else 0
+            kxs = [s + S // 2 - (kx0 + d - 1) * S for d in range(2)]
+            parts, blocks, a = [], [], 0
+            for cin in src_cins:
+                ws = w[a:a + cin]                                 # [cin][O][k][k]
+                for dy in range(2):
+                    for dx in range(2):
+                        parts.append(ws[:, :, kys[dy], kxs[dx]])   # [cin][O]
+                nch = _ceil(cin, 64)
+                blk = torch.zeros((nch, 2, 2, npad, 64), dtype=torch.float32, device=w.device)
+                for ch in range(nch):
+                    c0, c1 = ch * 64, min(cin, ch * 64 + 64)
+                    for dx in range(2):
+                        for dy in range(2):
+                            blk[ch, dx, dy, :O, :c1 - c0] = ws[c0:c1, :, kys[dy], kxs[dx]].t()
+                blocks.append(blk.reshape(-1, npad, 64))
+                a += cin
+            directs.append(torch.cat(parts, 0))
+            tcs.append(torch.cat(blocks, 0))
+    w_direct = torch.stack(directs).contiguous()
+    w_tc = torch.stack(tcs).to(torch.bfloat16).contiguous()
+    return w_direct, w_tc
+
+
+class PackedConv:
+    """Caches the packed forms of one conv layer's parameters, keyed by parameter identity/version."""
+
+    def __init__(self, weight, bias, transposed=False, stride=1):
+        self.weight, self.bias_p = weight, bias
+        self.transposed, self.stride = transposed, stride
+        self._cache = {}
+
+    @property
+    def N(self):
+        return self.weight.shape[1] if self.transposed else self.weight.shape[0]
+
+    @property
+    def ksize(self):
+        return self.weight.shape[2]
+
+    def get(self, src_cins):
+        key = (tuple(src_cins), self.weight.data_ptr(), self.weight._version,
+               self.bias_p.data_ptr(), self.bias_p._version)
+        hit = self._cache.get("k")
+        if hit is None or hit[0] != key:
+            if self.transposed:
+                wd, wt = _pack_convT(self.weight, src_cins, self.ksize // 2)
+            else:
+                wd, wt = _pack_conv(self.weight, src_cins, self.stride)
+            b = self.bias_p.detach().float().contiguous()
+            self._cache["k"] = (key, wd, wt, b)
+            hit = self._cache["k"]
+        return hit[1], hit[2], hit[3]
+
+
+# --------------------------------------------------------------------------------------------
+# ops
+# --------------------------------------------------------------------------------------------
+class ConvOp:
+    def __init__(self, desc, keep, temb_off=None):
+        self.desc, self.keep, self.temb_off = desc, keep, temb_off
+        h = C.c_void_p()
+        L.check(L.lib().srd_conv_plan_create(C.byref(desc), C.byref(h)), "srd_conv_plan_create")
+        self.handle = h
+        self.kernel = L.lib().srd_conv_plan_kernel(h)
+
+    def run(self, ctx):
+        temb = None
+        if self.temb_off is not None:
+            temb = C.c_void_p(ctx.temb_ptr + 4 * self.temb_off)
+        L.check(L.lib().srd_conv_run(self.handle, temb, _stream()), "srd_conv_run")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.lib().srd_conv_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class FnOp:
+    def __init__(self, fn, keep=()):
+        self.fn, self.keep = fn, keep
+
+    def run(self, ctx):
+        self.fn(ctx)
+
+
+class RunCtx:
+    """Per-launch dynamic state: the address of the time-embedding row(s) for this step."""
+
+    def __init__(self, temb_ptr=0):
+        self.temb_ptr = temb_ptr
+
+
+class Builder:
+    """Accumulates an ordered list of kernel launches over a set of activation buffers."""
+
+    def __init__(self, device, precision):
+        self.device = device
+        self.prec = precision if isinstance(precision, Precision) else Precision(precision)
+        self.ops = []
+
+    def act(self, B, H, W, C_, ct=None):
+        ct = _ceil(C_ if ct is None else ct, 8) * 8
+        return Act(B, H, W, ct, self.prec, self.device)
+
+    def run(self, ctx=None):
+        ctx = ctx or RunCtx()
+        for op in self.ops:
+            op.run(ctx)
+
+    def count_kernels(self):
+        n_tc = sum(1 for o in self.ops if isinstance(o, ConvOp) and o.kernel == L.KERNEL_TC)
+        return len(self.ops), n_tc
+
+    # ---- generic conv ----------------------------------------------------------------------
+    def conv(self, pw, srcs, out=None, out_coff=0, out2=None, out2_coff=0, act=L.ACT_NONE, alpha=1.0,
+             temb_off=None, temb_bstride=0, res1=None, res2=None, border=L.BORDER_KEEP, planar=None,
+             planar_c=0, planar_clamp01=0, head=None, kernel=None):
+        """srcs: list of (Act, c_off, cin); res1/res2: (Act, c_off, beta); head: (w[planar_c][N], b)."""
+        d = L.SrdConvDesc()
+        d.dtype = self.prec.dtype
+        d.kernel = self.prec.kernel if kernel is None else kernel
+        a0 = srcs[0][0]
+        d.n_src = len(srcs)
+        d.B, d.H_in, d.W_in = a0.B, a0.H, a0.W
+        for i, (a, coff, cin) in enumerate(srcs):
+            assert (a.B, a.H, a.W) == (a0.B, a0.H, a0.W), "conv sources must share B/H/W"
+            d.src[i].ptr, d.src[i].ct, d.src[i].c_off, d.src[i].cin = a.ptr, a.ct, coff, cin
+        wd, wt, bias = pw.get([s[2] for s in srcs])
+        if pw.transposed:
+            S = pw.ksize // 2
+            d.stride, d.nky, d.nkx, d.ky0, d.kx0, d.up = 1, 2, 2, 0, 0, S
+        else:
+            k = pw.ksize
+            d.stride, d.nky, d.nkx, d.up = pw.stride, k, k, 1
+            d.ky0 = d.kx0 = (3 - k) // 2
+        d.N = pw.N
+        d.w_direct, d.w_tc, d.bias = wd.data_ptr(), wt.data_ptr(), bias.data_ptr()
+        d.act, d.alpha = act, alpha
+        d.temb, d.temb_bstride = None, temb_bstride
+        keep = [wd, wt, bias, [s[0] for s in srcs], out, out2, planar]
+        if res1 is not None:
+            d.res1, d.res1_ct, d.res1_coff, d.beta1 = res1[0].ptr, res1[0].ct, res1[1], res1[2]
+            keep.append(res1[0])
+        if res2 is not None:
+            d.res2, d.res2_ct, d.res2_coff, d.beta2 = res2[0].ptr, res2[0].ct, res2[1], res2[2]
+            keep.append(res2[0])
+        d.H_out, d.W_out = a0.H * d.up // d.stride, a0.W * d.up // d.stride
+        for o in (out, out2):
+            if o is not None:
+                assert (o.B, o.H, o.W) == (a0.B, d.H_out, d.W_out), "conv output buffer has the wrong shape"
+        if out is not None:
+            d.out, d.out_ct, d.out_coff = out.ptr, out.ct, out_coff
+        if out2 is not None:
+            d.out2, d.out2_ct, d.out2_coff = out2.ptr, out2.ct, out2_coff
+        d.border = border
+        if planar is not None:
+            d.planar, d.planar_c, d.planar_clamp01 = planar.data_ptr(), planar_c, planar_clamp01
+        if head is not None:
+            d.head_w, d.head_b = head[0].data_ptr(), head[1].data_ptr()
+            keep.append(head)
+        op = ConvOp(d, keep, temb_off)
+        self.ops.append(op)
+        return op
+
+    # ---- converters ------------------------------------------------------------------------
+    def nchw_to_act(self, x_fn, act_buf, C_, scale=1.0, shift=0.0, border=L.BORDER_KEEP):
+        """x_fn() -> fp32 NCHW tensor (resolved at run time so static buffers can be swapped)."""
+        def f(ctx):
+            x = x_fn()
+            L.check(L.lib().srd_nchw_to_act(x.data_ptr(), act_buf.B, C_, act_buf.H, act_buf.W, scale, shift,
+                                            act_buf.ptr, act_buf.ct, self.prec.dtype, border, _stream()),
+                    "srd_nchw_to_act")
+        self.ops.append(FnOp(f, (act_buf,)))
+
+    def act_to_nchw(self, act_buf, c_off, C_, out):
+        def f(ctx):
+            L.check(L.lib().srd_act_to_nchw(act_buf.ptr, act_buf.ct, c_off, self.prec.dtype, act_buf.B, C_,
+                                            act_buf.H, act_buf.W, out.data_ptr(), _stream()), "srd_act_to_nchw")
+        self.ops.append(FnOp(f, (act_buf, out)))
+
+    def upsample2x(self, src, dst):
+        def f(ctx):
+            L.check(L.lib().srd_upsample_nearest2x(src.ptr, dst.ptr, self.prec.dtype, src.B, src.H, src.W,
+                                                   src.ct, _stream()), "srd_upsample_nearest2x")
+        assert src.ct == dst.ct
+        self.ops.append(FnOp(f, (src, dst)))
+
+
+# --------------------------------------------------------------------------------------------
+# layer programs (mirror the reference's module graph; see model.py for the modules)
+# --------------------------------------------------------------------------------------------
+def _pc(module, attr="_srd_pack", **kw):
+    """PackedConv attached to an nn.Conv2d / nn.ConvTranspose2d (cached on the module)."""
+    p = module.__dict__.get(attr)
+    if p is None or p.weight is not module.weight or p.bias_p is not module.bias:
+        transposed = isinstance(module, torch.nn.ConvTranspose2d)
+        stride = 1 if transposed else module.stride[0]
+        p = PackedConv(module.weight, module.bias, transposed=transposed, stride=stride)
+        module.__dict__[attr] = p
+    return p
+
+
+def build_resnet(bld, blk, srcs, dim_out, out, border, temb_off, temb_bstride=0, extra_res=None):
+    """ResnetBlock.forward :473-480.  srcs = K sources of the block input x (a list => fused concat).
+    Returns `out` (Act with dim_out channels).  extra_res: (Act, c_off, beta) added at the tail
+    (`x + cond` :830)."""
+    a0 = srcs[0][0]
+    B, H, W = a0.B, a0.H, a0.W
+    cin = sum(s[2] for s in srcs)
+    h1 = bld.act(B, H, W, dim_out)
+    use_temb = temb_off is not None
+    bld.conv(_pc(blk.block1.block[1]), srcs, out=h1, act=L.ACT_MISH, temb_off=temb_off,
+             temb_bstride=temb_bstride if use_temb else 0, border=L.BORDER_REFLECT)
+    if cin != dim_out:
+        r = bld.act(B, H, W, dim_out)
+        bld.conv(_pc(blk.res_conv), srcs, out=r, act=L.ACT_NONE, border=L.BORDER_KEEP)
+        res1 = (r, 0, 1.0)
+    else:
+        assert len(srcs) == 1
+        res1 = (srcs[0][0], srcs[0][1], 1.0)
+    bld.conv(_pc(blk.block2.block[1]), [(h1, 0, dim_out)], out=out, act=L.ACT_MISH, res1=res1,
+             res2=extra_res, border=border)
+    return out
+
+
+class UnetProgram:
+    """Unet.forward :820-847 for fixed (B, H, W) as a static launch list.
+
+    Inputs: `xin` (padded NHWC copy of x_t, 3 real channels, reflect ring) and `cond`
+    (cond_proj output, 64 channels).  Output: `eps` fp32 NCHW.  The time embedding comes from a
+    precomputed table row addressed through RunCtx.temb_ptr.
+    """
+
+    def __init__(self, unet, B, H, W, precision, device, cond_act=None, per_sample_temb=False):
+        from . import model as M
+        hp = M.hparams
+        bld = self.bld = Builder(device, precision)
+        self.B, self.H, self.W = B, H, W
+        dims = unet._dims
+        nlev = len(dims) - 1
+        if H % (2 ** (nlev - 1)) or W % (2 ** (nlev - 1)):
+            raise ValueError("Unet input %dx%d must be divisible by %d" % (H, W, 2 ** (nlev - 1)))
+        self.xin = bld.act(B, H, W, 3)
+        self.cond = cond_act if cond_act is not None else bld.act(B, H, W, dims[1])
+        self.eps = torch.empty((B, unet._out_dim, H, W), dtype=torch.float32, device=device)
+        # time-table offsets, in the order of unet.resnet_blocks()
+        offs, o = {}, 0
+        for blk in unet.resnet_blocks():
+            offs[id(blk)] = o
+            o += blk._dim_out
+        self.temb_S = o
+        temb_bstride = o if per_sample_temb else 0        # 0: one table row shared by the whole batch
+        RB, RK = L.BORDER_REFLECT, L.BORDER_KEEP
+        x_src = [(self.xin, 0, dims[0])]
+        hs = []
+        h, w = H, W
+        for i in range(nlev):
+            r0, r1, down = unet.downs[i]
+            d = dims[i + 1]
+            x1 = bld.act(B, h, w, d)
+            build_resnet(bld, r0, x_src, d, x1, RB, offs[id(r0)], temb_bstride)
+            x2 = bld.act(B, h, w, d)
+            extra = (self.cond, 0, 1.0) if i == 0 else None          # `x = x + cond` :830
+            build_resnet(bld, r1, [(x1, 0, d)], d, x2, RB, offs[id(r1)], temb_bstride, extra_res=extra)
+            if i == 0 and hp["res"] and hp["up_input"]:
+                raise NotImplementedError("hparams['up_input']=True is outside the hot path (SURVEY 8f-3)")
+            hs.append((x2, d))
+            if i < nlev - 1:
+                xd = bld.act(B, h // 2, w // 2, d)
+                bld.conv(_pc(down.conv[1]), [(x2, 0, d)], out=xd, act=L.ACT_NONE, border=RB)   # :494-503
+                x_src = [(xd, 0, d)]
+                h, w = h // 2, w // 2
+            else:
+                x_src = [(x2, 0, d)]
+        d = dims[-1]
+        m1 = bld.act(B, h, w, d)
+        build_resnet(bld, unet.mid_block1, x_src, d, m1, RB, offs[id(unet.mid_block1)], temb_bstride)
+        if hp["use_attn"]:
+            raise NotImplementedError("hparams['use_attn']=True is outside the hot path (SURVEY 2 #11)")
+        m2 = bld.act(B, h, w, d)
+        build_resnet(bld, unet.mid_block2, [(m1, 0, d)], d, m2, RB, offs[id(unet.mid_block2)], temb_bstride)
+        x, xd_ = m2, d
+        for j in range(nlev - 1):
+            r0, r1, up = unet.ups[j]
+            skip, sd = hs.pop()
+            dout = dims[nlev - 1 - j]
+            u1 = bld.act(B, h, w, dout)
+            build_resnet(bld, r0, [(x, 0, xd_), (skip, 0, sd)], dout, u1, RB, offs[id(r0)], temb_bstride)   # cat :842
+            u2 = bld.act(B, h, w, dout)
+            build_resnet(bld, r1, [(u1, 0, dout)], dout, u2, RK, offs[id(r1)], temb_bstride)   # feeds convT: zero ring
+            h, w = h * 2, w * 2
+            u3 = bld.act(B, h, w, dout)
+            bld.conv(_pc(up.conv[0]), [(u2, 0, dout)], out=u3, act=L.ACT_NONE, border=RB)   # Upsample :483-491
+            x, xd_ = u3, dout
+        fc0, fc1 = unet.final_conv[0].block[1], unet.final_conv[1]
+        od = unet._out_dim
+        if bld.prec.name == "bf16" and od <= 4:
+            hw = fc1.weight.detach().float().reshape(od, xd_).contiguous()
+            hb = fc1.bias.detach().float().contiguous()
+            bld.conv(_pc(fc0), [(x, 0, xd_)], out=None, act=L.ACT_MISH, planar=self.eps, planar_c=od,
+                     head=(hw, hb))
+        else:
+            f = bld.act(B, h, w, xd_)
+            bld.conv(_pc(fc0), [(x, 0, xd_)], out=f, act=L.ACT_MISH, border=RK)
+            bld.conv(_pc(fc1), [(f, 0, xd_)], planar=self.eps, planar_c=od)
+
+    def run(self, temb_ptr):
+        self.bld.run(RunCtx(temb_ptr))
+
+
+class RRDBProgram:
+    """RRDBNet.forward(x, get_fea=True) :727-749 for fixed (B, h, w)."""
+
+    def __init__(self, rrdb, B, h, w, precision, device, want_all_feas=True):
+        from . import model as M
+        hp = M.hparams
+        bld = self.bld = Builder(device, precision)
+        nf, gc, nb = rrdb._nf, rrdb._gc, len(rrdb.RRDB_trunk)
+        self.nf, self.nb, self.B, self.h, self.w = nf, nb, B, h, w
+        K, LR = L.BORDER_KEEP, L.ACT_LRELU02
+        self.xin = bld.act(B, h, w, rrdb._in_nc)
+        ctot = nf + 4 * gc
+        cats = [bld.act(B, h, w, ctot) for _ in range(2)]
+        self.fea_first = bld.act(B, h, w, nf)
+        self.feas = [bld.act(B, h, w, nf) for _ in range(nb + 1)]
+        # conv_first :730 (input already (x+1)/2, done by the converter)
+        bld.conv(_pc(rrdb.conv_first), [(self.xin, 0, rrdb._in_nc)], out=cats[0], out2=self.fea_first, border=K)
+        cur = 0
+        for i, blk in enumerate(rrdb.RRDB_trunk):
+            x_rrdb = self.fea_first if i == 0 else self.feas[i - 1]
+            for j, rdb in enumerate((blk.RDB1, blk.RDB2, blk.RDB3)):
+                c, n = cats[cur], cats[cur ^ 1]
+                for k, conv in enumerate((rdb.conv1, rdb.conv2, rdb.conv3, rdb.conv4)):     # :685-688
+                    bld.conv(_pc(conv), [(c, 0, nf + k * gc)], out=c, out_coff=nf + k * gc, act=LR, border=K)
+                if j < 2:       # x5*0.2 + x :690
+                    bld.conv(_pc(rdb.conv5), [(c, 0, ctot)], out=n, alpha=0.2, res1=(c, 0, 1.0), border=K)
+                else:           # (x5*0.2 + x)*0.2 + x_rrdb :690,706
+                    bld.conv(_pc(rdb.conv5), [(c, 0, ctot)], out=n, out2=self.feas[i], alpha=0.04,
+                             res1=(c, 0, 0.2), res2=(x_rrdb, 0, 1.0), border=K)
+                cur ^= 1
+        # trunk_conv + fea_first :734-736
+        bld.conv(_pc(rrdb.trunk_conv), [(cats[cur], 0, nf)], out=self.feas[nb], res1=(self.fea_first, 0, 1.0),
+                 border=K)
+        # HR head :738-745
+        self.out = torch.empty((B, rrdb._out_nc, h * hp["sr_scale"], w * hp["sr_scale"]), dtype=torch.float32,
+                               device=device)
+        fea, hh, ww = self.feas[nb], h, w
+        ups = [rrdb.upconv1, rrdb.upconv2] + ([rrdb.upconv3] if hp["sr_scale"] == 8 else [])
+        for conv in ups:
+            u = bld.act(B, hh * 2, ww * 2, nf)
+            bld.upsample2x(fea, u)
+            hh, ww = hh * 2, ww * 2
+            v = bld.act(B, hh, ww, nf)
+            bld.conv(_pc(conv), [(u, 0, nf)], out=v, act=LR, border=K)
+            fea = v
+        hr = bld.act(B, hh, ww, nf)
+        bld.conv(_pc(rrdb.HRconv), [(fea, 0, nf)], out=hr, act=LR, border=K)      # lrelu(fea_hr) :743
+        bld.conv(_pc(rrdb.conv_last), [(hr, 0, nf)], planar=self.out, planar_c=rrdb._out_nc, planar_clamp01=1)
+
+    def load_input(self, img_lr):
+        L.check(L.lib().srd_nchw_to_act(img_lr.data_ptr(), self.B, img_lr.shape[1], self.h, self.w, 0.5, 0.5,
+                                        self.xin.ptr, self.xin.ct, self.bld.prec.dtype, L.BORDER_KEEP,
+                                        _stream()), "srd_nchw_to_act")   # (x+1)/2 :729
+
+    def run(self):
+        self.bld.run()
+
+    def feas_nchw(self):
+        outs = []
+        for a in self.feas:
+            o = torch.empty((self.B, self.nf, self.h, self.w), dtype=torch.float32, device=a.t.device)
+            L.check(L.lib().srd_act_to_nchw(a.ptr, a.ct, 0, self.bld.prec.dtype, self.B, self.nf, self.h, self.w,
+                                            o.data_ptr(), _stream()), "srd_act_to_nchw")
+            outs.append(o)
+        return outs
+
+
+class CondProgram:
+    """cond = cond_proj(cat(cond[2::3], 1)) :825 -- ConvTranspose2d(3*cond_dim, dim, 2S, S, S/2),
+    time-invariant, so computed once per image."""
+
+    def __init__(self, unet, fea_acts, precision, device):
+        bld = self.bld = Builder(device, precision)
+        sel = fea_acts[2::3]
+        a0 = sel[0]
+        S = unet.cond_proj.stride[0]
+        cin_total = unet.cond_proj.weight.shape[0]
+        cins = [unet._cond_dim] * len(sel)
+        if sum(cins) != cin_total:
+            raise RuntimeError(
+                "cond_proj expects %d input channels but the RRDB features provide %d (%d maps of %d): "
+                "cond_dim / rrdb_num_feat / rrdb_num_block mismatch" % (cin_total, sum(cins), len(sel), cins[0]))
+        self.cond = bld.act(a0.B, a0.H * S, a0.W * S, unet._dims[1])
+        bld.conv(_pc(unet.cond_proj), [(a, 0, c) for a, c in zip(sel, cins)], out=self.cond, border=L.BORDER_KEEP)
+
+    def run(self):
+        self.bld.run()
+
+
+# --------------------------------------------------------------------------------------------
+# time table
+# --------------------------------------------------------------------------------------------
+def time_table(unet, t_values):
+    """[n_t][S] fp32 table of every ResnetBlock's `mlp(time_emb)` :821-822,:476 for the given t's."""
+    dev = unet.mlp[0].weight.device
+    dim = unet._dim
+    half = dim // 2
+    e = math.log(10000) / (half - 1)
+    freqs = torch.exp(torch.arange(half) * -e).to(dev).float().contiguous()     # :415-416 (CPU, then moved)
+    blocks = unet.resnet_blocks()
+    w_blk = torch.cat([b.mlp[1].weight.detach().float() for b in blocks], 0).contiguous()
+    b_blk = torch.cat([b.mlp[1].bias.detach().float() for b in blocks], 0).contiguous()
+    S = w_blk.shape[0]
+    t_values = t_values.to(dev).float().contiguous()
+    out = torch.empty((t_values.numel(), S), dtype=torch.float32, device=dev)
+    w0, b0 = unet.mlp[0].weight.detach().float().contiguous(), unet.mlp[0].bias.detach().float().contiguous()
+    w2, b2 = unet.mlp[2].weight.detach().float().contiguous(), unet.mlp[2].bias.detach().float().contiguous()
+    L.check(L.lib().srd_time_table(t_values.data_ptr(), t_values.numel(), dim, freqs.data_ptr(), w0.data_ptr(),
+                                   b0.data_ptr(), w2.data_ptr(), b2.data_ptr(), w_blk.data_ptr(), b_blk.data_ptr(),
+                                   S, out.data_ptr(), _stream()), "srd_time_table")
+    return out
+
+
+def params_signature(module):
+    return tuple((p.data_ptr(), p._version) for p in module.parameters())
+
+
+# --------------------------------------------------------------------------------------------
+# sampler plan: GaussianDiffusion.sample :1062-1091 as (optionally) ONE CUDA graph
+# --------------------------------------------------------------------------------------------
+COEF_NAMES = ("sqrt_recip_alphas_cumprod", "sqrt_recipm1_alphas_cumprod", "posterior_mean_coef1",
+              "posterior_mean_coef2", "posterior_log_variance_clipped")
+
+
+def coef_table(diffusion):
+    """[T][5] fp32 rows consumed by srd_p_sample_step (the six `extract` gathers of :968-981)."""
+    return torch.stack([getattr(diffusion, n).detach().float() for n in COEF_NAMES], 1).contiguous()
+
+
+def p_sample_step(x, eps, noise, coef, t_i32, x_out, clip_denoised=True, seed=0, step=0, image_offset=0,
+                  x0_out=None, img_out=None, img_lr_up=None, res_rescale=1.0, clip_input=True, nhwc_out=None,
+                  act_dtype=L.BF16):
+    a = L.SrdPSampleArgs()
+    B, C_, H, W = x.shape
+    a.x, a.eps, a.noise = x.data_ptr(), eps.data_ptr(), (noise.data_ptr() if noise is not None else None)
+    a.coef, a.t = coef.data_ptr(), t_i32.data_ptr()
+    a.B, a.C, a.H, a.W = B, C_, H, W
+    a.clip_denoised = 1 if clip_denoised else 0
+    a.seed, a.step, a.image_offset = seed, step, image_offset
+    a.x_out = x_out.data_ptr()
+    a.x0_out = x0_out.data_ptr() if x0_out is not None else None
+    if img_out is not None:
+        a.img_out, a.img_lr_up = img_out.data_ptr(), img_lr_up.data_ptr()
+    a.res_rescale, a.clip_input = res_rescale, 1 if clip_input else 0
+    if nhwc_out is not None:
+        a.nhwc_out, a.nhwc_ct = nhwc_out.ptr, nhwc_out.ct
+    a.act_dtype = act_dtype
+    L.check(L.lib().srd_p_sample_step(C.byref(a), _stream()), "srd_p_sample_step")
+
+
+class SamplerPlan:
+    """Everything `sample()` needs for one (B, h, w, T, precision): static buffers, the RRDB /
+    cond_proj / Unet launch lists, the time and coefficient tables, and the captured graph."""
+
+    def __init__(self, diffusion, B, h, w, precision, device):
+        from . import model as M
+        hp = M.hparams
+        self.prec = Precision(precision)
+        self.B, self.h, self.w = B, h, w
+        s = hp["sr_scale"]
+        self.H, self.W = h * s, w * s
+        self.T = diffusion.num_timesteps
+        unet, rrdb = diffusion.denoise_fn, diffusion.rrdb
+        self.rrdb_prog = RRDBProgram(rrdb, B, h, w, self.prec, device)
+        self.cond_prog = CondProgram(unet, self.rrdb_prog.feas, self.prec, device)
+        self.unet_prog = UnetProgram(unet, B, self.H, self.W, self.prec, device, cond_act=self.cond_prog.cond)
+        C_ = unet._out_dim
+        f32 = dict(dtype=torch.float32, device=device)
+        self.x = torch.empty((B, C_, self.H, self.W), **f32)
+        self.img_lr = torch.empty((B, rrdb._in_nc, h, w), **f32)
+        self.img_lr_up = torch.empty((B, C_, self.H, self.W), **f32)
+        self.img = torch.empty((B, C_, self.H, self.W), **f32)
+        self.coef = coef_table(diffusion)
+        self.t_idx = torch.arange(self.T, dtype=torch.int32, device=device)[:, None].repeat(1, B).contiguous()
+        self.temb = time_table(unet, torch.arange(self.T, dtype=torch.float32))
+        self.res_rescale = float(hp["res_rescale"])
+        self.clip_input = bool(hp["clip_input"])
+        self.noise_buf = None
+        self.graphs = {}
+        self.sig = (params_signature(diffusion), self.T, hp["res_rescale"], hp["clip_input"])
+
+    # ---- pieces -----------------------------------------------------------------------------
+    def encode(self):
+        """RRDB encoder + cond_proj: once per image (cached across all T steps)."""
+        self.rrdb_prog.load_input(self.img_lr)
+        self.rrdb_prog.run()
+        self.cond_prog.run()
+
+    def load_x(self):
+        L.check(L.lib().srd_nchw_to_act(self.x.data_ptr(), self.B, self.x.shape[1], self.H, self.W, 1.0, 0.0,
+                                        self.unet_prog.xin.ptr, self.unet_prog.xin.ct, self.prec.dtype,
+                                        L.BORDER_REFLECT, _stream()), "srd_nchw_to_act")
+
+    def step(self, i, k, noise, seed, image_offset, x0_out=None, fuse_img=True):
+        """One p_sample :1051-1060 at timestep i (k-th step of the loop)."""
+        self.unet_prog.run(self.temb.data_ptr() + 4 * i * self.temb.shape[1])
+        last = (i == 0)
+        p_sample_step(self.x, self.unet_prog.eps, noise, self.coef, self.t_idx[i], self.x, True, seed, k + 1,
+                      image_offset, x0_out=x0_out,
+                      img_out=self.img if (last and fuse_img) else None, img_lr_up=self.img_lr_up,
+                      res_rescale=self.res_rescale, clip_input=self.clip_input,
+                      nhwc_out=None if last else self.unet_prog.xin, act_dtype=self.prec.dtype)
+
+    def loop(self, noises, seed, image_offset):
+        self.load_x()
+        for k, i in enumerate(reversed(range(self.T))):
+            self.step(i, k, None if noises is None else noises[k], seed, image_offset)
+
+    def ensure_noise_buf(self):
+        if self.noise_buf is None:
+            self.noise_buf = torch.empty((self.T,) + tuple(self.x.shape), dtype=torch.float32, device=self.x.device)
+        return self.noise_buf
+
+    def noise_bytes(self):
+        return 4 * self.T * self.x.numel()
+
+    def run_graph(self, use_noise_buf, seed, image_offset):
+        """Replay (capturing on first use) encode + the whole T-step loop as one CUDA graph.
+        Philox seed/offset are baked into the captured kernel arguments, so they key the graph."""
+        key = (use_noise_buf, seed if not use_noise_buf else 0, image_offset if not use_noise_buf else 0)
+        g = self.graphs.get(key)
+        if g is None:
+            if len(self.graphs) >= 4:
+                self.graphs.clear()
+            noises = self.ensure_noise_buf() if use_noise_buf else None
+            # warm-up outside capture (lazy module/func loading, cudaFuncSetAttribute)
+            x_save = self.x.clone()
+            side = torch.cuda.Stream()
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                self.encode()
+                self.load_x()
+                self.step(self.T - 1, 0, None if noises is None else noises[0], seed, image_offset)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            self.x.copy_(x_save)
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                self.encode()
+                self.loop(noises, seed, image_offset)
+            self.graphs[key] = g
+        g.replay()
+
+    def n_launches(self):
+        n_r, _ = self.rrdb_prog.bld.count_kernels()
+        n_c, _ = self.cond_prog.bld.count_kernels()
+        n_u, _ = self.unet_prog.bld.count_kernels()
+        return (n_r + 1) + n_c + 1 + self.T * (n_u + 1)

@@ -1,0 +1,532 @@
+"""Drop-in mirror of the reference's `srdiff/model.py` module API for the reverse-diffusion
+inference path: the module-global ``hparams`` dict, ``RRDBNet`` / ``Unet`` /
+``GaussianDiffusion`` with the reference's constructor signatures, parameter names and shapes
+(state-dict compatible, Appendix C), and ``sample / p_sample / res2img / img2res``.
+
+Parameters live in ordinary nn.Conv2d / nn.Linear containers (fp32, NCHW) -- that is the API
+truth -- but no forward ever calls ATen arithmetic: every forward converts to padded NHWC and
+launches the sm_100a kernels of libsrdiff_b200.so through `engine.py`.  CPU tensors raise.
+
+Line numbers cite /root/reference/srdiff/model.py.
+"""
+import math
+from functools import partial
+
+import numpy as np
+import torch
+from torch import nn
+
+from . import _lib as L
+from . import engine as E
+
+# module-global config dict, filled by the caller from srdiff/config.yaml (:274; st_app1.py:1568-1578)
+hparams = {}
+
+
+class Runtime:
+    """Knobs that do not exist in the reference (it has one precision and one device path)."""
+    precision = "bf16"        # "bf16" (tcgen05 path) | "fp32" (validation mode, CUDA-core fp32) | "bf16_direct"
+    noise = "torch"           # "torch": x_T / per-step noise via torch.randn + noise_like (reference RNG order)
+    #                           "philox": generated inside the p_sample kernel (throughput mode)
+    graph = True              # capture encode + T-step loop in one CUDA graph
+    noise_budget_bytes = 8 << 30
+    seed_counter = 0
+    image_offset = 0          # global index of image 0 of this shard (multi-GPU shard invariance)
+
+
+runtime = Runtime()
+
+
+def exists(x):
+    return x is not None
+
+
+def default(val, d):
+    from inspect import isfunction
+    if exists(val):
+        return val
+    return d() if isfunction(d) else d
+
+
+# ------------------------------------------------------------------------------------------ blocks
+class Mish(nn.Module):
+    """:422-424"""
+
+    def forward(self, x):
+        E._require_cuda(x, "Mish input")
+        xc = x.contiguous().float()
+        y = torch.empty_like(xc)
+        L.check(L.lib().srd_mish_f32(xc.data_ptr(), y.data_ptr(), xc.numel(), E._stream()), "srd_mish_f32")
+        return y
+
+
+class SinusoidalPosEmb(nn.Module):
+    """:407-419.  Parameter-free; evaluated inside srd_time_table on the hot path."""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.dim = dim
+
+
+def _run_single(x, build):
+    """Stand-alone forward of a sub-module: NCHW fp32 in -> program -> NCHW fp32 out."""
+    E._require_cuda(x, "input")
+    x = x.contiguous().float()
+    B, C_, H, W = x.shape
+    bld = E.Builder(x.device, runtime.precision)
+    out_act, out_c = build(bld, x, B, C_, H, W)
+    out = torch.empty((B, out_c, out_act.H, out_act.W), dtype=torch.float32, device=x.device)
+    bld.act_to_nchw(out_act, 0, out_c, out)
+    bld.run()
+    return out
+
+
+class Block(nn.Module):
+    """:439-457 (groups == 0 only: the config hard-wires it, :757)."""
+
+    def __init__(self, dim, dim_out, groups=8):
+        super().__init__()
+        if groups != 0:
+            raise NotImplementedError("GroupNorm Block (gn_groups > 0) is outside the hot path (SURVEY 8f-3)")
+        self.block = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(dim, dim_out, 3), Mish())
+
+    def forward(self, x):
+        conv = self.block[1]
+
+        def build(bld, x, B, C_, H, W):
+            xin = bld.act(B, H, W, C_)
+            bld.nchw_to_act(lambda: x, xin, C_, border=L.BORDER_REFLECT)
+            out = bld.act(B, H, W, conv.out_channels)
+            bld.conv(E._pc(conv), [(xin, 0, C_)], out=out, act=L.ACT_MISH)
+            return out, conv.out_channels
+        return _run_single(x, build)
+
+
+class ResnetBlock(nn.Module):
+    """:460-480"""
+
+    def __init__(self, dim, dim_out, *, time_emb_dim=0, groups=8):
+        super().__init__()
+        if time_emb_dim > 0:
+            self.mlp = nn.Sequential(Mish(), nn.Linear(time_emb_dim, dim_out))
+        self.block1 = Block(dim, dim_out, groups=groups)
+        self.block2 = Block(dim_out, dim_out, groups=groups)
+        self.res_conv = nn.Conv2d(dim, dim_out, 1) if dim != dim_out else nn.Identity()
+        self._dim, self._dim_out = dim, dim_out
+
+    def forward(self, x, time_emb=None, cond=None):
+        if cond is not None:
+            raise NotImplementedError("ResnetBlock(cond=...) is never used by the reference's Unet")
+        if time_emb is not None:
+            raise NotImplementedError(
+                "stand-alone ResnetBlock.forward takes no time_emb: on this path the time embedding is a "
+                "precomputed table consumed by Unet.forward (srd_time_table)")
+
+        def build(bld, x, B, C_, H, W):
+            xin = bld.act(B, H, W, C_)
+            bld.nchw_to_act(lambda: x, xin, C_, border=L.BORDER_REFLECT)
+            out = bld.act(B, H, W, self._dim_out)
+            E.build_resnet(bld, self, [(xin, 0, C_)], self._dim_out, out, L.BORDER_KEEP, None)
+            return out, self._dim_out
+        return _run_single(x, build)
+
+
+class Upsample(nn.Module):
+    """:483-491 ConvTranspose2d(dim, dim, 4, 2, 1)"""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.conv = nn.Sequential(nn.ConvTranspose2d(dim, dim, 4, 2, 1))
+
+    def forward(self, x):
+        conv = self.conv[0]
+
+        def build(bld, x, B, C_, H, W):
+            xin = bld.act(B, H, W, C_)
+            bld.nchw_to_act(lambda: x, xin, C_, border=L.BORDER_KEEP)
+            out = bld.act(B, 2 * H, 2 * W, conv.out_channels)
+            bld.conv(E._pc(conv), [(xin, 0, C_)], out=out)
+            return out, conv.out_channels
+        return _run_single(x, build)
+
+
+class Downsample(nn.Module):
+    """:494-503 ReflectionPad2d(1) + Conv2d(dim, dim, 3, 2)"""
+
+    def __init__(self, dim):
+        super().__init__()
+        self.conv = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(dim, dim, 3, 2))
+
+    def forward(self, x):
+        conv = self.conv[1]
+
+        def build(bld, x, B, C_, H, W):
+            xin = bld.act(B, H, W, C_)
+            bld.nchw_to_act(lambda: x, xin, C_, border=L.BORDER_REFLECT)
+            out = bld.act(B, H // 2, W // 2, conv.out_channels)
+            bld.conv(E._pc(conv), [(xin, 0, C_)], out=out)
+            return out, conv.out_channels
+        return _run_single(x, build)
+
+
+# ------------------------------------------------------------------------------------------ RRDB
+def make_layer(block, n_layers, seq=False):
+    """:98-105"""
+    layers = [block() for _ in range(n_layers)]
+    return nn.Sequential(*layers) if seq else nn.ModuleList(layers)
+
+
+class ResidualDenseBlock_5C(nn.Module):
+    """:670-690 (parameter container; executed by engine.RRDBProgram)."""
+
+    def __init__(self, nf=64, gc=32, bias=True):
+        super().__init__()
+        self.conv1 = nn.Conv2d(nf, gc, 3, 1, 1, bias=bias)
+        self.conv2 = nn.Conv2d(nf + gc, gc, 3, 1, 1, bias=bias)
+        self.conv3 = nn.Conv2d(nf + 2 * gc, gc, 3, 1, 1, bias=bias)
+        self.conv4 = nn.Conv2d(nf + 3 * gc, gc, 3, 1, 1, bias=bias)
+        self.conv5 = nn.Conv2d(nf + 4 * gc, nf, 3, 1, 1, bias=bias)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+
+
+class RRDB(nn.Module):
+    """:693-706"""
+
+    def __init__(self, nf, gc=32):
+        super().__init__()
+        self.RDB1 = ResidualDenseBlock_5C(nf, gc)
+        self.RDB2 = ResidualDenseBlock_5C(nf, gc)
+        self.RDB3 = ResidualDenseBlock_5C(nf, gc)
+
+
+class RRDBNet(nn.Module):
+    """:709-749"""
+
+    def __init__(self, in_nc, out_nc, nf, nb, gc=32):
+        super().__init__()
+        self.conv_first = nn.Conv2d(in_nc, nf, 3, 1, 1, bias=True)
+        self.RRDB_trunk = make_layer(partial(RRDB, nf=nf, gc=gc), nb)
+        self.trunk_conv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.upconv1 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.upconv2 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        if hparams['sr_scale'] == 8:
+            self.upconv3 = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.HRconv = nn.Conv2d(nf, nf, 3, 1, 1, bias=True)
+        self.conv_last = nn.Conv2d(nf, out_nc, 3, 1, 1, bias=True)
+        self.lrelu = nn.LeakyReLU(negative_slope=0.2)
+        self._in_nc, self._out_nc, self._nf, self._gc = in_nc, out_nc, nf, gc
+        self._progs = {}
+
+    def _program(self, B, h, w, device):
+        key = (B, h, w, runtime.precision, str(device), E.params_signature(self), hparams['sr_scale'])
+        p = self._progs.get("p")
+        if p is None or p[0] != key:
+            p = (key, E.RRDBProgram(self, B, h, w, runtime.precision, device))
+            self._progs["p"] = p
+        return p[1]
+
+    @torch.no_grad()
+    def forward(self, x, get_fea=False):
+        E._require_cuda(x, "RRDBNet input")
+        x = x.contiguous().float()
+        B, _, h, w = x.shape
+        prog = self._program(B, h, w, x.device)
+        prog.load_input(x)
+        prog.run()
+        out = prog.out.clone()
+        if get_fea:
+            return out, prog.feas_nchw()
+        return out
+
+
+# ------------------------------------------------------------------------------------------ Unet
+class Unet(nn.Module):
+    """:752-856"""
+
+    def __init__(self, dim, out_dim=None, dim_mults=(1, 2, 4, 8), cond_dim=32):
+        super().__init__()
+        dims = [3, *map(lambda m: dim * m, dim_mults)]
+        in_out = list(zip(dims[:-1], dims[1:]))
+        groups = 0
+        self.cond_proj = nn.ConvTranspose2d(cond_dim * ((hparams['rrdb_num_block'] + 1) // 3), dim,
+                                            hparams['sr_scale'] * 2, hparams['sr_scale'], hparams['sr_scale'] // 2)
+        self.time_pos_emb = SinusoidalPosEmb(dim)
+        self.mlp = nn.Sequential(nn.Linear(dim, dim * 4), Mish(), nn.Linear(dim * 4, dim))
+        self.downs = nn.ModuleList([])
+        self.ups = nn.ModuleList([])
+        num_resolutions = len(in_out)
+        for ind, (dim_in, dim_out) in enumerate(in_out):
+            is_last = ind >= (num_resolutions - 1)
+            self.downs.append(nn.ModuleList([
+                ResnetBlock(dim_in, dim_out, time_emb_dim=dim, groups=groups),
+                ResnetBlock(dim_out, dim_out, time_emb_dim=dim, groups=groups),
+                Downsample(dim_out) if not is_last else nn.Identity()]))
+        mid_dim = dims[-1]
+        self.mid_block1 = ResnetBlock(mid_dim, mid_dim, time_emb_dim=dim, groups=groups)
+        if hparams['use_attn']:
+            raise NotImplementedError("use_attn=True: LinearAttention is outside the hot path (SURVEY 2 #11)")
+        self.mid_block2 = ResnetBlock(mid_dim, mid_dim, time_emb_dim=dim, groups=groups)
+        for ind, (dim_in, dim_out) in enumerate(reversed(in_out[1:])):
+            is_last = ind >= (num_resolutions - 1)          # never true: three Upsamples
+            self.ups.append(nn.ModuleList([
+                ResnetBlock(dim_out * 2, dim_in, time_emb_dim=dim, groups=groups),
+                ResnetBlock(dim_in, dim_in, time_emb_dim=dim, groups=groups),
+                Upsample(dim_in) if not is_last else nn.Identity()]))
+        self.final_conv = nn.Sequential(Block(dim, dim, groups=groups), nn.Conv2d(dim, out_dim, 1))
+        if hparams['res'] and hparams['up_input']:
+            raise NotImplementedError("up_input=True is outside the hot path (SURVEY 8f-3)")
+        if hparams['use_wn']:
+            raise NotImplementedError("use_wn=True is outside the hot path (SURVEY 8f-3)")
+        if hparams['weight_init']:
+            raise NotImplementedError("weight_init=True is a training-time option outside the hot path")
+        self._dim, self._dims, self._out_dim, self._cond_dim = dim, dims, out_dim, cond_dim
+        self._progs = {}
+
+    def resnet_blocks(self):
+        """Fixed order used for the columns of the time table."""
+        blocks = []
+        for r0, r1, _ in self.downs:
+            blocks += [r0, r1]
+        blocks += [self.mid_block1, self.mid_block2]
+        for r0, r1, _ in self.ups:
+            blocks += [r0, r1]
+        return blocks
+
+    @torch.no_grad()
+    def forward(self, x, time, cond, img_lr_up):
+        """x [B,3,H,W], time [B] (any per-sample values), cond = list of RRDB feature maps."""
+        E._require_cuda(x, "Unet input")
+        x = x.contiguous().float()
+        B, _, H, W = x.shape
+        dev = x.device
+        sel = cond[2::3]
+        key = (B, H, W, runtime.precision, str(dev), E.params_signature(self),
+               tuple(tuple(f.shape) for f in sel))
+        p = self._progs.get("p")
+        if p is None or p[0] != key:
+            bld = E.Builder(dev, runtime.precision)
+            fea_acts = [bld.act(B, f.shape[2], f.shape[3], f.shape[1]) for f in cond]
+            if any(f.shape[1] != self._cond_dim for f in sel):
+                raise RuntimeError("cond features have %d channels, Unet was built with cond_dim=%d"
+                                   % (sel[0].shape[1], self._cond_dim))
+            cprog = E.CondProgram(self, fea_acts, bld.prec, dev)
+            uprog = E.UnetProgram(self, B, H, W, bld.prec, dev, cond_act=cprog.cond, per_sample_temb=True)
+            p = (key, (bld, fea_acts, cprog, uprog))
+            self._progs["p"] = p
+        bld, fea_acts, cprog, uprog = p[1]
+        for f, a in list(zip(cond, fea_acts))[2::3]:
+            fc = f.contiguous().float()
+            L.check(L.lib().srd_nchw_to_act(fc.data_ptr(), B, fc.shape[1], a.H, a.W, 1.0, 0.0, a.ptr, a.ct,
+                                            bld.prec.dtype, L.BORDER_KEEP, E._stream()), "srd_nchw_to_act")
+        cprog.run()
+        L.check(L.lib().srd_nchw_to_act(x.data_ptr(), B, x.shape[1], H, W, 1.0, 0.0, uprog.xin.ptr, uprog.xin.ct,
+                                        bld.prec.dtype, L.BORDER_REFLECT, E._stream()), "srd_nchw_to_act")
+        table = E.time_table(self, time.reshape(-1).float())
+        if table.shape[0] != B:
+            raise RuntimeError("time must have one entry per image")
+        self._last_table = table                         # must outlive the asynchronous launches
+        uprog.run(table.data_ptr())
+        return uprog.eps.clone()
+
+
+# ------------------------------------------------------------------------------------------ schedule
+def extract(a, t, x_shape):
+    """:860-863 (kept for API parity; on the hot path the gathers live inside srd_p_sample_step)."""
+    b, *_ = t.shape
+    out = a.gather(-1, t)
+    return out.reshape(b, *((1,) * (len(x_shape) - 1)))
+
+
+def noise_like(shape, device, repeat=False):
+    """:866-869"""
+    if repeat:
+        return torch.randn((1, *shape[1:]), device=device).repeat(shape[0], *((1,) * (len(shape) - 1)))
+    return torch.randn(shape, device=device)
+
+
+def _warmup_beta(beta_start, beta_end, num_diffusion_timesteps, warmup_frac):
+    betas = beta_end * np.ones(num_diffusion_timesteps, dtype=np.float64)
+    warmup_time = int(num_diffusion_timesteps * warmup_frac)
+    betas[:warmup_time] = np.linspace(beta_start, beta_end, warmup_time, dtype=np.float64)
+    return betas
+
+
+def get_beta_schedule(num_diffusion_timesteps, beta_schedule='linear', beta_start=0.0001, beta_end=0.02):
+    """:879-895"""
+    T = num_diffusion_timesteps
+    if beta_schedule == 'quad':
+        betas = np.linspace(beta_start ** 0.5, beta_end ** 0.5, T, dtype=np.float64) ** 2
+    elif beta_schedule == 'linear':
+        betas = np.linspace(beta_start, beta_end, T, dtype=np.float64)
+    elif beta_schedule == 'warmup10':
+        betas = _warmup_beta(beta_start, beta_end, T, 0.1)
+    elif beta_schedule == 'warmup50':
+        betas = _warmup_beta(beta_start, beta_end, T, 0.5)
+    elif beta_schedule == 'const':
+        betas = beta_end * np.ones(T, dtype=np.float64)
+    elif beta_schedule == 'jsd':
+        betas = 1. / np.linspace(T, 1, T, dtype=np.float64)
+    else:
+        raise NotImplementedError(beta_schedule)
+    assert betas.shape == (T,)
+    return betas
+
+
+def cosine_beta_schedule(timesteps, s=0.008):
+    """:898-908 -- note linspace(0, steps, steps)."""
+    steps = timesteps + 1
+    x = np.linspace(0, steps, steps)
+    alphas_cumprod = np.cos(((x / steps) + s) / (1 + s) * np.pi * 0.5) ** 2
+    alphas_cumprod = alphas_cumprod / alphas_cumprod[0]
+    betas = 1 - (alphas_cumprod[1:] / alphas_cumprod[:-1])
+    return np.clip(betas, a_min=0, a_max=0.999)
+
+
+# ------------------------------------------------------------------------------------------ sampler
+class GaussianDiffusion(nn.Module):
+    """:911-1134 (inference path)."""
+
+    def __init__(self, denoise_fn, rrdb_net, timesteps=1000, loss_type='l1'):
+        super().__init__()
+        self.denoise_fn = denoise_fn
+        self.rrdb = rrdb_net
+        if hparams['beta_schedule'] == 'cosine':
+            betas = cosine_beta_schedule(timesteps, s=hparams['beta_s'])
+        if hparams['beta_schedule'] == 'linear':
+            betas = get_beta_schedule(timesteps, beta_end=hparams['beta_end'])
+            if hparams['res']:
+                betas[-1] = 0.999
+        alphas = 1. - betas
+        alphas_cumprod = np.cumprod(alphas, axis=0)
+        alphas_cumprod_prev = np.append(1., alphas_cumprod[:-1])
+        timesteps, = betas.shape
+        self.num_timesteps = int(timesteps)
+        self.loss_type = loss_type
+        to_torch = partial(torch.tensor, dtype=torch.float32)
+        self.register_buffer('betas', to_torch(betas))
+        self.register_buffer('alphas_cumprod', to_torch(alphas_cumprod))
+        self.register_buffer('alphas_cumprod_prev', to_torch(alphas_cumprod_prev))
+        self.register_buffer('sqrt_alphas_cumprod', to_torch(np.sqrt(alphas_cumprod)))
+        self.register_buffer('sqrt_one_minus_alphas_cumprod', to_torch(np.sqrt(1. - alphas_cumprod)))
+        self.register_buffer('log_one_minus_alphas_cumprod', to_torch(np.log(1. - alphas_cumprod)))
+        self.register_buffer('sqrt_recip_alphas_cumprod', to_torch(np.sqrt(1. / alphas_cumprod)))
+        self.register_buffer('sqrt_recipm1_alphas_cumprod', to_torch(np.sqrt(1. / alphas_cumprod - 1)))
+        posterior_variance = betas * (1. - alphas_cumprod_prev) / (1. - alphas_cumprod)
+        self.register_buffer('posterior_variance', to_torch(posterior_variance))
+        self.register_buffer('posterior_log_variance_clipped',
+                             to_torch(np.log(np.maximum(posterior_variance, 1e-20))))
+        self.register_buffer('posterior_mean_coef1',
+                             to_torch(betas * np.sqrt(alphas_cumprod_prev) / (1. - alphas_cumprod)))
+        self.register_buffer('posterior_mean_coef2',
+                             to_torch((1. - alphas_cumprod_prev) * np.sqrt(alphas) / (1. - alphas_cumprod)))
+        self.sample_tqdm = True
+        self._plans = {}
+        self.last_stats = {}
+
+    # ---- plan cache -------------------------------------------------------------------------
+    def _plan(self, B, h, w, device):
+        sig = (E.params_signature(self), self.num_timesteps, hparams['res_rescale'], hparams['clip_input'])
+        key = (B, h, w, runtime.precision, str(device))
+        p = self._plans.get(key)
+        if p is None or p.sig != sig:
+            if len(self._plans) >= 2:
+                self._plans.clear()
+            p = E.SamplerPlan(self, B, h, w, runtime.precision, device)
+            self._plans[key] = p
+        return p
+
+    def _elementwise(self, x, img_lr_up, clip_input, inverse):
+        E._require_cuda(x, "image")
+        if clip_input is None:
+            clip_input = hparams['clip_input']
+        if not hparams['res']:
+            return x
+        xc, uc = x.contiguous().float(), img_lr_up.contiguous().float()
+        out = torch.empty_like(xc)
+        L.check(L.lib().srd_res2img(xc.data_ptr(), uc.data_ptr(), out.data_ptr(), xc.numel(),
+                                    float(hparams['res_rescale']), 1 if clip_input else 0, inverse, E._stream()),
+                "srd_res2img")
+        return out
+
+    def res2img(self, img_, img_lr_up, clip_input=None):
+        """:1118-1125"""
+        return self._elementwise(img_, img_lr_up, clip_input, 0)
+
+    def img2res(self, x, img_lr_up, clip_input=None):
+        """:1127-1134"""
+        return self._elementwise(x, img_lr_up, clip_input, 1)
+
+    @torch.no_grad()
+    def p_sample(self, x, t, cond, img_lr_up, noise_pred=None, clip_denoised=True, repeat_noise=False):
+        """:1050-1060 stand-alone (arbitrary per-sample t).  Returns (x_prev, x0_pred)."""
+        E._require_cuda(x, "p_sample input")
+        x = x.contiguous().float()
+        if noise_pred is None:
+            noise_pred = self.denoise_fn(x, t, cond=cond, img_lr_up=img_lr_up)
+        noise = noise_like(x.shape, x.device, repeat_noise).contiguous().float()
+        coef = E.coef_table(self)
+        t32 = t.to(device=x.device, dtype=torch.int32).contiguous()
+        x_out, x0 = torch.empty_like(x), torch.empty_like(x)
+        E.p_sample_step(x, noise_pred.contiguous().float(), noise, coef, t32, x_out, clip_denoised, x0_out=x0)
+        return x_out, x0
+
+    @torch.no_grad()
+    def sample(self, img_lr, img_lr_up, shape, save_intermediate=False):
+        """:1062-1091.  Returns (img, rrdb_out[, images])."""
+        device = self.betas.device
+        E._require_cuda(self.betas, "GaussianDiffusion")
+        E._require_cuda(img_lr, "img_lr")
+        if not hparams['res']:
+            raise NotImplementedError("hparams['res']=False start (q_sample of img_lr_up) is a 'next' row (SURVEY 8f-2)")
+        if not hparams['use_rrdb']:
+            raise NotImplementedError("hparams['use_rrdb']=False is outside the hot path")
+        b = shape[0]
+        B, _, h, w = img_lr.shape
+        if b != B or tuple(shape) != tuple(img_lr_up.shape):
+            raise RuntimeError("shape %s inconsistent with img_lr %s / img_lr_up %s"
+                               % (tuple(shape), tuple(img_lr.shape), tuple(img_lr_up.shape)))
+        plan = self._plan(B, h, w, device)
+        if (plan.H, plan.W) != (shape[2], shape[3]):
+            raise RuntimeError("img_lr_up must be sr_scale x img_lr")
+        T = self.num_timesteps
+        use_torch_noise = runtime.noise == "torch" and plan.noise_bytes() <= runtime.noise_budget_bytes
+        runtime.seed_counter += 1
+        seed = (torch.cuda.default_generators[device.index or 0].initial_seed() * 1000003 + runtime.seed_counter) \
+            & 0xFFFFFFFFFFFFFFFF
+        # ---- x_T :1070 (drawn before the RRDB forward, like the reference)
+        if use_torch_noise:
+            plan.x.copy_(torch.randn(shape, device=device))
+        else:
+            L.check(L.lib().srd_randn(plan.x.data_ptr(), B, plan.x[0].numel(), seed, 0, runtime.image_offset,
+                                      E._stream()), "srd_randn")
+        plan.img_lr.copy_(img_lr)
+        plan.img_lr_up.copy_(img_lr_up)
+        eager = save_intermediate or not runtime.graph
+        images = []
+        if use_torch_noise and not eager:
+            nb = plan.ensure_noise_buf()
+            for k in range(T):                       # one draw per step, t == 0 included
+                nb[k].copy_(noise_like(shape, device))
+        if not eager:
+            plan.run_graph(use_torch_noise, seed, runtime.image_offset)
+        else:
+            plan.encode()
+            plan.load_x()
+            it = reversed(range(T))
+            if self.sample_tqdm:
+                from tqdm import tqdm
+                it = tqdm(it, desc='sampling loop time step', total=T)
+            x0 = torch.empty_like(plan.x) if save_intermediate else None
+            for k, i in enumerate(it):
+                noise = noise_like(shape, device).contiguous().float() if use_torch_noise else None
+                plan.step(i, k, noise, seed, runtime.image_offset, x0_out=x0)
+                if save_intermediate:
+                    images.append((self.res2img(plan.x, plan.img_lr_up).cpu(),
+                                   self.res2img(x0, plan.img_lr_up).cpu()))
+        self.last_stats = {"gpu_launches": plan.n_launches(), "graph": not eager,
+                           "noise": "torch" if use_torch_noise else "philox"}
+        img = plan.img.clone()
+        rrdb_out = plan.rrdb_prog.out.clone()
+        if save_intermediate:
+            return img, rrdb_out, images
+        return img, rrdb_out

@@ -92,6 +92,9 @@ typedef struct SrdConvPlan SrdConvPlan;
 
 const char* srd_last_error(void);
 int srd_version(void);
+/* ABI self-check for FFI bindings: which = 0 -> sizeof(SrdConvDesc), 1 -> sizeof(SrdPSampleArgs),
+ * 2 -> offsetof(SrdConvDesc, head_b), 3 -> offsetof(SrdPSampleArgs, act_dtype). */
+int srd_abi_sizeof(int32_t which);
 /* 1 if the tcgen05/TMA path can serve this descriptor (bf16, channel/stride alignment...). */
 int srd_conv_tc_supported(const SrdConvDesc* desc);
 /* Validates the descriptor, picks the kernel, encodes the TMA tensor maps. Host-only work. */

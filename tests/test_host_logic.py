@@ -1,0 +1,130 @@
+"""CPU tests of the host side: weight packing / tap tables (via tests/emulate.py), state-dict
+contract, schedule buffers, C-ABI symbol export, loud failure without CUDA."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+import emulate as EM
+from conftest import ROOT, build_ours, golden
+
+
+def _nchw(o):
+    return o.permute(0, 3, 1, 2)
+
+
+@pytest.mark.parametrize("cins,O,k,stride,reflect", [
+    ([64], 64, 3, 1, True), ([3], 64, 3, 1, True), ([96, 64], 48, 3, 1, True), ([32, 16, 16], 16, 3, 1, False),
+    ([64], 64, 3, 2, True), ([130], 24, 3, 2, True), ([64], 128, 1, 1, True), ([100, 92], 3, 1, 1, False)])
+def test_pack_conv_layouts(cins, O, k, stride, reflect):
+    from dgm_img_super_resolution_b200 import engine as E
+    torch.manual_seed(0)
+    I = sum(cins)
+    x = torch.randn(2, I, 8, 12)
+    w = torch.randn(O, I, k, k) * 0.1
+    if k == 3:
+        xp = F.pad(x, (1, 1, 1, 1), mode="reflect" if reflect else "constant")
+        want = F.conv2d(xp, w, stride=stride)
+    else:
+        want = F.conv2d(x, w)
+    wd, wt = E._pack_conv(w, cins, stride)
+    srcs, a = [], 0
+    for c in cins:
+        srcs.append(EM.to_padded_nhwc(x[:, a:a + c], reflect))
+        a += c
+    k0 = (3 - k) // 2
+    got_d = _nchw(EM.emulate_direct(srcs, cins, wd, O, stride, k, k0, 1))
+    assert torch.allclose(got_d, want, atol=1e-4, rtol=1e-4)
+    got_t = _nchw(EM.emulate_tc(srcs, cins, wt, O, stride, k, k0, 1))
+    assert torch.allclose(got_t, want, atol=0.08, rtol=0.02)        # weights rounded to bf16
+    assert wt.shape[-2] % 16 == 0 and wt.shape[-1] == 64 and wt.dtype == torch.bfloat16
+
+
+@pytest.mark.parametrize("cins,O,S", [([64], 64, 2), ([192], 40, 2), ([32, 32, 32], 64, 4), ([70, 26], 16, 4)])
+def test_pack_conv_transpose_phases(cins, O, S):
+    from dgm_img_super_resolution_b200 import engine as E
+    torch.manual_seed(1)
+    I = sum(cins)
+    x = torch.randn(2, I, 5, 7)
+    w = torch.randn(I, O, 2 * S, 2 * S) * 0.1
+    want = F.conv_transpose2d(x, w, stride=S, padding=S // 2)
+    wd, wt = E._pack_convT(w, cins, S)
+    srcs, a = [], 0
+    for c in cins:
+        srcs.append(EM.to_padded_nhwc(x[:, a:a + c], False))
+        a += c
+    got_d = _nchw(EM.emulate_direct(srcs, cins, wd, O, 1, 2, 0, S))
+    assert got_d.shape == want.shape
+    assert torch.allclose(got_d, want, atol=1e-4, rtol=1e-4)
+    got_t = _nchw(EM.emulate_tc(srcs, cins, wt, O, 1, 2, 0, S))
+    assert torch.allclose(got_t, want, atol=0.08, rtol=0.02)
+
+
+def test_state_dict_contract(hp):
+    M, diff = build_ours(hp)
+    sd = diff.state_dict()
+    chk = __import__("json").load(open(os.path.join(ROOT, "tests", "golden", "state_checksum.json")))
+    assert set(sd) == set(chk) and len(sd) == 396
+    for k, v in sd.items():
+        assert float(v.double().sum()) == pytest.approx(chk[k][0], rel=1e-9, abs=1e-9), k
+        assert float(v.double().abs().sum()) == pytest.approx(chk[k][1], rel=1e-9), k
+    g = golden("schedules.pt")["cosine_T100"]
+    for k, v in g.items():
+        assert torch.equal(sd[k], v), k
+    # load_state_dict round trip, strict and non-strict (st_app1.py:1645-1648)
+    M2, diff2 = build_ours(hp, seed=99)
+    diff2.load_state_dict(sd, strict=True)
+    diff2.load_state_dict({k: v for k, v in sd.items() if "rrdb" in k}, strict=False)
+    assert diff.num_timesteps == 100 and diff.sample_tqdm is False and hasattr(diff, "denoise_fn") and hasattr(diff, "rrdb")
+
+
+def test_other_timesteps_and_schedules(hp):
+    g = golden("schedules.pt")
+    M, d25 = build_ours(hp, timesteps=25)
+    assert all(torch.equal(getattr(d25, k), v) for k, v in g["cosine_T25"].items())
+    M, dl = build_ours(dict(hp, beta_schedule="linear"), timesteps=100)
+    assert all(torch.equal(getattr(dl, k), v) for k, v in g["linear_T100"].items())
+    with pytest.raises(NotImplementedError):
+        M.get_beta_schedule(10, "nope")
+
+
+def test_unsupported_config_is_loud(hp):
+    with pytest.raises(NotImplementedError):
+        build_ours(dict(hp, use_attn=True))
+    with pytest.raises(KeyError):
+        import dgm_img_super_resolution_b200.model as M
+        M.hparams.clear()
+        M.RRDBNet(3, 3, 32, 8, 16)          # reference: KeyError on missing hparams (:720)
+
+
+def test_library_exports_every_declared_symbol():
+    from dgm_img_super_resolution_b200 import _lib
+    assert os.path.isfile(_lib.LIB_PATH), "libsrdiff_b200.so is not built: run __graft_entry__.build()"
+    hdr = open(os.path.join(ROOT, "include", "srdiff_b200.h")).read()
+    declared = set(re.findall(r"\b(srd_[a-z0-9_]+)\s*\(", hdr))
+    assert declared == set(_lib.SYMBOLS), declared ^ set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    L = _lib.lib()
+    assert L.srd_version() >= 100
+    # struct sizes must agree with the header (x86-64 ABI): spot-check through an invalid call
+    d = _lib.SrdConvDesc()
+    h = ctypes.c_void_p()
+    assert L.srd_conv_plan_create(ctypes.byref(d), ctypes.byref(h)) != 0
+    assert b"conv" in L.srd_last_error()
+
+
+def test_no_cpu_fallback(hp):
+    M, diff = build_ours(hp)
+    from dgm_img_super_resolution_b200._lib import SrdError
+    x = torch.zeros(1, 3, 8, 8)
+    with pytest.raises(SrdError):
+        diff.rrdb(x)
+    with pytest.raises(SrdError):
+        diff.sample(x, torch.zeros(1, 3, 32, 32), (1, 3, 32, 32))
+    with pytest.raises(SrdError):
+        M.Mish()(x)
