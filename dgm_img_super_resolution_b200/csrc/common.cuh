@@ -99,9 +99,12 @@ __device__ __forceinline__ float mish_precise(float x) {
 }
 // fast: with n = e^x, tanh(log(1+n)) = (n^2+2n)/(n^2+2n+2): one ex2 + one rcp on the MUFU pipe.
 __device__ __forceinline__ float mish_fast(float x) {
-  float n = exp2f(fminf(x, 20.f) * 1.4426950408889634f);
-  float m = n * (n + 2.f);
-  return x * __fdividef(m, m + 2.f);
+  float n, r;
+  const float a = fminf(x, 20.f) * 1.4426950408889634f;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(n) : "f"(a));
+  const float m = n * (n + 2.f);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(m + 2.f));
+  return x * (m * r);
 }
 template <bool PRECISE>
 __device__ __forceinline__ float apply_act(float x, int act) {

@@ -27,11 +27,13 @@
 
 namespace srd {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_THREADS = 320;          // TMA warp + MMA warp + 8 epilogue warps
 constexpr int TILE_W = 8, TILE_H = 16;
 constexpr int BOX_ROWS = TILE_H + 2;
 constexpr int A_BYTES = BOX_ROWS * TILE_W * 128;   // 18432: one {64ch x 8px x 18rows} bf16 box
 constexpr int MAX_STAGES = 8;
+constexpr int BAR_BYTES = 512;           // mbarriers + TMEM slot
+constexpr int VEC_BYTES = (512 + 1024 + 4 + 2 * 128 * 4) * 4;   // epilogue vectors (see conv_tc_kernel)
 
 struct TcArgs {
   CUtensorMap tmA[SRD_MAX_SRC];
@@ -50,6 +52,7 @@ struct TcArgs {
   const float* head_w;
   const float* head_b;
   int* err_flag;
+  int fast;                // epilogue fast path eligible (N % 16 == 0, uniform temb, aligned windows)
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -76,10 +79,9 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must not hang the GPU (a hang costs the whole box).
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
-  if (mbar_try(bar, parity)) return;
-  const long long t0 = clock64();
+  uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
-    if (clock64() - t0 > 4000000000LL) {
+    if (++spins > (1u << 25)) {                 // ~seconds: far beyond any legitimate wait
       if (err_flag) atomicExch(err_flag, code);
       __trap();
     }
@@ -145,6 +147,238 @@ __device__ __forceinline__ int tap_off(const TcArgs& a, int ld, int j, int ky0) 
   return a.stride == 2 ? (ld == 0 ? j : 0) : ky0 + j;
 }
 
+// ------------------------------------------------------------------------------------------ epilogue
+// Per-launch constants of the fused epilogue staged in shared memory (float): bias[Npad],
+// temb[Npad] (zeros when absent), head weights [4][Npad] + head bias[4], and the partial head
+// sums exchanged between the two warps that share a TMEM lane quarter.
+struct EpiSmem {
+  const float* bias;
+  const float* temb;
+  const float* head_w;
+  const float* head_b;
+  float* hpart;     // [2][128][4]
+};
+
+__device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
+  const uint32_t w[4] = {u.x, u.y, u.z, u.w};
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    f[2 * i] = __uint_as_float(w[i] << 16);
+    f[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u);
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ float act_fast(float x) {
+  if (ACT == SRD_ACT_MISH) return mish_fast(x);
+  if (ACT == SRD_ACT_LRELU02) return fmaxf(x, 0.2f * x);
+  return x;
+}
+
+__device__ __forceinline__ void st16_bf16(__nv_bfloat16* p, const float (&v)[16]) {
+  uint4 a, b;
+  a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]);
+  a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
+  b.x = pack_bf16x2(v[8], v[9]); b.y = pack_bf16x2(v[10], v[11]);
+  b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
+  reinterpret_cast<uint4*>(p)[0] = a;
+  reinterpret_cast<uint4*>(p)[1] = b;
+}
+
+// Write one pixel's 16-channel chunk, plus the mirrored ring copies this pixel owns (reflect).
+__device__ __forceinline__ void store_chunk(__nv_bfloat16* base, int ct, size_t pix, int Wp, int Hp,
+                                            uint32_t edge, const float (&v)[16]) {
+  st16_bf16(base + pix * ct, v);
+  if (edge) {   // rare: only pixels in row/col 1 or H-2/W-2 of a reflect-ringed output
+    const bool top = edge & 1u, bot = edge & 2u, lef = edge & 4u, rig = edge & 8u;
+    const long long dn = (long long)Wp * ct;
+    __nv_bfloat16* p = base + pix * ct;
+    if (top) st16_bf16(p - 2 * dn, v);
+    if (bot) st16_bf16(p + 2 * dn, v);
+    if (lef) st16_bf16(p - 2 * ct, v);
+    if (rig) st16_bf16(p + 2 * ct, v);
+    if (top && lef) st16_bf16(p - 2 * dn - 2 * ct, v);
+    if (top && rig) st16_bf16(p - 2 * dn + 2 * ct, v);
+    if (bot && lef) st16_bf16(p + 2 * dn - 2 * ct, v);
+    if (bot && rig) st16_bf16(p + 2 * dn + 2 * ct, v);
+    (void)Hp;
+  }
+}
+
+// Fast path: N % 16 == 0, batch-uniform temb, 16-byte aligned channel windows.
+template <int ACT>
+__device__ __forceinline__ void epi_chunk_fast(const TcArgs& a, const EpiSmem& es, int c0, const uint32_t (&r)[16],
+                                               bool valid, size_t pix, uint32_t edge, const uint4 (&q1)[2],
+                                               const uint4 (&q2)[2], float (&head)[4]) {
+  float v[16];
+  const float4* sb = reinterpret_cast<const float4*>(es.bias + c0);
+  const float4* st = reinterpret_cast<const float4*>(es.temb + c0);
+  const float alpha = a.ep.alpha;
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 b4 = sb[q], t4 = st[q];
+    v[4 * q + 0] = fmaf(act_fast<ACT>(__uint_as_float(r[4 * q + 0]) + b4.x), alpha, t4.x);
+    v[4 * q + 1] = fmaf(act_fast<ACT>(__uint_as_float(r[4 * q + 1]) + b4.y), alpha, t4.y);
+    v[4 * q + 2] = fmaf(act_fast<ACT>(__uint_as_float(r[4 * q + 2]) + b4.z), alpha, t4.z);
+    v[4 * q + 3] = fmaf(act_fast<ACT>(__uint_as_float(r[4 * q + 3]) + b4.w), alpha, t4.w);
+  }
+  if (a.ep.res1) {
+    float f[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      unpack_bf16x8(q1[h], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 * h + i] = fmaf(a.ep.beta1, f[i], v[8 * h + i]);
+    }
+  }
+  if (a.ep.res2) {
+    float f[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      unpack_bf16x8(q2[h], f);
+#pragma unroll
+      for (int i = 0; i < 8; ++i) v[8 * h + i] = fmaf(a.ep.beta2, f[i], v[8 * h + i]);
+    }
+  }
+  if (valid) {
+    const int Wp = a.ep.W_out + 2, Hp = a.ep.H_out + 2;
+    if (a.ep.out)
+      store_chunk(static_cast<__nv_bfloat16*>(a.ep.out) + a.ep.out_coff + c0, a.ep.out_ct, pix, Wp, Hp, edge, v);
+    if (a.ep.out2)
+      store_chunk(static_cast<__nv_bfloat16*>(a.ep.out2) + a.ep.out2_coff + c0, a.ep.out2_ct, pix, Wp, Hp, edge, v);
+  }
+  if (es.head_w) {
+    for (int jh = 0; jh < a.ep.planar_c; ++jh) {
+      const float4* hw = reinterpret_cast<const float4*>(es.head_w + jh * a.Npad + c0);
+      float acc = head[jh];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 w4 = hw[q];
+        acc = fmaf(w4.x, v[4 * q + 0], acc); acc = fmaf(w4.y, v[4 * q + 1], acc);
+        acc = fmaf(w4.z, v[4 * q + 2], acc); acc = fmaf(w4.w, v[4 * q + 3], acc);
+      }
+      head[jh] = acc;
+    }
+  }
+}
+
+template <int ACT>
+__device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es, uint32_t tmem_base,
+                                              uint32_t t_full0, uint32_t t_empty0, int warp, int lane) {
+  Ring rt{0, 0, 2};
+  const int S = a.up;
+  const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
+  const int half = (warp - 2) >> 2;             // two warps per quarter split the 16-column chunks
+  const int m = quarter * 32 + lane;
+  const int g = m >> 3, px = m & 7;
+  const int nchunks = a.Npad >> 4;
+  const bool has_head = es.head_w != nullptr;
+  int hbuf = 0;
+  for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+    const int phase = item / a.items_per_phase;
+    const int t0 = (item % a.items_per_phase) * a.MT;
+    const int pr = phase / S, ps = phase % S;
+    mbar_wait(t_full0 + 8u * rt.stage, rt.phase, a.err_flag, 6);
+    tc_fence_after();
+    bool released = false;
+    for (int mt = 0; mt < a.MT; ++mt) {
+      const int tt = t0 + mt;
+      const int rowblk = tt / a.n_colblk, colblk = tt % a.n_colblk;
+      const int V = rowblk * TILE_H + a.vstart + g;
+      const int x = colblk * TILE_W + px;
+      bool valid = (tt < a.tiles_per_phase) && (V < a.n_vrows) && (x < a.W_m);
+      int b = 0, y = 0;
+      if (valid) {
+        b = V / a.period;
+        y = V % a.period - a.voff;
+        valid = (y >= 0) && (y < a.H_m);
+      }
+      const int oy = y * S + pr, ox = x * S + ps;
+      const int Ho = a.ep.H_out, Wo = a.ep.W_out;
+      const size_t pix = valid ? ((size_t)(b * (Ho + 2) + oy + 1) * (Wo + 2) + ox + 1) : 0;
+      uint32_t edge = 0;
+      if (valid && a.ep.border == SRD_BORDER_REFLECT)
+        edge = (oy == 1 ? 1u : 0u) | (oy == Ho - 2 ? 2u : 0u) | (ox == 1 ? 4u : 0u) | (ox == Wo - 2 ? 8u : 0u);
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                             (uint32_t)((rt.stage * a.MT + mt) * a.Npad);
+      float head[4] = {0.f, 0.f, 0.f, 0.f};
+      const bool last_mt = (mt == a.MT - 1);
+      if (a.fast) {
+        const __nv_bfloat16* r1p = a.ep.res1 ? static_cast<const __nv_bfloat16*>(a.ep.res1) + pix * a.ep.res1_ct + a.ep.res1_coff : nullptr;
+        const __nv_bfloat16* r2p = a.ep.res2 ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
+        uint4 n1[2] = {}, n2[2] = {};
+        if (valid && half < nchunks) {
+          if (r1p) { n1[0] = reinterpret_cast<const uint4*>(r1p + 16 * half)[0]; n1[1] = reinterpret_cast<const uint4*>(r1p + 16 * half)[1]; }
+          if (r2p) { n2[0] = reinterpret_cast<const uint4*>(r2p + 16 * half)[0]; n2[1] = reinterpret_cast<const uint4*>(r2p + 16 * half)[1]; }
+        }
+        for (int c = half; c < nchunks; c += 2) {
+          uint32_t r[16];
+          tc_ld16(tbase + (uint32_t)(c * 16), r);
+          uint4 q1[2] = {n1[0], n1[1]}, q2[2] = {n2[0], n2[1]};
+          if (valid && c + 2 < nchunks) {      // prefetch the next chunk's residuals behind this chunk's math
+            if (r1p) { n1[0] = reinterpret_cast<const uint4*>(r1p + 16 * (c + 2))[0]; n1[1] = reinterpret_cast<const uint4*>(r1p + 16 * (c + 2))[1]; }
+            if (r2p) { n2[0] = reinterpret_cast<const uint4*>(r2p + 16 * (c + 2))[0]; n2[1] = reinterpret_cast<const uint4*>(r2p + 16 * (c + 2))[1]; }
+          }
+          tc_ld_wait();
+          if (last_mt && c + 2 >= nchunks) {   // accumulator fully read: hand the TMEM stage back early
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty0 + 8u * rt.stage);
+            released = true;
+          }
+          epi_chunk_fast<ACT>(a, es, c * 16, r, valid, pix, edge, q1, q2, head);
+        }
+        if (has_head) {                        // combine the two halves' partial 1x1 sums
+          float* hp = es.hpart + ((size_t)hbuf * 128 + m) * 4;
+          if (half == 1) { hp[0] = head[0]; hp[1] = head[1]; hp[2] = head[2]; hp[3] = head[3]; }
+          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+          if (half == 0 && valid) {
+            for (int jh = 0; jh < a.ep.planar_c; ++jh)
+              a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + hp[jh] + es.head_b[jh];
+          }
+          hbuf ^= 1;
+        }
+      } else {
+        // generic path (ragged N, per-image temb rows, planar output): one warp per quarter does all chunks
+        if (half == 0) {
+          for (int c0 = 0; c0 < a.Npad; c0 += 16) {
+            uint32_t r[16];
+            tc_ld16(tbase + (uint32_t)c0, r);
+            tc_ld_wait();
+            if (valid && c0 < a.ep.N) {
+              float v[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+              epilogue_math<__nv_bfloat16, 16, 8, false>(a.ep, b, oy, ox, c0, v);
+              epilogue_store<__nv_bfloat16, 16, 8>(a.ep, b, oy, ox, c0, v, !has_head);
+              if (has_head) {
+                const int nv = min(16, a.ep.N - c0);
+                for (int jh = 0; jh < a.ep.planar_c; ++jh) {
+                  float acc = head[jh];
+#pragma unroll
+                  for (int i = 0; i < 16; ++i)
+                    if (i < nv) acc = fmaf(es.head_w[jh * a.Npad + c0 + i], v[i], acc);
+                  head[jh] = acc;
+                }
+              }
+            }
+          }
+          if (has_head && valid) {
+            for (int jh = 0; jh < a.ep.planar_c; ++jh)
+              a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
+          }
+        }
+      }
+    }
+    if (!released) {
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty0 + 8u * rt.stage);
+    }
+    rt.next();
+  }
+}
+
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -161,13 +395,19 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   auto T_full = [&](int s) { return bar_base + 8u * (4 * MAX_STAGES + s); };
   auto T_empty = [&](int s) { return bar_base + 8u * (4 * MAX_STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (4 * MAX_STAGES + 4);
-  volatile uint32_t* tmem_slot_ptr =
-      reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
+  uint8_t* gen_base = smem_raw + (bar_base - smem_u32(smem_raw));       // generic pointer to bar_base
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + 8 * (4 * MAX_STAGES + 4));
+  float* vec = reinterpret_cast<float*>(gen_base + BAR_BYTES);
+  float* s_bias = vec;                 // [256]
+  float* s_temb = vec + 256;           // [256]
+  float* s_head = vec + 512;           // [4][256]
+  float* s_headb = vec + 512 + 1024;   // [4]
+  float* s_hpart = vec + 512 + 1024 + 4;   // [2][128][4]
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.a_stages; ++s) { mbar_init(A_full(s), 1); mbar_init(A_empty(s), 1); }
     for (int s = 0; s < a.b_stages; ++s) { mbar_init(B_full(s), 1); mbar_init(B_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(T_full(s), 1); mbar_init(T_empty(s), 4); }
+    for (int s = 0; s < 2; ++s) { mbar_init(T_full(s), 1); mbar_init(T_empty(s), 8); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int s = 0; s < a.n_src; ++s)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA[s]) : "memory");
@@ -177,6 +417,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  // stage the per-channel epilogue vectors
+  for (int i = threadIdx.x; i < a.Npad; i += TC_THREADS) {
+    s_bias[i] = (i < a.ep.N) ? __ldg(a.ep.bias + i) : 0.f;
+    s_temb[i] = (a.ep.temb && a.ep.temb_bstride == 0 && i < a.ep.N) ? __ldg(a.ep.temb + i) : 0.f;
+  }
+  if (a.head_w) {
+    for (int i = threadIdx.x; i < 4 * a.Npad; i += TC_THREADS) {
+      const int jh = i / a.Npad, c = i % a.Npad;
+      s_head[i] = (jh < a.ep.planar_c && c < a.ep.N) ? __ldg(a.head_w + (size_t)jh * a.ep.N + c) : 0.f;
+    }
+    if (threadIdx.x < 4) s_headb[threadIdx.x] = (threadIdx.x < a.ep.planar_c) ? __ldg(a.head_b + threadIdx.x) : 0.f;
   }
   tc_fence_before();
   __syncthreads();
@@ -275,67 +527,16 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       }
     }
   } else {
-    // ================================================================= epilogue (warps 2..5)
-    Ring rt{0, 0, 2};
-    const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
-    const int m = quarter * 32 + lane;
-    const int g = m >> 3, px = m & 7;
-    const bool has_head = a.head_w != nullptr;
-    for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-      const int phase = item / a.items_per_phase;
-      const int t0 = (item % a.items_per_phase) * a.MT;
-      const int pr = phase / S, ps = phase % S;
-      mbar_wait(T_full(rt.stage), rt.phase, a.err_flag, 6);
-      tc_fence_after();
-      for (int mt = 0; mt < a.MT; ++mt) {
-        const int tt = t0 + mt;
-        const int rowblk = tt / a.n_colblk, colblk = tt % a.n_colblk;
-        const int V = rowblk * TILE_H + a.vstart + g;
-        const int x = colblk * TILE_W + px;
-        bool valid = (tt < a.tiles_per_phase) && (V < a.n_vrows) && (x < a.W_m);
-        int b = 0, y = 0;
-        if (valid) {
-          b = V / a.period;
-          y = V % a.period - a.voff;
-          valid = (y >= 0) && (y < a.H_m);
-        }
-        const int oy = y * S + pr, ox = x * S + ps;
-        const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                               (uint32_t)((rt.stage * a.MT + mt) * a.Npad);
-        float head[4] = {0.f, 0.f, 0.f, 0.f};
-        for (int c0 = 0; c0 < a.Npad; c0 += 16) {
-          uint32_t r[16];
-          tc_ld16(tbase + (uint32_t)c0, r);
-          tc_ld_wait();
-          if (valid && c0 < a.ep.N) {
-            float v[16];
-#pragma unroll
-            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-            epilogue_math<__nv_bfloat16, 16, 8, false>(a.ep, b, oy, ox, c0, v);
-            epilogue_store<__nv_bfloat16, 16, 8>(a.ep, b, oy, ox, c0, v, !has_head);
-            if (has_head) {
-              const int nv = min(16, a.ep.N - c0);
-              for (int jh = 0; jh < a.ep.planar_c; ++jh) {
-                float acc = head[jh];
-#pragma unroll
-                for (int i = 0; i < 16; ++i)
-                  if (i < nv) acc = fmaf(__ldg(a.head_w + (size_t)jh * a.ep.N + c0 + i), v[i], acc);
-                head[jh] = acc;
-              }
-            }
-          }
-        }
-        if (has_head && valid) {
-          for (int jh = 0; jh < a.ep.planar_c; ++jh)
-            a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * a.ep.H_out + oy) * a.ep.W_out + ox] =
-                head[jh] + __ldg(a.head_b + jh);
-        }
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(T_empty(rt.stage));
-      rt.next();
-    }
+    // ================================================================= epilogue (warps 2..9)
+    EpiSmem es;
+    es.bias = s_bias; es.temb = s_temb;
+    es.head_w = a.head_w ? s_head : nullptr; es.head_b = s_headb; es.hpart = s_hpart;
+    if (a.ep.act == SRD_ACT_MISH)
+      epilogue_role<SRD_ACT_MISH>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
+    else if (a.ep.act == SRD_ACT_LRELU02)
+      epilogue_role<SRD_ACT_LRELU02>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
+    else
+      epilogue_role<SRD_ACT_NONE>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
   }
 
   tc_fence_before();
@@ -420,14 +621,21 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   a.ep = make_epi(d, nullptr);
   a.head_w = d.head_w; a.head_b = d.head_b;
   a.err_flag = err_flag;
+  {
+    auto ok8 = [](const void* p, int ct, int coff) { return !p || ((ct % 8) == 0 && (coff % 8) == 0); };
+    a.fast = (d.N % 16 == 0) && (!d.temb || d.temb_bstride == 0) && d.temb_bstride == 0 &&
+             ok8(d.out, d.out_ct, d.out_coff) && ok8(d.out2, d.out2_ct, d.out2_coff) &&
+             ok8(d.res1, d.res1_ct, d.res1_coff) && ok8(d.res2, d.res2_ct, d.res2_coff) &&
+             (!d.planar || d.head_w);
+  }
   // shared memory: A ring + B ring + barriers
   const int B_BYTES = a.Npad * 128;
-  const int budget = 216 * 1024;
+  const int budget = 204 * 1024;
   a.a_stages = (a.MT == 2) ? 3 : 4;
   int bst = (budget - a.a_stages * a.MT * A_BYTES) / B_BYTES;
   a.b_stages = bst > MAX_STAGES ? MAX_STAGES : bst;
   SRD_CHECK(a.b_stages >= 2, "conv_tc: not enough shared memory for the weight ring");
-  plan->smem = a.a_stages * a.MT * A_BYTES + a.b_stages * B_BYTES + 8 * (4 * MAX_STAGES + 4) + 16 + 1024;
+  plan->smem = a.a_stages * a.MT * A_BYTES + a.b_stages * B_BYTES + BAR_BYTES + VEC_BYTES + 1024;
   plan->grid = a.n_items < n_sm ? a.n_items : n_sm;
 
   // ---- tensor maps
