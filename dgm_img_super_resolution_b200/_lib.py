@@ -52,6 +52,7 @@ class SrdPSampleArgs(C.Structure):
         ("img_out", C.c_void_p), ("img_lr_up", C.c_void_p), ("res_rescale", C.c_float),
         ("clip_input", C.c_int32),
         ("nhwc_out", C.c_void_p), ("nhwc_ct", C.c_int32), ("act_dtype", C.c_int32),
+        ("seed_ptr", C.c_void_p),
     ]
 
 
@@ -67,6 +68,7 @@ SYMBOLS = {
     "srd_conv_plan_kernel": (C.c_int, [_vp]),
     "srd_conv_run": (C.c_int, [_vp, _vp, _vp]),
     "srd_watchdog_flag": (C.c_int, []),
+    "srd_tc_set_mode": (C.c_int, [_i32, _i32]),
     "srd_time_table": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "srd_p_sample_step": (C.c_int, [C.POINTER(SrdPSampleArgs), _vp]),
     "srd_randn": (C.c_int, [_vp, _i32, _i32, _u64, _u32, _u32, _vp]),
@@ -98,10 +100,13 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         abi = (C.sizeof(SrdConvDesc), C.sizeof(SrdPSampleArgs), SrdConvDesc.head_b.offset,
-               SrdPSampleArgs.act_dtype.offset)
+               SrdPSampleArgs.seed_ptr.offset)
         got = tuple(L.srd_abi_sizeof(i) for i in range(4))
         if abi != got:
             raise SrdError("ctypes structs disagree with include/srdiff_b200.h: %s vs %s" % (abi, got))
+        # tuning / validation switches of the tcgen05 kernel (see srd_tc_set_mode in the header)
+        if "SRD_TC_A_MODE" in os.environ or "SRD_TC_B_RESIDENT" in os.environ:
+            L.srd_tc_set_mode(int(os.environ.get("SRD_TC_A_MODE", "0")), int(os.environ.get("SRD_TC_B_RESIDENT", "1")))
         _lib = L
     return _lib
 

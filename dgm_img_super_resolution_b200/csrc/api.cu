@@ -24,6 +24,7 @@ TcPlan* tc_plan_new();
 void tc_plan_delete(TcPlan*);
 int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag);
 int launch_conv_tc(const TcPlan& plan, const float* temb, cudaStream_t stream);
+void tc_set_mode(int a_mode, int b_resident);
 
 static int* g_err_flag_dev = nullptr;   // device-visible pointer to a host-mapped int
 static int* g_err_flag_host = nullptr;
@@ -95,7 +96,7 @@ int srd_abi_sizeof(int32_t which) {
     case 0: return (int)sizeof(SrdConvDesc);
     case 1: return (int)sizeof(SrdPSampleArgs);
     case 2: return (int)offsetof(SrdConvDesc, head_b);
-    case 3: return (int)offsetof(SrdPSampleArgs, act_dtype);
+    case 3: return (int)offsetof(SrdPSampleArgs, seed_ptr);
     default: return -1;
   }
 }
@@ -143,6 +144,12 @@ int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream) {
   SRD_CHECK(plan != nullptr, "srd_conv_run: NULL plan");
   if (plan->kernel == SRD_KERNEL_TC) return launch_conv_tc(*plan->tc, temb, (cudaStream_t)stream);
   return launch_conv_direct(plan->desc, temb, (cudaStream_t)stream);
+}
+
+int srd_tc_set_mode(int32_t a_mode, int32_t b_resident) {
+  SRD_CHECK(a_mode >= 0 && a_mode <= 2, "srd_tc_set_mode: a_mode must be 0, 1 or 2");
+  tc_set_mode(a_mode, b_resident ? 1 : 0);
+  return 0;
 }
 
 /* Non-zero after a tcgen05 pipeline watchdog fired (code = which wait timed out). */

@@ -31,6 +31,9 @@ constexpr int TC_THREADS = 320;          // TMA warp + MMA warp + 8 epilogue war
 constexpr int TILE_W = 8, TILE_H = 16;
 constexpr int BOX_ROWS = TILE_H + 2;
 constexpr int A_BYTES = BOX_ROWS * TILE_W * 128;   // 18432: one {64ch x 8px x 18rows} bf16 box
+constexpr int HALO_W = TILE_W + 2;
+constexpr int A_HALO_BYTES = BOX_ROWS * HALO_W * 128;      // 23040: one {64ch x 10px x 18rows} box (all 9 taps)
+constexpr int A_HALO_STAGE = (A_HALO_BYTES + 1023) / 1024 * 1024;
 constexpr int MAX_STAGES = 8;
 constexpr int BAR_BYTES = 512;           // mbarriers + TMEM slot
 constexpr int VEC_BYTES = (512 + 1024 + 4 + 2 * 128 * 4) * 4;   // epilogue vectors (see conv_tc_kernel)
@@ -53,6 +56,13 @@ struct TcArgs {
   const float* head_b;
   int* err_flag;
   int fast;                // epilogue fast path eligible (N % 16 == 0, uniform temb, aligned windows)
+  int a_mode;              // 0: one box per (chunk, kx), ky by 1024 B row offsets (always-aligned descriptors)
+                           // 1|2: ONE halo box per chunk, (ky,kx) by 128 B-granular descriptor start offsets
+                           //      (2: descriptor base_offset = (addr >> 7) & 7)
+  int a_stage_bytes;       // bytes of one A tile slot inside a stage
+  int b_resident;          // all weight k-blocks stay in shared memory for the whole kernel
+  int kb_total;
+  int b_region_bytes;      // bytes of the weight region (ring or resident)
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -129,6 +139,11 @@ __device__ __forceinline__ void tc_ld_wait() { asm volatile("tcgen05.wait::ld.sy
 // K-major, 128B-swizzled operand tile: rows of 64 bf16 (128 B), 8-row groups 1024 B apart.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(1024 >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+
+__device__ __forceinline__ uint64_t umma_desc_sw128_ex(uint32_t saddr, uint32_t sbo_bytes, uint32_t base_off) {
+  return (uint64_t)((saddr >> 4) & 0x3FFF) | ((uint64_t)(sbo_bytes >> 4) << 32) | (1ull << 46) |
+         ((uint64_t)(base_off & 7u) << 49) | (2ull << 61);
 }
 
 struct Ring {
@@ -385,8 +400,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int B_BYTES = a.Npad * 128;
   const uint32_t a_base = smem_base;
-  const uint32_t b_base = a_base + (uint32_t)a.a_stages * a.MT * A_BYTES;
-  const uint32_t bar_base = b_base + (uint32_t)a.b_stages * B_BYTES;
+  const uint32_t b_base = a_base + (uint32_t)a.a_stages * a.MT * a.a_stage_bytes;
+  const uint32_t bar_base = b_base + (uint32_t)a.b_region_bytes;
   // barrier layout (8 B each): A_full[8] A_empty[8] B_full[8] B_empty[8] T_full[2] T_empty[2]
   auto A_full = [&](int s) { return bar_base + 8u * s; };
   auto A_empty = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
@@ -395,6 +410,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   auto T_full = [&](int s) { return bar_base + 8u * (4 * MAX_STAGES + s); };
   auto T_empty = [&](int s) { return bar_base + 8u * (4 * MAX_STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (4 * MAX_STAGES + 4);
+  const uint32_t B_res = bar_base + 8u * (4 * MAX_STAGES + 5);
   uint8_t* gen_base = smem_raw + (bar_base - smem_u32(smem_raw));       // generic pointer to bar_base
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + 8 * (4 * MAX_STAGES + 4));
   float* vec = reinterpret_cast<float*>(gen_base + BAR_BYTES);
@@ -408,6 +424,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int s = 0; s < a.a_stages; ++s) { mbar_init(A_full(s), 1); mbar_init(A_empty(s), 1); }
     for (int s = 0; s < a.b_stages; ++s) { mbar_init(B_full(s), 1); mbar_init(B_empty(s), 1); }
     for (int s = 0; s < 2; ++s) { mbar_init(T_full(s), 1); mbar_init(T_empty(s), 8); }
+    mbar_init(B_res, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int s = 0; s < a.n_src; ++s)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA[s]) : "memory");
@@ -440,6 +457,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // ================================================================= TMA producer
     if (lane == 0) {
       Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages};
+      if (a.b_resident) {
+        mbar_expect_tx(B_res, (uint32_t)(a.kb_total * B_BYTES));
+        for (int kb = 0; kb < a.kb_total; ++kb)
+          tma_load_2d(b_base + (uint32_t)kb * B_BYTES, &a.tmB, B_res, 0, kb * a.Npad);
+      }
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         const int phase = item / a.items_per_phase;
         const int t0 = (item % a.items_per_phase) * a.MT;
@@ -449,6 +471,29 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         int kb = phase * a.kb_per_phase;
         for (int s = 0; s < a.n_src; ++s) {
           for (int ch = 0; ch < a.nchunk[s]; ++ch) {
+            if (a.a_mode) {
+              // ---- one halo box per (source, chunk): all taps come from it
+              mbar_wait(A_empty(ra.stage), ra.phase ^ 1, a.err_flag, 1);
+              mbar_expect_tx(A_full(ra.stage), (uint32_t)(a.MT * A_HALO_BYTES));
+              for (int mt = 0; mt < a.MT; ++mt) {
+                const int tt = t0 + mt;
+                const int rowblk = tt / a.n_colblk, colblk = tt % a.n_colblk;
+                const int V0 = rowblk * TILE_H + a.vstart, x0 = colblk * TILE_W;
+                tma_load_3d(a_base + (uint32_t)(ra.stage * a.MT + mt) * a.a_stage_bytes, &a.tmA[s],
+                            A_full(ra.stage), ch * 64, x0, V0 - 1);
+              }
+              ra.next();
+              if (!a.b_resident) {
+                for (int j = 0; j < a.nkx * a.nky; ++j) {
+                  mbar_wait(B_empty(rb.stage), rb.phase ^ 1, a.err_flag, 2);
+                  mbar_expect_tx(B_full(rb.stage), (uint32_t)B_BYTES);
+                  tma_load_2d(b_base + (uint32_t)rb.stage * B_BYTES, &a.tmB, B_full(rb.stage), 0, kb * a.Npad);
+                  rb.next();
+                  ++kb;
+                }
+              }
+              continue;
+            }
             for (int kxi = 0; kxi < a.nkx; ++kxi) {
               const int kxp = kx0 + kxi;
               for (int ld = 0; ld < n_loads(a); ++ld) {
@@ -458,7 +503,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                   const int tt = t0 + mt;
                   const int rowblk = tt / a.n_colblk, colblk = tt % a.n_colblk;
                   const int V0 = rowblk * TILE_H + a.vstart, x0 = colblk * TILE_W;
-                  const uint32_t dst = a_base + (uint32_t)(ra.stage * a.MT + mt) * A_BYTES;
+                  const uint32_t dst = a_base + (uint32_t)(ra.stage * a.MT + mt) * a.a_stage_bytes;
                   if (a.stride == 1)
                     tma_load_3d(dst, &a.tmA[s], A_full(ra.stage), ch * 64, x0 + kxp, V0 - 1);
                   else
@@ -466,13 +511,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
                                 ld, V0);
                 }
                 ra.next();
-                const int nt = n_taps(a, ld, ky0);
-                for (int j = 0; j < nt; ++j) {
-                  mbar_wait(B_empty(rb.stage), rb.phase ^ 1, a.err_flag, 2);
-                  mbar_expect_tx(B_full(rb.stage), (uint32_t)B_BYTES);
-                  tma_load_2d(b_base + (uint32_t)rb.stage * B_BYTES, &a.tmB, B_full(rb.stage), 0, kb * a.Npad);
-                  rb.next();
-                  ++kb;
+                if (!a.b_resident) {
+                  const int nt = n_taps(a, ld, ky0);
+                  for (int j = 0; j < nt; ++j) {
+                    mbar_wait(B_empty(rb.stage), rb.phase ^ 1, a.err_flag, 2);
+                    mbar_expect_tx(B_full(rb.stage), (uint32_t)B_BYTES);
+                    tma_load_2d(b_base + (uint32_t)rb.stage * B_BYTES, &a.tmB, B_full(rb.stage), 0, kb * a.Npad);
+                    rb.next();
+                    ++kb;
+                  }
                 }
               }
             }
@@ -484,38 +531,68 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     // ================================================================= MMA issuer
     if (lane == 0) {
       Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages}, rt{0, 0, 2};
+      if (a.b_resident) {
+        mbar_wait(B_res, 0, a.err_flag, 7);
+        tc_fence_after();
+      }
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         const int phase = item / a.items_per_phase;
-        const int pr = phase / S;
-        int ky0 = a.ky0;
-        if (S > 1) ky0 = (pr >= S / 2) ? 1 : 0;
+        const int pr = phase / S, ps = phase % S;
+        int ky0 = a.ky0, kx0 = a.kx0;
+        if (S > 1) { ky0 = (pr >= S / 2) ? 1 : 0; kx0 = (ps >= S / 2) ? 1 : 0; }
         mbar_wait(T_empty(rt.stage), rt.phase ^ 1, a.err_flag, 3);
         tc_fence_after();
         uint32_t kcount = 0;
+        int kb = phase * a.kb_per_phase;
+        // one tap = MT x 4 MMAs (K = 64) against one weight k-block
+        auto issue_tap = [&](uint32_t a_stage_addr, uint32_t a_off, uint32_t sbo, bool halo) {
+          uint32_t b_addr;
+          if (a.b_resident) {
+            b_addr = b_base + (uint32_t)kb * B_BYTES;
+          } else {
+            mbar_wait(B_full(rb.stage), rb.phase, a.err_flag, 5);
+            tc_fence_after();
+            b_addr = b_base + (uint32_t)rb.stage * B_BYTES;
+          }
+          for (int mt = 0; mt < a.MT; ++mt) {
+            const uint32_t a_addr = a_stage_addr + (uint32_t)mt * a.a_stage_bytes + a_off;
+            const uint32_t d = tmem_base + (uint32_t)((rt.stage * a.MT + mt) * a.Npad);
+#pragma unroll
+            for (int k4 = 0; k4 < 4; ++k4) {
+              const uint32_t aa = a_addr + k4 * 32;
+              const uint64_t ad = halo ? umma_desc_sw128_ex(aa, sbo, a.a_mode == 2 ? (aa >> 7) : 0u)
+                                       : umma_desc_sw128(aa);
+              tc_mma_bf16(d, ad, umma_desc_sw128(b_addr + k4 * 32), a.idesc, (kcount | (uint32_t)k4) != 0u);
+            }
+          }
+          if (!a.b_resident) {
+            tc_commit(B_empty(rb.stage));
+            rb.next();
+          }
+          ++kb;
+          ++kcount;
+        };
         for (int s = 0; s < a.n_src; ++s) {
           for (int ch = 0; ch < a.nchunk[s]; ++ch) {
+            if (a.a_mode) {
+              mbar_wait(A_full(ra.stage), ra.phase, a.err_flag, 4);
+              tc_fence_after();
+              const uint32_t st_addr = a_base + (uint32_t)(ra.stage * a.MT) * a.a_stage_bytes;
+              for (int kxi = 0; kxi < a.nkx; ++kxi)
+                for (int kyi = 0; kyi < a.nky; ++kyi)
+                  issue_tap(st_addr, (uint32_t)((ky0 + kyi) * HALO_W + (kx0 + kxi)) * 128u, HALO_W * 128u, true);
+              tc_commit(A_empty(ra.stage));
+              ra.next();
+              continue;
+            }
             for (int kxi = 0; kxi < a.nkx; ++kxi) {
               for (int ld = 0; ld < n_loads(a); ++ld) {
                 mbar_wait(A_full(ra.stage), ra.phase, a.err_flag, 4);
                 tc_fence_after();
+                const uint32_t st_addr = a_base + (uint32_t)(ra.stage * a.MT) * a.a_stage_bytes;
                 const int nt = n_taps(a, ld, ky0);
-                for (int j = 0; j < nt; ++j) {
-                  mbar_wait(B_full(rb.stage), rb.phase, a.err_flag, 5);
-                  tc_fence_after();
-                  const uint32_t off = (uint32_t)tap_off(a, ld, j, ky0) * (TILE_W * 128);
-                  const uint32_t b_addr = b_base + (uint32_t)rb.stage * B_BYTES;
-                  for (int mt = 0; mt < a.MT; ++mt) {
-                    const uint32_t a_addr = a_base + (uint32_t)(ra.stage * a.MT + mt) * A_BYTES + off;
-                    const uint32_t d = tmem_base + (uint32_t)((rt.stage * a.MT + mt) * a.Npad);
-#pragma unroll
-                    for (int k4 = 0; k4 < 4; ++k4)
-                      tc_mma_bf16(d, umma_desc_sw128(a_addr + k4 * 32), umma_desc_sw128(b_addr + k4 * 32),
-                                  a.idesc, (kcount | (uint32_t)k4) != 0u);
-                  }
-                  tc_commit(B_empty(rb.stage));
-                  rb.next();
-                  ++kcount;
-                }
+                for (int j = 0; j < nt; ++j)
+                  issue_tap(st_addr, (uint32_t)tap_off(a, ld, j, ky0) * (TILE_W * 128), 1024u, false);
                 tc_commit(A_empty(ra.stage));
                 ra.next();
               }
@@ -563,6 +640,11 @@ static EncodeTiledFn get_encode_fn() {
   fn = (EncodeTiledFn)p;
   return fn;
 }
+
+// tuning / validation switches (srd_tc_set_mode): A-operand mode for stride-1 convs, resident weights
+static int g_a_mode = 1;
+static int g_b_resident = 1;
+void tc_set_mode(int a_mode, int b_resident) { g_a_mode = a_mode; g_b_resident = b_resident; }
 
 int tc_supported(const SrdConvDesc& d, const char** why) {
   const char* w = nullptr;
@@ -628,14 +710,30 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
              ok8(d.res1, d.res1_ct, d.res1_coff) && ok8(d.res2, d.res2_ct, d.res2_coff) &&
              (!d.planar || d.head_w);
   }
-  // shared memory: A ring + B ring + barriers
+  // shared memory: A ring + B ring (or resident weights) + barriers + epilogue vectors
   const int B_BYTES = a.Npad * 128;
-  const int budget = 204 * 1024;
-  a.a_stages = (a.MT == 2) ? 3 : 4;
-  int bst = (budget - a.a_stages * a.MT * A_BYTES) / B_BYTES;
-  a.b_stages = bst > MAX_STAGES ? MAX_STAGES : bst;
-  SRD_CHECK(a.b_stages >= 2, "conv_tc: not enough shared memory for the weight ring");
-  plan->smem = a.a_stages * a.MT * A_BYTES + a.b_stages * B_BYTES + BAR_BYTES + VEC_BYTES + 1024;
+  const int budget = 227 * 1024 - BAR_BYTES - VEC_BYTES - 1024;
+  a.a_mode = (d.stride == 1) ? g_a_mode : 0;
+  a.a_stage_bytes = a.a_mode ? A_HALO_STAGE : A_BYTES;
+  a.kb_total = n_phase * kb;
+  const int stage_bytes = a.MT * a.a_stage_bytes;
+  const long long res_bytes = (long long)a.kb_total * B_BYTES;
+  a.b_resident = g_b_resident && (res_bytes + 2LL * stage_bytes <= budget) && res_bytes < (1 << 20);
+  int b_bytes_total;
+  if (a.b_resident) {
+    int ast = (int)((budget - res_bytes) / stage_bytes);
+    a.a_stages = ast > 4 ? 4 : ast;
+    a.b_stages = 1;
+    b_bytes_total = (int)res_bytes;
+  } else {
+    a.a_stages = a.a_mode ? (a.MT == 2 ? 2 : 3) : ((a.MT == 2) ? 3 : 4);
+    int bst = (budget - a.a_stages * stage_bytes) / B_BYTES;
+    a.b_stages = bst > MAX_STAGES ? MAX_STAGES : bst;
+    SRD_CHECK(a.b_stages >= 2, "conv_tc: not enough shared memory for the weight ring");
+    b_bytes_total = a.b_stages * B_BYTES;
+  }
+  a.b_region_bytes = b_bytes_total;
+  plan->smem = a.a_stages * stage_bytes + b_bytes_total + BAR_BYTES + VEC_BYTES + 1024;
   plan->grid = a.n_items < n_sm ? a.n_items : n_sm;
 
   // ---- tensor maps
@@ -646,7 +744,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
     if (d.stride == 1) {
       cuuint64_t dims[3] = {(cuuint64_t)s.cin, (cuuint64_t)Wp, (cuuint64_t)d.B * Hp};
       cuuint64_t strides[2] = {(cuuint64_t)s.ct * 2, (cuuint64_t)Wp * s.ct * 2};
-      cuuint32_t box[3] = {64, TILE_W, BOX_ROWS};
+      cuuint32_t box[3] = {64, (cuuint32_t)(a.a_mode ? HALO_W : TILE_W), BOX_ROWS};
       cuuint32_t es[3] = {1, 1, 1};
       r = enc(&a.tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

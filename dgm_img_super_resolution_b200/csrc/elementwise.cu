@@ -68,6 +68,7 @@ template <int V, typename T>
 __global__ void __launch_bounds__(256) p_sample_kernel(const SrdPSampleArgs a) {
   const int HW = a.H * a.W;
   const int nq = HW / V;                       // V divides W (checked on the host)
+  const uint64_t seed = a.seed_ptr ? __ldg(reinterpret_cast<const unsigned long long*>(a.seed_ptr)) : a.seed;
   const long long total = (long long)a.B * nq;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
@@ -107,13 +108,13 @@ __global__ void __launch_bounds__(256) p_sample_kernel(const SrdPSampleArgs a) {
         // quad index over the image's [C][H][W] element order, 4 elements per Philox call
         float z4[4];
         if (V == 4) {
-          normal4(a.seed, (uint32_t)((c * HW + pix) >> 2), a.image_offset + b, a.step, z4);
+          normal4(seed, (uint32_t)((c * HW + pix) >> 2), a.image_offset + b, a.step, z4);
 #pragma unroll
           for (int v = 0; v < V; ++v) zv[v] = z4[v];
         } else {
           for (int v = 0; v < V; ++v) {
             const int e = c * HW + pix + v;
-            normal4(a.seed, (uint32_t)(e >> 2), a.image_offset + b, a.step, z4);
+            normal4(seed, (uint32_t)(e >> 2), a.image_offset + b, a.step, z4);
             zv[v] = z4[e & 3];
           }
         }

@@ -540,7 +540,7 @@ def coef_table(diffusion):
 
 def p_sample_step(x, eps, noise, coef, t_i32, x_out, clip_denoised=True, seed=0, step=0, image_offset=0,
                   x0_out=None, img_out=None, img_lr_up=None, res_rescale=1.0, clip_input=True, nhwc_out=None,
-                  act_dtype=L.BF16):
+                  act_dtype=L.BF16, seed_dev=None):
     a = L.SrdPSampleArgs()
     B, C_, H, W = x.shape
     a.x, a.eps, a.noise = x.data_ptr(), eps.data_ptr(), (noise.data_ptr() if noise is not None else None)
@@ -556,6 +556,7 @@ def p_sample_step(x, eps, noise, coef, t_i32, x_out, clip_denoised=True, seed=0,
     if nhwc_out is not None:
         a.nhwc_out, a.nhwc_ct = nhwc_out.ptr, nhwc_out.ct
     a.act_dtype = act_dtype
+    a.seed_ptr = seed_dev.data_ptr() if seed_dev is not None else None
     L.check(L.lib().srd_p_sample_step(C.byref(a), _stream()), "srd_p_sample_step")
 
 
@@ -587,6 +588,7 @@ class SamplerPlan:
         self.res_rescale = float(hp["res_rescale"])
         self.clip_input = bool(hp["clip_input"])
         self.noise_buf = None
+        self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)   # Philox seed, read by the kernels
         self.graphs = {}
         self.sig = (params_signature(diffusion), self.T, hp["res_rescale"], hp["clip_input"])
 
@@ -610,7 +612,8 @@ class SamplerPlan:
                       image_offset, x0_out=x0_out,
                       img_out=self.img if (last and fuse_img) else None, img_lr_up=self.img_lr_up,
                       res_rescale=self.res_rescale, clip_input=self.clip_input,
-                      nhwc_out=None if last else self.unet_prog.xin, act_dtype=self.prec.dtype)
+                      nhwc_out=None if last else self.unet_prog.xin, act_dtype=self.prec.dtype,
+                      seed_dev=self.seed_dev)
 
     def loop(self, noises, seed, image_offset):
         self.load_x()
@@ -627,8 +630,10 @@ class SamplerPlan:
 
     def run_graph(self, use_noise_buf, seed, image_offset):
         """Replay (capturing on first use) encode + the whole T-step loop as one CUDA graph.
-        Philox seed/offset are baked into the captured kernel arguments, so they key the graph."""
-        key = (use_noise_buf, seed if not use_noise_buf else 0, image_offset if not use_noise_buf else 0)
+        The Philox seed lives in device memory (`seed_dev`), so a new seed does not need a new graph;
+        the shard's image offset is baked into the kernel arguments and keys the graph."""
+        self.seed_dev.fill_(seed & 0x7FFFFFFFFFFFFFFF)
+        key = (use_noise_buf, image_offset if not use_noise_buf else 0)
         g = self.graphs.get(key)
         if g is None:
             if len(self.graphs) >= 4:

@@ -492,7 +492,7 @@ class GaussianDiffusion(nn.Module):
         use_torch_noise = runtime.noise == "torch" and plan.noise_bytes() <= runtime.noise_budget_bytes
         runtime.seed_counter += 1
         seed = (torch.cuda.default_generators[device.index or 0].initial_seed() * 1000003 + runtime.seed_counter) \
-            & 0xFFFFFFFFFFFFFFFF
+            & 0x7FFFFFFFFFFFFFFF
         # ---- x_T :1070 (drawn before the RRDB forward, like the reference)
         if use_torch_noise:
             plan.x.copy_(torch.randn(shape, device=device))
@@ -510,6 +510,7 @@ class GaussianDiffusion(nn.Module):
         if not eager:
             plan.run_graph(use_torch_noise, seed, runtime.image_offset)
         else:
+            plan.seed_dev.fill_(seed)
             plan.encode()
             plan.load_x()
             it = reversed(range(T))

@@ -93,7 +93,7 @@ typedef struct SrdConvPlan SrdConvPlan;
 const char* srd_last_error(void);
 int srd_version(void);
 /* ABI self-check for FFI bindings: which = 0 -> sizeof(SrdConvDesc), 1 -> sizeof(SrdPSampleArgs),
- * 2 -> offsetof(SrdConvDesc, head_b), 3 -> offsetof(SrdPSampleArgs, act_dtype). */
+ * 2 -> offsetof(SrdConvDesc, head_b), 3 -> offsetof(SrdPSampleArgs, seed_ptr). */
 int srd_abi_sizeof(int32_t which);
 /* 1 if the tcgen05/TMA path can serve this descriptor (bf16, channel/stride alignment...). */
 int srd_conv_tc_supported(const SrdConvDesc* desc);
@@ -104,6 +104,11 @@ int srd_conv_plan_destroy(SrdConvPlan* plan);
 int srd_conv_plan_kernel(const SrdConvPlan* plan);
 /* Launch.  `temb` overrides desc.temb when non-NULL (per-step row of the time table). */
 int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream);
+/* Tuning switches for plans created afterwards.  a_mode: 0 = one TMA box per (chunk, kx) with
+ * 1024 B-aligned UMMA descriptors; 1|2 = one halo box per chunk, taps addressed by 128 B-granular
+ * descriptor start offsets (2 also sets the descriptor base_offset).  b_resident: keep all weight
+ * k-blocks in shared memory when they fit. */
+int srd_tc_set_mode(int32_t a_mode, int32_t b_resident);
 /* Non-zero after the tcgen05 pipeline watchdog fired (value = which wait timed out). */
 int srd_watchdog_flag(void);
 
@@ -135,6 +140,8 @@ typedef struct {
   float* x_out; float* x0_out;
   float* img_out; const float* img_lr_up; float res_rescale; int32_t clip_input;
   void* nhwc_out; int32_t nhwc_ct; int32_t act_dtype;
+  const uint64_t* seed_ptr;   /* optional: Philox seed read from device memory (overrides `seed`), so a
+                                 captured CUDA graph can be replayed with a new seed */
 } SrdPSampleArgs;
 int srd_p_sample_step(const SrdPSampleArgs* args, void* stream);
 
