@@ -146,6 +146,29 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_ex(uint32_t saddr, uint32_t 
          ((uint64_t)(base_off & 7u) << 49) | (2ull << 61);
 }
 
+// Descriptor split into 32-bit halves: lo = start address >> 4 (LBO = 0); hi = SBO >> 4 | version 1 (bit 46)
+// | SWIZZLE_128B (bits 61-63).  Advancing the start address is an add on the low word.
+constexpr uint32_t DESC_HI_1024 = (1024u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t DESC_HI_HALO = ((uint32_t)(TILE_W + 2) * 128u >> 4) | (1u << 14) | (2u << 29);
+__device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi) {
+  uint64_t d;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
+  return d;
+}
+
+// Elect exactly one lane of a converged warp.  Unlike `lane == 0`, the compiler knows the guarded
+// region runs on a single thread, so tcgen05/TMA operands live in uniform registers without
+// per-instruction ELECT/BRA.U.ANY waterfall loops.
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n\t.reg .pred P1;\n\t"
+      "elect.sync _|P1, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P1;\n\t}"
+      : "=r"(pred));
+  return pred != 0;
+}
+
 struct Ring {
   int stage, phase, n;
   __device__ __forceinline__ void next() { if (++stage == n) { stage = 0; phase ^= 1; } }
@@ -201,13 +224,13 @@ __device__ __forceinline__ void st16_bf16(__nv_bfloat16* p, const float (&v)[16]
 }
 
 // Write one pixel's 16-channel chunk, plus the mirrored ring copies this pixel owns (reflect).
-__device__ __forceinline__ void store_chunk(__nv_bfloat16* base, int ct, size_t pix, int Wp, int Hp,
-                                            uint32_t edge, const float (&v)[16]) {
-  st16_bf16(base + pix * ct, v);
+// p points at the pixel's channel window (+ chunk offset); wp = padded pixels per row.
+__device__ __forceinline__ void store_chunk(__nv_bfloat16* p, int ct, long long wp, uint32_t edge,
+                                            const float (&v)[16]) {
+  st16_bf16(p, v);
   if (edge) {   // rare: only pixels in row/col 1 or H-2/W-2 of a reflect-ringed output
+    const long long dn = wp * ct;
     const bool top = edge & 1u, bot = edge & 2u, lef = edge & 4u, rig = edge & 8u;
-    const long long dn = (long long)Wp * ct;
-    __nv_bfloat16* p = base + pix * ct;
     if (top) st16_bf16(p - 2 * dn, v);
     if (bot) st16_bf16(p + 2 * dn, v);
     if (lef) st16_bf16(p - 2 * ct, v);
@@ -216,14 +239,38 @@ __device__ __forceinline__ void store_chunk(__nv_bfloat16* base, int ct, size_t 
     if (top && rig) st16_bf16(p - 2 * dn + 2 * ct, v);
     if (bot && lef) st16_bf16(p + 2 * dn - 2 * ct, v);
     if (bot && rig) st16_bf16(p + 2 * dn + 2 * ct, v);
-    (void)Hp;
   }
 }
+
+// alpha * act(x) + t with the activation resolved at compile time.
+template <int ACT>
+__device__ __forceinline__ float act_axpy(float x, float alpha, float t) {
+  if (ACT == SRD_ACT_MISH) {
+    // mish(x) = x * (1 - 2 / (n*(n+2) + 2)),  n = e^x   (1 ex2 + 1 rcp; see common.cuh)
+    float n, r;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(n) : "f"(fminf(x, 20.f) * 1.4426950408889634f));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(n, n + 2.f, 2.f)));
+    return fmaf(fmaf(-2.f * x, r, x), alpha, t);
+  }
+  if (ACT == SRD_ACT_LRELU02) return fmaf(fmaxf(x, 0.2f * x), alpha, t);
+  return fmaf(x, alpha, t);
+}
+
+// Per-tile, per-thread constants of the fast epilogue.
+struct TilePix {
+  bool valid;
+  uint32_t edge;
+  int b, oy, ox;
+  __nv_bfloat16* out;
+  __nv_bfloat16* out2;
+  const __nv_bfloat16* r1;
+  const __nv_bfloat16* r2;
+};
 
 // Fast path: N % 16 == 0, batch-uniform temb, 16-byte aligned channel windows.
 template <int ACT>
 __device__ __forceinline__ void epi_chunk_fast(const TcArgs& a, const EpiSmem& es, int c0, const uint32_t (&r)[16],
-                                               bool valid, size_t pix, uint32_t edge, const uint4 (&q1)[2],
+                                               const TilePix& tp, long long dn, const uint4 (&q1)[2],
                                                const uint4 (&q2)[2], float (&head)[4]) {
   float v[16];
   const float4* sb = reinterpret_cast<const float4*>(es.bias + c0);
@@ -232,12 +279,12 @@ __device__ __forceinline__ void epi_chunk_fast(const TcArgs& a, const EpiSmem& e
 #pragma unroll
   for (int q = 0; q < 4; ++q) {
     const float4 b4 = sb[q], t4 = st[q];
-    v[4 * q + 0] = fmaf(act_fast<ACT>(__uint_as_float(r[4 * q + 0]) + b4.x), alpha, t4.x);
-    v[4 * q + 1] = fmaf(act_fast<ACT>(__uint_as_float(r[4 * q + 1]) + b4.y), alpha, t4.y);
-    v[4 * q + 2] = fmaf(act_fast<ACT>(__uint_as_float(r[4 * q + 2]) + b4.z), alpha, t4.z);
-    v[4 * q + 3] = fmaf(act_fast<ACT>(__uint_as_float(r[4 * q + 3]) + b4.w), alpha, t4.w);
+    v[4 * q + 0] = act_axpy<ACT>(__uint_as_float(r[4 * q + 0]) + b4.x, alpha, t4.x);
+    v[4 * q + 1] = act_axpy<ACT>(__uint_as_float(r[4 * q + 1]) + b4.y, alpha, t4.y);
+    v[4 * q + 2] = act_axpy<ACT>(__uint_as_float(r[4 * q + 2]) + b4.z, alpha, t4.z);
+    v[4 * q + 3] = act_axpy<ACT>(__uint_as_float(r[4 * q + 3]) + b4.w, alpha, t4.w);
   }
-  if (a.ep.res1) {
+  if (tp.r1) {
     float f[8];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -246,7 +293,7 @@ __device__ __forceinline__ void epi_chunk_fast(const TcArgs& a, const EpiSmem& e
       for (int i = 0; i < 8; ++i) v[8 * h + i] = fmaf(a.ep.beta1, f[i], v[8 * h + i]);
     }
   }
-  if (a.ep.res2) {
+  if (tp.r2) {
     float f[8];
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
@@ -255,12 +302,9 @@ __device__ __forceinline__ void epi_chunk_fast(const TcArgs& a, const EpiSmem& e
       for (int i = 0; i < 8; ++i) v[8 * h + i] = fmaf(a.ep.beta2, f[i], v[8 * h + i]);
     }
   }
-  if (valid) {
-    const int Wp = a.ep.W_out + 2, Hp = a.ep.H_out + 2;
-    if (a.ep.out)
-      store_chunk(static_cast<__nv_bfloat16*>(a.ep.out) + a.ep.out_coff + c0, a.ep.out_ct, pix, Wp, Hp, edge, v);
-    if (a.ep.out2)
-      store_chunk(static_cast<__nv_bfloat16*>(a.ep.out2) + a.ep.out2_coff + c0, a.ep.out2_ct, pix, Wp, Hp, edge, v);
+  if (tp.valid) {
+    if (tp.out) store_chunk(tp.out + c0, a.ep.out_ct, dn, tp.edge, v);
+    if (tp.out2) store_chunk(tp.out2 + c0, a.ep.out2_ct, dn, tp.edge, v);   // out/out2 share H, W; dn uses out's ct
   }
   if (es.head_w) {
     for (int jh = 0; jh < a.ep.planar_c; ++jh) {
@@ -283,11 +327,15 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
   Ring rt{0, 0, 2};
   const int S = a.up;
   const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
-  const int half = (warp - 2) >> 2;             // two warps per quarter split the 16-column chunks
+  const int half = (warp - 2) >> 2;             // two warps share each lane quarter
   const int m = quarter * 32 + lane;
   const int g = m >> 3, px = m & 7;
   const int nchunks = a.Npad >> 4;
   const bool has_head = es.head_w != nullptr;
+  // MT == 2: each half owns one tile (all chunks); MT == 1: the halves split the 16-column chunks.
+  const bool split_tiles = (a.MT == 2);
+  const int c_begin = split_tiles ? 0 : half, c_step = split_tiles ? 1 : 2;
+  const int Ho = a.ep.H_out, Wo = a.ep.W_out;
   int hbuf = 0;
   for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
     const int phase = item / a.items_per_phase;
@@ -296,66 +344,80 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
     mbar_wait(t_full0 + 8u * rt.stage, rt.phase, a.err_flag, 6);
     tc_fence_after();
     bool released = false;
-    for (int mt = 0; mt < a.MT; ++mt) {
+    const int mt_lo = split_tiles ? half : 0, mt_hi = split_tiles ? half + 1 : a.MT;
+    for (int mt = mt_lo; mt < mt_hi; ++mt) {
       const int tt = t0 + mt;
-      const int rowblk = tt / a.n_colblk, colblk = tt % a.n_colblk;
-      const int V = rowblk * TILE_H + a.vstart + g;
+      const int rowblk = tt / a.n_colblk, colblk = tt - rowblk * a.n_colblk;
+      // virtual stacked row -> (image, row) without a per-thread division
+      const int V0 = rowblk * TILE_H + a.vstart;
+      int b = V0 / a.period;
+      int vv = V0 - b * a.period + g;
+      while (vv >= a.period) { vv -= a.period; ++b; }
+      const int y = vv - a.voff;
       const int x = colblk * TILE_W + px;
-      bool valid = (tt < a.tiles_per_phase) && (V < a.n_vrows) && (x < a.W_m);
-      int b = 0, y = 0;
-      if (valid) {
-        b = V / a.period;
-        y = V % a.period - a.voff;
-        valid = (y >= 0) && (y < a.H_m);
-      }
+      const bool valid = (tt < a.tiles_per_phase) && (V0 + g < a.n_vrows) && (x < a.W_m) && (y >= 0) && (y < a.H_m);
       const int oy = y * S + pr, ox = x * S + ps;
-      const int Ho = a.ep.H_out, Wo = a.ep.W_out;
-      const size_t pix = valid ? ((size_t)(b * (Ho + 2) + oy + 1) * (Wo + 2) + ox + 1) : 0;
-      uint32_t edge = 0;
-      if (valid && a.ep.border == SRD_BORDER_REFLECT)
-        edge = (oy == 1 ? 1u : 0u) | (oy == Ho - 2 ? 2u : 0u) | (ox == 1 ? 4u : 0u) | (ox == Wo - 2 ? 8u : 0u);
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                              (uint32_t)((rt.stage * a.MT + mt) * a.Npad);
       float head[4] = {0.f, 0.f, 0.f, 0.f};
-      const bool last_mt = (mt == a.MT - 1);
+      const bool last_tile = (mt == mt_hi - 1);
       if (a.fast) {
-        const __nv_bfloat16* r1p = a.ep.res1 ? static_cast<const __nv_bfloat16*>(a.ep.res1) + pix * a.ep.res1_ct + a.ep.res1_coff : nullptr;
-        const __nv_bfloat16* r2p = a.ep.res2 ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
-        uint4 n1[2] = {}, n2[2] = {};
-        if (valid && half < nchunks) {
-          if (r1p) { n1[0] = reinterpret_cast<const uint4*>(r1p + 16 * half)[0]; n1[1] = reinterpret_cast<const uint4*>(r1p + 16 * half)[1]; }
-          if (r2p) { n2[0] = reinterpret_cast<const uint4*>(r2p + 16 * half)[0]; n2[1] = reinterpret_cast<const uint4*>(r2p + 16 * half)[1]; }
-        }
-        for (int c = half; c < nchunks; c += 2) {
+        TilePix tp;
+        tp.valid = valid; tp.b = b; tp.oy = oy; tp.ox = ox;
+        const size_t pix = valid ? ((size_t)(b * (Ho + 2) + oy + 1) * (Wo + 2) + ox + 1) : 0;
+        tp.edge = 0;
+        if (valid && a.ep.border == SRD_BORDER_REFLECT)
+          tp.edge = (oy == 1 ? 1u : 0u) | (oy == Ho - 2 ? 2u : 0u) | (ox == 1 ? 4u : 0u) | (ox == Wo - 2 ? 8u : 0u);
+        tp.out = a.ep.out ? static_cast<__nv_bfloat16*>(a.ep.out) + pix * a.ep.out_ct + a.ep.out_coff : nullptr;
+        tp.out2 = a.ep.out2 ? static_cast<__nv_bfloat16*>(a.ep.out2) + pix * a.ep.out2_ct + a.ep.out2_coff : nullptr;
+        tp.r1 = (a.ep.res1 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res1) + pix * a.ep.res1_ct + a.ep.res1_coff : nullptr;
+        tp.r2 = (a.ep.res2 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
+        const long long dn = (long long)(Wo + 2);          // padded pixels per row; scaled by ct at use
+        // two residual register sets (A/B), alternated so prefetching needs no copies
+        uint4 A1[2] = {}, A2[2] = {}, B1[2] = {}, B2[2] = {};
+        auto ldres = [&](int c, uint4 (&x1)[2], uint4 (&x2)[2]) {
+          if (tp.r1) { const uint4* q = reinterpret_cast<const uint4*>(tp.r1 + 16 * c); x1[0] = q[0]; x1[1] = q[1]; }
+          if (tp.r2) { const uint4* q = reinterpret_cast<const uint4*>(tp.r2 + 16 * c); x2[0] = q[0]; x2[1] = q[1]; }
+        };
+        auto one = [&](int c, const uint4 (&c1)[2], const uint4 (&c2)[2], uint4 (&n1)[2], uint4 (&n2)[2]) {
           uint32_t r[16];
           tc_ld16(tbase + (uint32_t)(c * 16), r);
-          uint4 q1[2] = {n1[0], n1[1]}, q2[2] = {n2[0], n2[1]};
-          if (valid && c + 2 < nchunks) {      // prefetch the next chunk's residuals behind this chunk's math
-            if (r1p) { n1[0] = reinterpret_cast<const uint4*>(r1p + 16 * (c + 2))[0]; n1[1] = reinterpret_cast<const uint4*>(r1p + 16 * (c + 2))[1]; }
-            if (r2p) { n2[0] = reinterpret_cast<const uint4*>(r2p + 16 * (c + 2))[0]; n2[1] = reinterpret_cast<const uint4*>(r2p + 16 * (c + 2))[1]; }
-          }
+          if (c + c_step < nchunks) ldres(c + c_step, n1, n2);   // prefetch behind this chunk's math
           tc_ld_wait();
-          if (last_mt && c + 2 >= nchunks) {   // accumulator fully read: hand the TMEM stage back early
+          if (last_tile && c + c_step >= nchunks) {              // accumulator fully read: release the TMEM stage
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty0 + 8u * rt.stage);
             released = true;
           }
-          epi_chunk_fast<ACT>(a, es, c * 16, r, valid, pix, edge, q1, q2, head);
+          // store_chunk scales dn by the buffer's own ct
+          epi_chunk_fast<ACT>(a, es, c * 16, r, tp, dn, c1, c2, head);
+        };
+        int c = c_begin;
+        if (c < nchunks) ldres(c, A1, A2);
+        while (c < nchunks) {
+          one(c, A1, A2, B1, B2);
+          c += c_step;
+          if (c >= nchunks) break;
+          one(c, B1, B2, A1, A2);
+          c += c_step;
         }
-        if (has_head) {                        // combine the two halves' partial 1x1 sums
-          float* hp = es.hpart + ((size_t)hbuf * 128 + m) * 4;
-          if (half == 1) { hp[0] = head[0]; hp[1] = head[1]; hp[2] = head[2]; hp[3] = head[3]; }
-          asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-          if (half == 0 && valid) {
-            for (int jh = 0; jh < a.ep.planar_c; ++jh)
-              a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + hp[jh] + es.head_b[jh];
+        if (has_head) {
+          if (!split_tiles) {                  // combine the two halves' partial 1x1 sums
+            float* hp = es.hpart + ((size_t)hbuf * 128 + m) * 4;
+            if (half == 1) { hp[0] = head[0]; hp[1] = head[1]; hp[2] = head[2]; hp[3] = head[3]; }
+            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+            if (half == 0) { head[0] += hp[0]; head[1] += hp[1]; head[2] += hp[2]; head[3] += hp[3]; }
+            hbuf ^= 1;
           }
-          hbuf ^= 1;
+          if ((split_tiles || half == 0) && valid) {
+            for (int jh = 0; jh < a.ep.planar_c; ++jh)
+              a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
+          }
         }
       } else {
-        // generic path (ragged N, per-image temb rows, planar output): one warp per quarter does all chunks
-        if (half == 0) {
+        // generic path (ragged N, per-image temb rows, planar output): one warp per tile does all chunks
+        if (split_tiles || half == 0) {
           for (int c0 = 0; c0 < a.Npad; c0 += 16) {
             uint32_t r[16];
             tc_ld16(tbase + (uint32_t)c0, r);
@@ -455,7 +517,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int S = a.up;
   if (warp == 0) {
     // ================================================================= TMA producer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages};
       if (a.b_resident) {
         mbar_expect_tx(B_res, (uint32_t)(a.kb_total * B_BYTES));
@@ -529,8 +591,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   } else if (warp == 1) {
     // ================================================================= MMA issuer
-    if (lane == 0) {
+    if (elect_one_sync()) {
       Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages}, rt{0, 0, 2};
+      const uint32_t bB16 = (uint32_t)B_BYTES >> 4, aS16 = (uint32_t)a.a_stage_bytes >> 4;
+      const uint32_t a_lo_base = a_base >> 4, b_lo_base = b_base >> 4;
       if (a.b_resident) {
         mbar_wait(B_res, 0, a.err_flag, 7);
         tc_fence_after();
@@ -542,45 +606,48 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         if (S > 1) { ky0 = (pr >= S / 2) ? 1 : 0; kx0 = (ps >= S / 2) ? 1 : 0; }
         mbar_wait(T_empty(rt.stage), rt.phase ^ 1, a.err_flag, 3);
         tc_fence_after();
-        uint32_t kcount = 0;
+        uint32_t kcount = 0;     // 0 only for the first k-block of the item (accumulator overwrite)
         int kb = phase * a.kb_per_phase;
-        // one tap = MT x 4 MMAs (K = 64) against one weight k-block
-        auto issue_tap = [&](uint32_t a_stage_addr, uint32_t a_off, uint32_t sbo, bool halo) {
-          uint32_t b_addr;
+        // One tap = MT x 4 MMAs (K = 64) against one weight k-block.  The issuing thread is the
+        // critical resource (an MMA with N = 64 occupies the tensor pipe for only 32 cycles), so all
+        // descriptor arithmetic is 32-bit adds on the low word; the high words are constants.
+        const uint32_t d0 = tmem_base + (uint32_t)(rt.stage * a.MT) * (uint32_t)a.Npad;
+        auto issue_tap = [&](uint32_t a_lo, uint32_t a_hi) {
+          uint32_t b_lo;
           if (a.b_resident) {
-            b_addr = b_base + (uint32_t)kb * B_BYTES;
+            b_lo = b_lo_base + (uint32_t)kb * bB16;
           } else {
             mbar_wait(B_full(rb.stage), rb.phase, a.err_flag, 5);
             tc_fence_after();
-            b_addr = b_base + (uint32_t)rb.stage * B_BYTES;
+            b_lo = b_lo_base + (uint32_t)rb.stage * bB16;
           }
-          for (int mt = 0; mt < a.MT; ++mt) {
-            const uint32_t a_addr = a_stage_addr + (uint32_t)mt * a.a_stage_bytes + a_off;
-            const uint32_t d = tmem_base + (uint32_t)((rt.stage * a.MT + mt) * a.Npad);
-#pragma unroll
-            for (int k4 = 0; k4 < 4; ++k4) {
-              const uint32_t aa = a_addr + k4 * 32;
-              const uint64_t ad = halo ? umma_desc_sw128_ex(aa, sbo, a.a_mode == 2 ? (aa >> 7) : 0u)
-                                       : umma_desc_sw128(aa);
-              tc_mma_bf16(d, ad, umma_desc_sw128(b_addr + k4 * 32), a.idesc, (kcount | (uint32_t)k4) != 0u);
-            }
+          tc_mma_bf16(d0, mk_desc(a_lo, a_hi), mk_desc(b_lo, DESC_HI_1024), a.idesc, kcount);
+          tc_mma_bf16(d0, mk_desc(a_lo + 2, a_hi), mk_desc(b_lo + 2, DESC_HI_1024), a.idesc, 1u);
+          tc_mma_bf16(d0, mk_desc(a_lo + 4, a_hi), mk_desc(b_lo + 4, DESC_HI_1024), a.idesc, 1u);
+          tc_mma_bf16(d0, mk_desc(a_lo + 6, a_hi), mk_desc(b_lo + 6, DESC_HI_1024), a.idesc, 1u);
+          if (a.MT == 2) {
+            const uint32_t d1 = d0 + (uint32_t)a.Npad, a1 = a_lo + aS16;
+            tc_mma_bf16(d1, mk_desc(a1, a_hi), mk_desc(b_lo, DESC_HI_1024), a.idesc, kcount);
+            tc_mma_bf16(d1, mk_desc(a1 + 2, a_hi), mk_desc(b_lo + 2, DESC_HI_1024), a.idesc, 1u);
+            tc_mma_bf16(d1, mk_desc(a1 + 4, a_hi), mk_desc(b_lo + 4, DESC_HI_1024), a.idesc, 1u);
+            tc_mma_bf16(d1, mk_desc(a1 + 6, a_hi), mk_desc(b_lo + 6, DESC_HI_1024), a.idesc, 1u);
           }
           if (!a.b_resident) {
             tc_commit(B_empty(rb.stage));
             rb.next();
           }
           ++kb;
-          ++kcount;
+          kcount = 1u;
         };
         for (int s = 0; s < a.n_src; ++s) {
           for (int ch = 0; ch < a.nchunk[s]; ++ch) {
             if (a.a_mode) {
               mbar_wait(A_full(ra.stage), ra.phase, a.err_flag, 4);
               tc_fence_after();
-              const uint32_t st_addr = a_base + (uint32_t)(ra.stage * a.MT) * a.a_stage_bytes;
+              const uint32_t st_lo = a_lo_base + (uint32_t)(ra.stage * a.MT) * aS16 + (uint32_t)(ky0 * HALO_W + kx0) * 8u;
               for (int kxi = 0; kxi < a.nkx; ++kxi)
                 for (int kyi = 0; kyi < a.nky; ++kyi)
-                  issue_tap(st_addr, (uint32_t)((ky0 + kyi) * HALO_W + (kx0 + kxi)) * 128u, HALO_W * 128u, true);
+                  issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
               tc_commit(A_empty(ra.stage));
               ra.next();
               continue;
@@ -589,10 +656,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
               for (int ld = 0; ld < n_loads(a); ++ld) {
                 mbar_wait(A_full(ra.stage), ra.phase, a.err_flag, 4);
                 tc_fence_after();
-                const uint32_t st_addr = a_base + (uint32_t)(ra.stage * a.MT) * a.a_stage_bytes;
+                const uint32_t st_lo = a_lo_base + (uint32_t)(ra.stage * a.MT) * aS16;
                 const int nt = n_taps(a, ld, ky0);
                 for (int j = 0; j < nt; ++j)
-                  issue_tap(st_addr, (uint32_t)tap_off(a, ld, j, ky0) * (TILE_W * 128), 1024u, false);
+                  issue_tap(st_lo + (uint32_t)tap_off(a, ld, j, ky0) * (TILE_W * 8u), DESC_HI_1024);
                 tc_commit(A_empty(ra.stage));
                 ra.next();
               }

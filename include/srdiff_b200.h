@@ -105,9 +105,9 @@ int srd_conv_plan_kernel(const SrdConvPlan* plan);
 /* Launch.  `temb` overrides desc.temb when non-NULL (per-step row of the time table). */
 int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream);
 /* Tuning switches for plans created afterwards.  a_mode: 0 = one TMA box per (chunk, kx) with
- * 1024 B-aligned UMMA descriptors; 1|2 = one halo box per chunk, taps addressed by 128 B-granular
- * descriptor start offsets (2 also sets the descriptor base_offset).  b_resident: keep all weight
- * k-blocks in shared memory when they fit. */
+ * 1024 B-aligned UMMA descriptors; 1 = one halo box per chunk, taps addressed by 128 B-granular
+ * descriptor start offsets (default; validated on B200).  b_resident: keep all weight k-blocks
+ * in shared memory when they fit. */
 int srd_tc_set_mode(int32_t a_mode, int32_t b_resident);
 /* Non-zero after the tcgen05 pipeline watchdog fired (value = which wait timed out). */
 int srd_watchdog_flag(void);
