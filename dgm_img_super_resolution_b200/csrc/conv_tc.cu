@@ -41,6 +41,9 @@ constexpr int VEC_BYTES = (512 + 1024 + 4 + 2 * 128 * 4) * 4;   // epilogue vect
 struct TcArgs {
   CUtensorMap tmA[SRD_MAX_SRC];
   CUtensorMap tmB;
+  CUtensorMap tmO;         // output, box {64 ch, 8 px, 4 rows} = one epilogue warp's rows (TMA-staged epilogue)
+  CUtensorMap tmOrow;      // output, box {64 ch, 8 px, 1 row}
+  CUtensorMap tmR;         // residual res1, box {64 ch, 8 px, 4 rows}
   int n_src;
   int nchunk[SRD_MAX_SRC];
   int H_m, W_m;            // output positions per image (per phase)
@@ -63,6 +66,8 @@ struct TcArgs {
   int b_resident;          // all weight k-blocks stay in shared memory for the whole kernel
   int kb_total;
   int b_region_bytes;      // bytes of the weight region (ring or resident)
+  int epi_tma;             // TMA-staged epilogue (see epilogue_tma)
+  int epi_nbuf;            // staging buffers per epilogue half (1 | 2)
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -321,46 +326,61 @@ __device__ __forceinline__ void epi_chunk_fast(const TcArgs& a, const EpiSmem& e
   }
 }
 
+// Decode one tile for this thread: (image, row, col) of its output pixel, without divisions per thread.
+struct TileGeo {
+  int V0, x0;          // first virtual stacked row / first column of the tile
+  int b, y, x;         // this thread's image / row / col in the per-phase M grid
+  bool valid;
+};
+__device__ __forceinline__ TileGeo tile_geo(const TcArgs& a, int tt, int g, int px) {
+  TileGeo t;
+  const int rowblk = tt / a.n_colblk, colblk = tt - rowblk * a.n_colblk;
+  t.V0 = rowblk * TILE_H + a.vstart;
+  t.x0 = colblk * TILE_W;
+  int b = t.V0 / a.period;
+  int vv = t.V0 - b * a.period + g;
+  while (vv >= a.period) { vv -= a.period; ++b; }
+  t.b = b;
+  t.y = vv - a.voff;
+  t.x = t.x0 + px;
+  t.valid = (tt < a.tiles_per_phase) && (t.V0 + g < a.n_vrows) && (t.x < a.W_m) && (t.y >= 0) && (t.y < a.H_m);
+  return t;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Register epilogue: thread = pixel, direct 16 B global stores.  Used by the layers the TMA-staged
+// epilogue does not take (transposed-conv phases, stride 2, N % 64 != 0, fused 1x1 head, ragged W).
+// The two epilogue warpgroups (halves) ping-pong on the two TMEM accumulator stages: half h owns
+// the items with local index = h (mod 2), i.e. TMEM stage h.
+// ---------------------------------------------------------------------------------------------
 template <int ACT>
 __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es, uint32_t tmem_base,
                                               uint32_t t_full0, uint32_t t_empty0, int warp, int lane) {
-  Ring rt{0, 0, 2};
   const int S = a.up;
   const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
-  const int half = (warp - 2) >> 2;             // two warps share each lane quarter
+  const int half = (warp - 2) >> 2;
   const int m = quarter * 32 + lane;
   const int g = m >> 3, px = m & 7;
   const int nchunks = a.Npad >> 4;
   const bool has_head = es.head_w != nullptr;
-  // MT == 2: each half owns one tile (all chunks); MT == 1: the halves split the 16-column chunks.
-  const bool split_tiles = (a.MT == 2);
-  const int c_begin = split_tiles ? 0 : half, c_step = split_tiles ? 1 : 2;
   const int Ho = a.ep.H_out, Wo = a.ep.W_out;
-  int hbuf = 0;
-  for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+  const uint32_t t_full = t_full0 + 8u * half, t_empty = t_empty0 + 8u * half;
+  for (int it = half;; it += 2) {
+    const int item = blockIdx.x + it * gridDim.x;
+    if (item >= a.n_items) break;
     const int phase = item / a.items_per_phase;
     const int t0 = (item % a.items_per_phase) * a.MT;
     const int pr = phase / S, ps = phase % S;
-    mbar_wait(t_full0 + 8u * rt.stage, rt.phase, a.err_flag, 6);
+    mbar_wait(t_full, (uint32_t)(it >> 1) & 1u, a.err_flag, 6);
     tc_fence_after();
     bool released = false;
-    const int mt_lo = split_tiles ? half : 0, mt_hi = split_tiles ? half + 1 : a.MT;
-    for (int mt = mt_lo; mt < mt_hi; ++mt) {
-      const int tt = t0 + mt;
-      const int rowblk = tt / a.n_colblk, colblk = tt - rowblk * a.n_colblk;
-      // virtual stacked row -> (image, row) without a per-thread division
-      const int V0 = rowblk * TILE_H + a.vstart;
-      int b = V0 / a.period;
-      int vv = V0 - b * a.period + g;
-      while (vv >= a.period) { vv -= a.period; ++b; }
-      const int y = vv - a.voff;
-      const int x = colblk * TILE_W + px;
-      const bool valid = (tt < a.tiles_per_phase) && (V0 + g < a.n_vrows) && (x < a.W_m) && (y >= 0) && (y < a.H_m);
-      const int oy = y * S + pr, ox = x * S + ps;
-      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) +
-                             (uint32_t)((rt.stage * a.MT + mt) * a.Npad);
+    for (int mt = 0; mt < a.MT; ++mt) {
+      const TileGeo tg = tile_geo(a, t0 + mt, g, px);
+      const bool valid = tg.valid;
+      const int b = tg.b, oy = tg.y * S + pr, ox = tg.x * S + ps;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((half * a.MT + mt) * a.Npad);
       float head[4] = {0.f, 0.f, 0.f, 0.f};
-      const bool last_tile = (mt == mt_hi - 1);
+      const bool last_tile = (mt == a.MT - 1);
       if (a.fast) {
         TilePix tp;
         tp.valid = valid; tp.b = b; tp.oy = oy; tp.ox = ox;
@@ -372,7 +392,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
         tp.out2 = a.ep.out2 ? static_cast<__nv_bfloat16*>(a.ep.out2) + pix * a.ep.out2_ct + a.ep.out2_coff : nullptr;
         tp.r1 = (a.ep.res1 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res1) + pix * a.ep.res1_ct + a.ep.res1_coff : nullptr;
         tp.r2 = (a.ep.res2 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
-        const long long dn = (long long)(Wo + 2);          // padded pixels per row; scaled by ct at use
+        const long long wp = (long long)(Wo + 2);
         // two residual register sets (A/B), alternated so prefetching needs no copies
         uint4 A1[2] = {}, A2[2] = {}, B1[2] = {}, B2[2] = {};
         auto ldres = [&](int c, uint4 (&x1)[2], uint4 (&x2)[2]) {
@@ -382,78 +402,281 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
         auto one = [&](int c, const uint4 (&c1)[2], const uint4 (&c2)[2], uint4 (&n1)[2], uint4 (&n2)[2]) {
           uint32_t r[16];
           tc_ld16(tbase + (uint32_t)(c * 16), r);
-          if (c + c_step < nchunks) ldres(c + c_step, n1, n2);   // prefetch behind this chunk's math
+          if (c + 1 < nchunks) ldres(c + 1, n1, n2);             // prefetch behind this chunk's math
           tc_ld_wait();
-          if (last_tile && c + c_step >= nchunks) {              // accumulator fully read: release the TMEM stage
+          if (last_tile && c + 1 >= nchunks) {                   // accumulator fully read: release the TMEM stage
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty0 + 8u * rt.stage);
+            if (lane == 0) mbar_arrive(t_empty);
             released = true;
           }
-          // store_chunk scales dn by the buffer's own ct
-          epi_chunk_fast<ACT>(a, es, c * 16, r, tp, dn, c1, c2, head);
+          epi_chunk_fast<ACT>(a, es, c * 16, r, tp, wp, c1, c2, head);
         };
-        int c = c_begin;
-        if (c < nchunks) ldres(c, A1, A2);
+        int c = 0;
+        ldres(0, A1, A2);
         while (c < nchunks) {
           one(c, A1, A2, B1, B2);
-          c += c_step;
-          if (c >= nchunks) break;
+          if (++c >= nchunks) break;
           one(c, B1, B2, A1, A2);
-          c += c_step;
+          ++c;
         }
-        if (has_head) {
-          if (!split_tiles) {                  // combine the two halves' partial 1x1 sums
-            float* hp = es.hpart + ((size_t)hbuf * 128 + m) * 4;
-            if (half == 1) { hp[0] = head[0]; hp[1] = head[1]; hp[2] = head[2]; hp[3] = head[3]; }
-            asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-            if (half == 0) { head[0] += hp[0]; head[1] += hp[1]; head[2] += hp[2]; head[3] += hp[3]; }
-            hbuf ^= 1;
-          }
-          if ((split_tiles || half == 0) && valid) {
-            for (int jh = 0; jh < a.ep.planar_c; ++jh)
-              a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
-          }
+        if (has_head && valid) {
+          for (int jh = 0; jh < a.ep.planar_c; ++jh)
+            a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
         }
       } else {
-        // generic path (ragged N, per-image temb rows, planar output): one warp per tile does all chunks
-        if (split_tiles || half == 0) {
-          for (int c0 = 0; c0 < a.Npad; c0 += 16) {
-            uint32_t r[16];
-            tc_ld16(tbase + (uint32_t)c0, r);
-            tc_ld_wait();
-            if (valid && c0 < a.ep.N) {
-              float v[16];
+        // generic path (ragged N, per-image temb rows, planar output)
+        for (int c0 = 0; c0 < a.Npad; c0 += 16) {
+          uint32_t r[16];
+          tc_ld16(tbase + (uint32_t)c0, r);
+          tc_ld_wait();
+          if (valid && c0 < a.ep.N) {
+            float v[16];
 #pragma unroll
-              for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
-              epilogue_math<__nv_bfloat16, 16, 8, false>(a.ep, b, oy, ox, c0, v);
-              epilogue_store<__nv_bfloat16, 16, 8>(a.ep, b, oy, ox, c0, v, !has_head);
-              if (has_head) {
-                const int nv = min(16, a.ep.N - c0);
-                for (int jh = 0; jh < a.ep.planar_c; ++jh) {
-                  float acc = head[jh];
+            for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+            epilogue_math<__nv_bfloat16, 16, 8, false>(a.ep, b, oy, ox, c0, v);
+            epilogue_store<__nv_bfloat16, 16, 8>(a.ep, b, oy, ox, c0, v, !has_head);
+            if (has_head) {
+              const int nv = min(16, a.ep.N - c0);
+              for (int jh = 0; jh < a.ep.planar_c; ++jh) {
+                float acc = head[jh];
 #pragma unroll
-                  for (int i = 0; i < 16; ++i)
-                    if (i < nv) acc = fmaf(es.head_w[jh * a.Npad + c0 + i], v[i], acc);
-                  head[jh] = acc;
-                }
+                for (int i = 0; i < 16; ++i)
+                  if (i < nv) acc = fmaf(es.head_w[jh * a.Npad + c0 + i], v[i], acc);
+                head[jh] = acc;
               }
             }
           }
-          if (has_head && valid) {
-            for (int jh = 0; jh < a.ep.planar_c; ++jh)
-              a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
-          }
+        }
+        if (has_head && valid) {
+          for (int jh = 0; jh < a.ep.planar_c; ++jh)
+            a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
         }
       }
     }
     if (!released) {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty0 + 8u * rt.stage);
+      if (lane == 0) mbar_arrive(t_empty);
     }
-    rt.next();
   }
+}
+
+// ---------------------------------------------------------------------------------------------
+// TMA-staged epilogue (stride-1, up == 1, N % 64 == 0, W % 8 == 0, NHWC output):
+//   * the 128 px x 64 ch output sub-tile is assembled in a 128B-swizzled 16 KB shared-memory
+//     buffer and written with cp.async.bulk.tensor stores (full 128 B lines, no partial sectors);
+//   * the residual (res1) sub-tile is TMA-loaded into the SAME buffer ahead of time (while the MMAs
+//     of the tile still run) and updated in place, so its HBM latency is off the critical path;
+//   * reflect ring: mirrored ROWS are extra 1-row TMA stores of the same smem rows, mirrored
+//     COLUMNS (first / last column tile only) are per-thread 16 B stores;
+//   * zero ring (border == KEEP): masked rows are written as zeros by one full-box store.
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
+}
+
+struct StageSmem {
+  uint32_t base;        // shared address of THIS WARP's staging buffers ([nbuf][4 KB])
+  uint8_t* gen;         // generic pointer to the same
+  uint32_t r_full0;     // this warp's mbarrier for buffer 0 (buffer i at +8*i)
+};
+
+__device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+        "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]),
+        "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]),
+        "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr));
+}
+
+// Each epilogue WARP owns 32 TMEM lanes = 4 tile rows x 8 px and stages them in its own 4 KB
+// swizzled buffer(s): no cross-warp synchronisation, one lane issues the warp's TMA traffic.
+template <int ACT>
+__device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es, const StageSmem& sg,
+                                             uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0,
+                                             int warp, int lane) {
+  const int quarter = warp & 3, half = (warp - 2) >> 2;
+  const int m = quarter * 32 + lane;
+  const int g = m >> 3, px = m & 7;
+  const int nsj = a.Npad >> 6;                   // 64-channel sub-tiles per tile
+  const int n_sub = a.MT * nsj;                  // sub-tiles per item
+  const int nbuf = a.epi_nbuf;
+  const int Ho = a.ep.H_out, Wo = a.ep.W_out;
+  const bool reflect = (a.ep.border == SRD_BORDER_REFLECT);
+  const bool has_r1 = a.ep.res1 != nullptr;
+  const uint32_t t_full = t_full0 + 8u * half, t_empty = t_empty0 + 8u * half;
+  const uint32_t swz = (uint32_t)(lane & 7);     // == m & 7
+  uint8_t* my_row = sg.gen + lane * 128;         // this pixel's 128 B row inside a staging buffer
+  const int g0 = quarter * 4;                    // first tile row of this warp
+
+  // lane 0: make buffer (kn % nbuf) ready for this warp's rows of sub-tile kn
+  auto prepare = [&](uint32_t kn) {
+    const int itn = half + 2 * (int)(kn / (uint32_t)n_sub);
+    const int item = blockIdx.x + itn * gridDim.x;
+    if (item >= a.n_items) return;
+    const int rem = (int)(kn % (uint32_t)n_sub);
+    const int mt = rem / nsj, j = rem - mt * nsj;
+    const int tt = (item % a.items_per_phase) * a.MT + mt;
+    const int rowblk = tt / a.n_colblk, colblk = tt - rowblk * a.n_colblk;
+    const uint32_t buf = kn % (uint32_t)nbuf;
+    const uint32_t bar = sg.r_full0 + 8u * buf;
+    if (has_r1) {
+      mbar_expect_tx(bar, 4096u);
+      tma_load_3d(sg.base + buf * 4096u, &a.tmR, bar, j * 64, colblk * TILE_W + 1, rowblk * TILE_H + a.vstart + g0);
+    } else {
+      mbar_arrive(bar);
+    }
+  };
+
+  uint32_t k = 0;
+  if (lane == 0) prepare(0);
+  for (int it = half;; it += 2) {
+    const int item = blockIdx.x + it * gridDim.x;
+    if (item >= a.n_items) break;
+    const int t0 = (item % a.items_per_phase) * a.MT;
+    mbar_wait(t_full, (uint32_t)(it >> 1) & 1u, a.err_flag, 6);
+    tc_fence_after();
+    for (int mt = 0; mt < a.MT; ++mt) {
+      const TileGeo tg = tile_geo(a, t0 + mt, g, px);
+      const bool valid = tg.valid;
+      const int b = tg.b, oy = tg.y, ox = tg.x;
+      const size_t pix = valid ? ((size_t)(b * (Ho + 2) + oy + 1) * (Wo + 2) + ox + 1) : 0;
+      uint32_t edge = 0;
+      if (valid && reflect)
+        edge = (oy == 1 ? 1u : 0u) | (oy == Ho - 2 ? 2u : 0u) | (ox == 1 ? 4u : 0u) | (ox == Wo - 2 ? 8u : 0u);
+      __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(a.ep.out) + pix * a.ep.out_ct + a.ep.out_coff;
+      const __nv_bfloat16* r2p = (a.ep.res2 && valid)
+          ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((half * a.MT + mt) * a.Npad);
+      for (int j = 0; j < nsj; ++j, ++k) {
+        const uint32_t buf = k % (uint32_t)nbuf;
+        uint8_t* row = my_row + buf * 4096u;
+        bool buf_ready = false;
+#pragma unroll
+        for (int hb = 0; hb < 2; ++hb) {                         // two 32-channel blocks: 32 independent chains
+          const int c0 = j * 64 + hb * 32;
+          uint32_t r[32];
+          tc_ld32(tbase + (uint32_t)c0, r);
+          uint4 q2[4] = {};
+          if (r2p) {
+            const uint4* q = reinterpret_cast<const uint4*>(r2p + c0);
+            q2[0] = q[0]; q2[1] = q[1]; q2[2] = q[2]; q2[3] = q[3];
+          }
+          tc_ld_wait();
+          if (mt == a.MT - 1 && j == nsj - 1 && hb == 1) {       // accumulator fully read: release the TMEM stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty);
+          }
+          float v[32];
+          const float4* sb = reinterpret_cast<const float4*>(es.bias + c0);
+          const float4* st = reinterpret_cast<const float4*>(es.temb + c0);
+          const float alpha = a.ep.alpha;
+#pragma unroll
+          for (int q = 0; q < 8; ++q) {
+            const float4 b4 = sb[q], t4 = st[q];
+            v[4 * q + 0] = act_axpy<ACT>(__uint_as_float(r[4 * q + 0]) + b4.x, alpha, t4.x);
+            v[4 * q + 1] = act_axpy<ACT>(__uint_as_float(r[4 * q + 1]) + b4.y, alpha, t4.y);
+            v[4 * q + 2] = act_axpy<ACT>(__uint_as_float(r[4 * q + 2]) + b4.z, alpha, t4.z);
+            v[4 * q + 3] = act_axpy<ACT>(__uint_as_float(r[4 * q + 3]) + b4.w, alpha, t4.w);
+          }
+          if (!buf_ready) {                                      // staging buffer free / residual landed
+            mbar_wait(sg.r_full0 + 8u * buf, (k / (uint32_t)nbuf) & 1u, a.err_flag, 8);
+            buf_ready = true;
+          }
+          uint4* sp[4];
+#pragma unroll
+          for (int u = 0; u < 4; ++u) sp[u] = reinterpret_cast<uint4*>(row + (((uint32_t)(4 * hb + u) ^ swz) << 4));
+          if (has_r1) {
+            float f[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              unpack_bf16x8(*sp[u], f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 * u + i] = fmaf(a.ep.beta1, f[i], v[8 * u + i]);
+            }
+          }
+          if (r2p) {
+            float f[8];
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              unpack_bf16x8(q2[u], f);
+#pragma unroll
+              for (int i = 0; i < 8; ++i) v[8 * u + i] = fmaf(a.ep.beta2, f[i], v[8 * u + i]);
+            }
+          }
+#pragma unroll
+          for (int u = 0; u < 4; ++u) {
+            uint4 o = make_uint4(0, 0, 0, 0);                    // masked rows become the zero ring (KEEP)
+            if (valid) {
+              o.x = pack_bf16x2(v[8 * u + 0], v[8 * u + 1]); o.y = pack_bf16x2(v[8 * u + 2], v[8 * u + 3]);
+              o.z = pack_bf16x2(v[8 * u + 4], v[8 * u + 5]); o.w = pack_bf16x2(v[8 * u + 6], v[8 * u + 7]);
+            }
+            *sp[u] = o;
+          }
+          if (edge & 12u) {                                      // mirrored ring COLUMNS (+ corners): rare
+            const long long dn = (long long)(Wo + 2) * a.ep.out_ct;
+            const int ct = a.ep.out_ct;
+            const bool top = edge & 1u, bot = edge & 2u, lef = edge & 4u, rig = edge & 8u;
+#pragma unroll
+            for (int hh = 0; hh < 2; ++hh) {
+              float w[16];
+#pragma unroll
+              for (int i = 0; i < 16; ++i) w[i] = v[16 * hh + i];
+              __nv_bfloat16* p = outp + c0 + 16 * hh;
+              if (lef) st16_bf16(p - 2 * ct, w);
+              if (rig) st16_bf16(p + 2 * ct, w);
+              if (top && lef) st16_bf16(p - 2 * dn - 2 * ct, w);
+              if (top && rig) st16_bf16(p - 2 * dn + 2 * ct, w);
+              if (bot && lef) st16_bf16(p + 2 * dn - 2 * ct, w);
+              if (bot && rig) st16_bf16(p + 2 * dn + 2 * ct, w);
+            }
+          }
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
+        __syncwarp();
+        if (lane == 0) {
+          const uint32_t src = sg.base + buf * 4096u;
+          const int V0 = tg.V0 + g0, xc = tg.x0 + 1;               // this warp's 4 rows
+          bool whole = !reflect;
+          int yp0 = 0;
+          if (reflect) {                                           // stride 1: virtual row == padded stacked row
+            const int b0 = V0 / a.period;
+            yp0 = V0 - b0 * a.period;
+            whole = (yp0 >= 3) && (yp0 + 3 <= Ho - 2) && (V0 + 4 <= a.n_vrows);
+          }
+          if (whole) {
+            tma_store_3d(&a.tmO, src, j * 64, xc, V0);
+          } else {
+            int yp = yp0;
+            for (int gg = 0; gg < 4; ++gg, ++yp) {
+              if (yp >= a.period) yp -= a.period;
+              const int V = V0 + gg;
+              if (V >= a.n_vrows) break;
+              if (yp < 1 || yp > Ho) continue;                       // ring row: written by its mirror source
+              const uint32_t rs = src + (uint32_t)gg * 1024u;
+              tma_store_3d(&a.tmOrow, rs, j * 64, xc, V);
+              if (yp == 2) tma_store_3d(&a.tmOrow, rs, j * 64, xc, V - 2);          // oy == 1 -> ring row 0
+              if (yp == Ho - 1) tma_store_3d(&a.tmOrow, rs, j * 64, xc, V + 2);     // oy == H-2 -> ring row H+1
+            }
+          }
+          asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          // the buffer of sub-tile k+1 was last read by the store of sub-tile k+1-nbuf
+          if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+          else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          prepare(k + 1);
+        }
+        __syncwarp();
+      }
+    }
+  }
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
@@ -463,7 +686,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int B_BYTES = a.Npad * 128;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)a.a_stages * a.MT * a.a_stage_bytes;
-  const uint32_t bar_base = b_base + (uint32_t)a.b_region_bytes;
+  const uint32_t stg_base = b_base + (uint32_t)a.b_region_bytes;        // staging: [half][buf][16 KB]
+  const uint32_t stg_bytes = a.epi_tma ? (uint32_t)(2 * a.epi_nbuf) * 16384u : 0u;
+  const uint32_t bar_base = stg_base + stg_bytes;
   // barrier layout (8 B each): A_full[8] A_empty[8] B_full[8] B_empty[8] T_full[2] T_empty[2]
   auto A_full = [&](int s) { return bar_base + 8u * s; };
   auto A_empty = [&](int s) { return bar_base + 8u * (MAX_STAGES + s); };
@@ -473,6 +698,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   auto T_empty = [&](int s) { return bar_base + 8u * (4 * MAX_STAGES + 2 + s); };
   const uint32_t tmem_slot = bar_base + 8u * (4 * MAX_STAGES + 4);
   const uint32_t B_res = bar_base + 8u * (4 * MAX_STAGES + 5);
+  const uint32_t R_full0 = bar_base + 8u * (4 * MAX_STAGES + 6);        // [epilogue warp][buf] -> 16 barriers
   uint8_t* gen_base = smem_raw + (bar_base - smem_u32(smem_raw));       // generic pointer to bar_base
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + 8 * (4 * MAX_STAGES + 4));
   float* vec = reinterpret_cast<float*>(gen_base + BAR_BYTES);
@@ -485,12 +711,18 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < a.a_stages; ++s) { mbar_init(A_full(s), 1); mbar_init(A_empty(s), 1); }
     for (int s = 0; s < a.b_stages; ++s) { mbar_init(B_full(s), 1); mbar_init(B_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(T_full(s), 1); mbar_init(T_empty(s), 8); }
+    for (int s = 0; s < 2; ++s) { mbar_init(T_full(s), 1); mbar_init(T_empty(s), 4); }
     mbar_init(B_res, 1);
+    for (int s = 0; s < 16; ++s) mbar_init(R_full0 + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int s = 0; s < a.n_src; ++s)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA[s]) : "memory");
     asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmB) : "memory");
+    if (a.epi_tma) {
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmO) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmOrow) : "memory");
+      if (a.ep.res1) asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmR) : "memory");
+    }
   }
   if (warp == 1) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
@@ -675,7 +907,17 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     EpiSmem es;
     es.bias = s_bias; es.temb = s_temb;
     es.head_w = a.head_w ? s_head : nullptr; es.head_b = s_headb; es.hpart = s_hpart;
-    if (a.ep.act == SRD_ACT_MISH)
+    if (a.epi_tma) {
+      const int ew = warp - 2;                         // epilogue warp 0..7
+      StageSmem sg;
+      sg.base = stg_base + (uint32_t)(ew * a.epi_nbuf) * 4096u;
+      sg.gen = smem_raw + (sg.base - smem_u32(smem_raw));
+      sg.r_full0 = R_full0 + 8u * (uint32_t)(ew * 2);
+      if (a.ep.act == SRD_ACT_MISH)
+        epilogue_tma<SRD_ACT_MISH>(a, es, sg, tmem_base, T_full(0), T_empty(0), warp, lane);
+      else
+        epilogue_tma<SRD_ACT_NONE>(a, es, sg, tmem_base, T_full(0), T_empty(0), warp, lane);
+    } else if (a.ep.act == SRD_ACT_MISH)
       epilogue_role<SRD_ACT_MISH>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
     else if (a.ep.act == SRD_ACT_LRELU02)
       epilogue_role<SRD_ACT_LRELU02>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
@@ -711,7 +953,12 @@ static EncodeTiledFn get_encode_fn() {
 // tuning / validation switches (srd_tc_set_mode): A-operand mode for stride-1 convs, resident weights
 static int g_a_mode = 1;
 static int g_b_resident = 1;
-void tc_set_mode(int a_mode, int b_resident) { g_a_mode = a_mode; g_b_resident = b_resident; }
+static int g_epi_tma = 1;
+void tc_set_mode(int a_mode, int b_resident) {
+  g_a_mode = a_mode & 1;
+  g_epi_tma = (a_mode & 2) ? 0 : 1;      // bit 1 of a_mode disables the TMA-staged epilogue
+  g_b_resident = b_resident;
+}
 
 int tc_supported(const SrdConvDesc& d, const char** why) {
   const char* w = nullptr;
@@ -759,48 +1006,80 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
   const int n_phase = d.up * d.up;
-  a.MT = (2 * 2 * a.Npad <= 512 && (long long)n_phase * a.tiles_per_phase >= 2LL * n_sm) ? 2 : 1;
-  a.items_per_phase = (a.tiles_per_phase + a.MT - 1) / a.MT;
-  a.n_items = n_phase * a.items_per_phase;
   int kb = 0;
   const int taps = d.nky * d.nkx;
   for (int i = 0; i < d.n_src; ++i) { a.nchunk[i] = (d.src[i].cin + 63) / 64; kb += a.nchunk[i] * taps; }
   a.kb_per_phase = kb;
+  a.kb_total = n_phase * kb;
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
   a.ep = make_epi(d, nullptr);
   a.head_w = d.head_w; a.head_b = d.head_b;
   a.err_flag = err_flag;
   {
     auto ok8 = [](const void* p, int ct, int coff) { return !p || ((ct % 8) == 0 && (coff % 8) == 0); };
-    a.fast = (d.N % 16 == 0) && (!d.temb || d.temb_bstride == 0) && d.temb_bstride == 0 &&
+    a.fast = (d.N % 16 == 0) && d.temb_bstride == 0 &&
              ok8(d.out, d.out_ct, d.out_coff) && ok8(d.out2, d.out2_ct, d.out2_coff) &&
              ok8(d.res1, d.res1_ct, d.res1_coff) && ok8(d.res2, d.res2_ct, d.res2_coff) &&
              (!d.planar || d.head_w);
   }
-  // shared memory: A ring + B ring (or resident weights) + barriers + epilogue vectors
+  a.epi_tma = g_epi_tma && a.fast && d.stride == 1 && d.up == 1 && (d.N % 64 == 0) && d.out && !d.out2 &&
+              !d.planar && !d.head_w && (a.W_m % TILE_W == 0) && d.act != SRD_ACT_LRELU02 && d.H_out >= 4;
+  // ---- shared-memory plan: A ring + weights (ring or resident) + staging + barriers + epilogue vectors
   const int B_BYTES = a.Npad * 128;
   const int budget = 227 * 1024 - BAR_BYTES - VEC_BYTES - 1024;
   a.a_mode = (d.stride == 1) ? g_a_mode : 0;
   a.a_stage_bytes = a.a_mode ? A_HALO_STAGE : A_BYTES;
-  a.kb_total = n_phase * kb;
-  const int stage_bytes = a.MT * a.a_stage_bytes;
   const long long res_bytes = (long long)a.kb_total * B_BYTES;
-  a.b_resident = g_b_resident && (res_bytes + 2LL * stage_bytes <= budget) && res_bytes < (1 << 20);
-  int b_bytes_total;
-  if (a.b_resident) {
-    int ast = (int)((budget - res_bytes) / stage_bytes);
-    a.a_stages = ast > 4 ? 4 : ast;
-    a.b_stages = 1;
-    b_bytes_total = (int)res_bytes;
-  } else {
-    a.a_stages = a.a_mode ? (a.MT == 2 ? 2 : 3) : ((a.MT == 2) ? 3 : 4);
-    int bst = (budget - a.a_stages * stage_bytes) / B_BYTES;
-    a.b_stages = bst > MAX_STAGES ? MAX_STAGES : bst;
-    SRD_CHECK(a.b_stages >= 2, "conv_tc: not enough shared memory for the weight ring");
-    b_bytes_total = a.b_stages * B_BYTES;
+  const long long n_tiles_all = (long long)n_phase * a.tiles_per_phase;
+  const bool mt2_ok = (2 * 2 * a.Npad <= 512) && n_tiles_all >= 2LL * n_sm;
+  bool planned = false;
+  int b_bytes_total = 0, stage_bytes = 0;
+  // preference: staging depth 2 before 1; resident weights (MT = 1: nothing is re-streamed) before a ring;
+  // for rings MT = 2 (each weight tile shared by two M tiles) before MT = 1.
+  for (int nbuf = a.epi_tma ? 2 : 0; !planned; --nbuf) {
+    const int stg = 2 * nbuf * 16384;
+    for (int pass = 0; pass < 3 && !planned; ++pass) {
+      const bool resident = (pass == 0);
+      const int MT = resident ? 1 : (pass == 1 ? 2 : 1);
+      if (resident && !(g_b_resident && res_bytes < (1 << 20))) continue;
+      if (pass == 1 && !mt2_ok) continue;
+      const int sb = MT * a.a_stage_bytes;
+      if (resident) {
+        const long long left = (long long)budget - stg - res_bytes;
+        if (left < 2LL * sb) continue;
+        const int ast = (int)(left / sb);
+        a.a_stages = ast > 4 ? 4 : ast;
+        a.b_stages = 1;
+        b_bytes_total = (int)res_bytes;
+      } else {
+        const int ast = a.a_mode ? 2 : 3;
+        const int left = budget - stg - ast * sb;
+        if (left < 3 * B_BYTES) continue;
+        const int bst = left / B_BYTES;
+        a.a_stages = ast;
+        a.b_stages = bst > MAX_STAGES ? MAX_STAGES : bst;
+        b_bytes_total = a.b_stages * B_BYTES;
+        if (budget - stg - b_bytes_total - ast * sb >= sb) a.a_stages = ast + 1;   // spare room: third A stage
+      }
+      a.b_resident = resident ? 1 : 0;
+      a.MT = MT;
+      a.epi_nbuf = nbuf;
+      stage_bytes = sb;
+      planned = true;
+    }
+    if (planned) break;
+    if (nbuf <= (a.epi_tma ? 1 : 0)) {
+      if (!a.epi_tma) break;
+      a.epi_tma = 0;              // staging does not fit: register epilogue
+      nbuf = 1;                   // loop decrements to 0
+    }
   }
+  SRD_CHECK(planned, "conv_tc: no shared-memory plan fits (N=%d)", d.N);
+  a.items_per_phase = (a.tiles_per_phase + a.MT - 1) / a.MT;
+  a.n_items = n_phase * a.items_per_phase;
   a.b_region_bytes = b_bytes_total;
-  plan->smem = a.a_stages * stage_bytes + b_bytes_total + BAR_BYTES + VEC_BYTES + 1024;
+  const int stg_total = a.epi_tma ? 2 * a.epi_nbuf * 16384 : 0;
+  plan->smem = a.a_stages * stage_bytes + b_bytes_total + stg_total + BAR_BYTES + VEC_BYTES + 1024;
   plan->grid = a.n_items < n_sm ? a.n_items : n_sm;
 
   // ---- tensor maps
@@ -838,6 +1117,27 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
+  }
+  if (a.epi_tma) {
+    const int Hop = d.H_out + 2, Wop = d.W_out + 2;
+    auto enc_out = [&](CUtensorMap* tm, const void* ptr, int ct, int coff, int rows) {
+      void* base = (void*)((const __nv_bfloat16*)ptr + coff);
+      cuuint64_t dims[3] = {(cuuint64_t)d.N, (cuuint64_t)Wop, (cuuint64_t)d.B * Hop};
+      cuuint64_t strides[2] = {(cuuint64_t)ct * 2, (cuuint64_t)Wop * ct * 2};
+      cuuint32_t box[3] = {64, TILE_W, (cuuint32_t)rows};
+      cuuint32_t es[3] = {1, 1, 1};
+      return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
+    SRD_CHECK(((uintptr_t)d.out % 16) == 0, "conv_tc: out must be 16-byte aligned");
+    CUresult r = enc_out(&a.tmO, d.out, d.out_ct, d.out_coff, 4);
+    SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
+    r = enc_out(&a.tmOrow, d.out, d.out_ct, d.out_coff, 1);
+    SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(out row) failed with %d", (int)r);
+    if (d.res1) {
+      r = enc_out(&a.tmR, d.res1, d.res1_ct, d.res1_coff, 4);
+      SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(res1) failed with %d", (int)r);
+    }
   }
   static bool attr_set = false;
   if (!attr_set) {

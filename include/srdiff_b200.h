@@ -106,8 +106,8 @@ int srd_conv_plan_kernel(const SrdConvPlan* plan);
 int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream);
 /* Tuning switches for plans created afterwards.  a_mode: 0 = one TMA box per (chunk, kx) with
  * 1024 B-aligned UMMA descriptors; 1 = one halo box per chunk, taps addressed by 128 B-granular
- * descriptor start offsets (default; validated on B200).  b_resident: keep all weight k-blocks
- * in shared memory when they fit. */
+ * descriptor start offsets (default; validated on B200); +2 disables the TMA-staged epilogue.
+ * b_resident: keep all weight k-blocks in shared memory when they fit. */
 int srd_tc_set_mode(int32_t a_mode, int32_t b_resident);
 /* Non-zero after the tcgen05 pipeline watchdog fired (value = which wait timed out). */
 int srd_watchdog_flag(void);
