@@ -69,6 +69,7 @@ SYMBOLS = {
     "srd_conv_run": (C.c_int, [_vp, _vp, _vp]),
     "srd_watchdog_flag": (C.c_int, []),
     "srd_tc_set_mode": (C.c_int, [_i32, _i32]),
+    "srd_tc_set_debug": (C.c_int, [_vp]),
     "srd_time_table": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "srd_p_sample_step": (C.c_int, [C.POINTER(SrdPSampleArgs), _vp]),
     "srd_randn": (C.c_int, [_vp, _i32, _i32, _u64, _u32, _u32, _vp]),

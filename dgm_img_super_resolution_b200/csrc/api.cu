@@ -25,6 +25,7 @@ void tc_plan_delete(TcPlan*);
 int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag);
 int launch_conv_tc(const TcPlan& plan, const float* temb, cudaStream_t stream);
 void tc_set_mode(int a_mode, int b_resident);
+void tc_set_debug(unsigned long long* p);
 
 static int* g_err_flag_dev = nullptr;   // device-visible pointer to a host-mapped int
 static int* g_err_flag_host = nullptr;
@@ -149,6 +150,11 @@ int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream) {
 int srd_tc_set_mode(int32_t a_mode, int32_t b_resident) {
   SRD_CHECK(a_mode >= 0 && a_mode <= 3, "srd_tc_set_mode: a_mode must be in 0..3");
   tc_set_mode(a_mode, b_resident ? 1 : 0);
+  return 0;
+}
+
+int srd_tc_set_debug(void* buf) {
+  tc_set_debug((unsigned long long*)buf);
   return 0;
 }
 

@@ -35,6 +35,7 @@ constexpr int HALO_W = TILE_W + 2;
 constexpr int A_HALO_BYTES = BOX_ROWS * HALO_W * 128;      // 23040: one {64ch x 10px x 18rows} box (all 9 taps)
 constexpr int A_HALO_STAGE = (A_HALO_BYTES + 1023) / 1024 * 1024;
 constexpr int MAX_STAGES = 8;
+constexpr int DBG_ITEMS = 64;
 constexpr int BAR_BYTES = 512;           // mbarriers + TMEM slot
 constexpr int VEC_BYTES = (512 + 1024 + 4 + 2 * 128 * 4) * 4;   // epilogue vectors (see conv_tc_kernel)
 
@@ -68,6 +69,7 @@ struct TcArgs {
   int b_region_bytes;      // bytes of the weight region (ring or resident)
   int epi_tma;             // TMA-staged epilogue (see epilogue_tma)
   int epi_nbuf;            // staging buffers per epilogue half (1 | 2)
+  unsigned long long* dbg; // optional timeline buffer [cta][DBG_ITEMS][8] of clock64 stamps (debug)
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -174,6 +176,11 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+__device__ __forceinline__ void dbg_stamp(const TcArgs& a, int item_local, int ev) {
+  if (a.dbg && item_local < DBG_ITEMS)
+    a.dbg[((size_t)blockIdx.x * DBG_ITEMS + item_local) * 8 + ev] = (unsigned long long)clock64();
+}
+
 struct Ring {
   int stage, phase, n;
   __device__ __forceinline__ void next() { if (++stage == n) { stage = 0; phase ^= 1; } }
@@ -218,14 +225,32 @@ __device__ __forceinline__ float act_fast(float x) {
   return x;
 }
 
+// 16 bf16 channels = 32 B = one full DRAM sector.  When the destination is 32 B aligned, one 256-bit
+// store (sm_100 STG.256) writes the whole sector; two 16 B stores would be two PARTIAL-sector writes.
 __device__ __forceinline__ void st16_bf16(__nv_bfloat16* p, const float (&v)[16]) {
   uint4 a, b;
   a.x = pack_bf16x2(v[0], v[1]); a.y = pack_bf16x2(v[2], v[3]);
   a.z = pack_bf16x2(v[4], v[5]); a.w = pack_bf16x2(v[6], v[7]);
   b.x = pack_bf16x2(v[8], v[9]); b.y = pack_bf16x2(v[10], v[11]);
   b.z = pack_bf16x2(v[12], v[13]); b.w = pack_bf16x2(v[14], v[15]);
-  reinterpret_cast<uint4*>(p)[0] = a;
-  reinterpret_cast<uint4*>(p)[1] = b;
+  if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+    asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};"
+                 ::"l"(p), "r"(a.x), "r"(a.y), "r"(a.z), "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w) : "memory");
+  } else {
+    reinterpret_cast<uint4*>(p)[0] = a;
+    reinterpret_cast<uint4*>(p)[1] = b;
+  }
+}
+// 32 B residual load (one sector) when aligned
+__device__ __forceinline__ void ld16_bf16(const __nv_bfloat16* p, uint4 (&x)[2]) {
+  if ((reinterpret_cast<uintptr_t>(p) & 31) == 0) {
+    asm volatile("ld.global.v8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+                 : "=r"(x[0].x), "=r"(x[0].y), "=r"(x[0].z), "=r"(x[0].w), "=r"(x[1].x), "=r"(x[1].y), "=r"(x[1].z), "=r"(x[1].w)
+                 : "l"(p));
+  } else {
+    const uint4* q = reinterpret_cast<const uint4*>(p);
+    x[0] = q[0]; x[1] = q[1];
+  }
 }
 
 // Write one pixel's 16-channel chunk, plus the mirrored ring copies this pixel owns (reflect).
@@ -396,8 +421,8 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
         // two residual register sets (A/B), alternated so prefetching needs no copies
         uint4 A1[2] = {}, A2[2] = {}, B1[2] = {}, B2[2] = {};
         auto ldres = [&](int c, uint4 (&x1)[2], uint4 (&x2)[2]) {
-          if (tp.r1) { const uint4* q = reinterpret_cast<const uint4*>(tp.r1 + 16 * c); x1[0] = q[0]; x1[1] = q[1]; }
-          if (tp.r2) { const uint4* q = reinterpret_cast<const uint4*>(tp.r2 + 16 * c); x2[0] = q[0]; x2[1] = q[1]; }
+          if (tp.r1) ld16_bf16(tp.r1 + 16 * c, x1);
+          if (tp.r2) ld16_bf16(tp.r2 + 16 * c, x2);
         };
         auto one = [&](int c, const uint4 (&c1)[2], const uint4 (&c2)[2], uint4 (&n1)[2], uint4 (&n2)[2]) {
           uint32_t r[16];
@@ -542,6 +567,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     const int t0 = (item % a.items_per_phase) * a.MT;
     mbar_wait(t_full, (uint32_t)(it >> 1) & 1u, a.err_flag, 6);
     tc_fence_after();
+    if (quarter == 0 && lane == 0) dbg_stamp(a, it, 5);
     for (int mt = 0; mt < a.MT; ++mt) {
       const TileGeo tg = tile_geo(a, t0 + mt, g, px);
       const bool valid = tg.valid;
@@ -557,86 +583,78 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
       for (int j = 0; j < nsj; ++j, ++k) {
         const uint32_t buf = k % (uint32_t)nbuf;
         uint8_t* row = my_row + buf * 4096u;
-        bool buf_ready = false;
-#pragma unroll
-        for (int hb = 0; hb < 2; ++hb) {                         // two 32-channel blocks: 32 independent chains
-          const int c0 = j * 64 + hb * 32;
-          uint32_t r[32];
-          tc_ld32(tbase + (uint32_t)c0, r);
-          uint4 q2[4] = {};
-          if (r2p) {
-            const uint4* q = reinterpret_cast<const uint4*>(r2p + c0);
-            q2[0] = q[0]; q2[1] = q[1]; q2[2] = q[2]; q2[3] = q[3];
-          }
-          tc_ld_wait();
-          if (mt == a.MT - 1 && j == nsj - 1 && hb == 1) {       // accumulator fully read: release the TMEM stage
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty);
-          }
-          float v[32];
+        mbar_wait(sg.r_full0 + 8u * buf, (k / (uint32_t)nbuf) & 1u, a.err_flag, 8);   // buffer free / residual landed
+        const bool last_sub = (mt == a.MT - 1 && j == nsj - 1);
+        // Compact hot loop (one 16-channel chunk per iteration, NOT unrolled: the body must stay
+        // resident in the instruction cache; rare ring / second-residual work lives outside).
+#pragma unroll 1
+        for (int cc = 0; cc < 4; ++cc) {
+          const int c0 = j * 64 + cc * 16;
+          uint32_t r[16];
+          tc_ld16(tbase + (uint32_t)c0, r);
+          uint4* s0 = reinterpret_cast<uint4*>(row + (((uint32_t)(2 * cc) ^ swz) << 4));
+          uint4* s1 = reinterpret_cast<uint4*>(row + (((uint32_t)(2 * cc + 1) ^ swz) << 4));
           const float4* sb = reinterpret_cast<const float4*>(es.bias + c0);
           const float4* st = reinterpret_cast<const float4*>(es.temb + c0);
           const float alpha = a.ep.alpha;
+          tc_ld_wait();
+          if (last_sub && cc == 3) {                             // accumulator fully read: release the TMEM stage
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(t_empty);
+            if (quarter == 0 && lane == 0) dbg_stamp(a, it, 6);
+          }
+          float v[16];
 #pragma unroll
-          for (int q = 0; q < 8; ++q) {
+          for (int q = 0; q < 4; ++q) {
             const float4 b4 = sb[q], t4 = st[q];
             v[4 * q + 0] = act_axpy<ACT>(__uint_as_float(r[4 * q + 0]) + b4.x, alpha, t4.x);
             v[4 * q + 1] = act_axpy<ACT>(__uint_as_float(r[4 * q + 1]) + b4.y, alpha, t4.y);
             v[4 * q + 2] = act_axpy<ACT>(__uint_as_float(r[4 * q + 2]) + b4.z, alpha, t4.z);
             v[4 * q + 3] = act_axpy<ACT>(__uint_as_float(r[4 * q + 3]) + b4.w, alpha, t4.w);
           }
-          if (!buf_ready) {                                      // staging buffer free / residual landed
-            mbar_wait(sg.r_full0 + 8u * buf, (k / (uint32_t)nbuf) & 1u, a.err_flag, 8);
-            buf_ready = true;
-          }
-          uint4* sp[4];
-#pragma unroll
-          for (int u = 0; u < 4; ++u) sp[u] = reinterpret_cast<uint4*>(row + (((uint32_t)(4 * hb + u) ^ swz) << 4));
           if (has_r1) {
             float f[8];
+            unpack_bf16x8(*s0, f);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              unpack_bf16x8(*sp[u], f);
+            for (int i = 0; i < 8; ++i) v[i] = fmaf(a.ep.beta1, f[i], v[i]);
+            unpack_bf16x8(*s1, f);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[8 * u + i] = fmaf(a.ep.beta1, f[i], v[8 * u + i]);
-            }
+            for (int i = 0; i < 8; ++i) v[8 + i] = fmaf(a.ep.beta1, f[i], v[8 + i]);
           }
           if (r2p) {
+            const uint4* q = reinterpret_cast<const uint4*>(r2p + c0);
             float f[8];
+            unpack_bf16x8(q[0], f);
 #pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              unpack_bf16x8(q2[u], f);
+            for (int i = 0; i < 8; ++i) v[i] = fmaf(a.ep.beta2, f[i], v[i]);
+            unpack_bf16x8(q[1], f);
 #pragma unroll
-              for (int i = 0; i < 8; ++i) v[8 * u + i] = fmaf(a.ep.beta2, f[i], v[8 * u + i]);
-            }
+            for (int i = 0; i < 8; ++i) v[8 + i] = fmaf(a.ep.beta2, f[i], v[8 + i]);
           }
-#pragma unroll
-          for (int u = 0; u < 4; ++u) {
-            uint4 o = make_uint4(0, 0, 0, 0);                    // masked rows become the zero ring (KEEP)
-            if (valid) {
-              o.x = pack_bf16x2(v[8 * u + 0], v[8 * u + 1]); o.y = pack_bf16x2(v[8 * u + 2], v[8 * u + 3]);
-              o.z = pack_bf16x2(v[8 * u + 4], v[8 * u + 5]); o.w = pack_bf16x2(v[8 * u + 6], v[8 * u + 7]);
-            }
-            *sp[u] = o;
+          uint4 o0 = make_uint4(0, 0, 0, 0), o1 = o0;            // masked rows become the zero ring (KEEP)
+          if (valid) {
+            o0.x = pack_bf16x2(v[0], v[1]); o0.y = pack_bf16x2(v[2], v[3]);
+            o0.z = pack_bf16x2(v[4], v[5]); o0.w = pack_bf16x2(v[6], v[7]);
+            o1.x = pack_bf16x2(v[8], v[9]); o1.y = pack_bf16x2(v[10], v[11]);
+            o1.z = pack_bf16x2(v[12], v[13]); o1.w = pack_bf16x2(v[14], v[15]);
           }
-          if (edge & 12u) {                                      // mirrored ring COLUMNS (+ corners): rare
-            const long long dn = (long long)(Wo + 2) * a.ep.out_ct;
-            const int ct = a.ep.out_ct;
-            const bool top = edge & 1u, bot = edge & 2u, lef = edge & 4u, rig = edge & 8u;
-#pragma unroll
-            for (int hh = 0; hh < 2; ++hh) {
-              float w[16];
-#pragma unroll
-              for (int i = 0; i < 16; ++i) w[i] = v[16 * hh + i];
-              __nv_bfloat16* p = outp + c0 + 16 * hh;
-              if (lef) st16_bf16(p - 2 * ct, w);
-              if (rig) st16_bf16(p + 2 * ct, w);
-              if (top && lef) st16_bf16(p - 2 * dn - 2 * ct, w);
-              if (top && rig) st16_bf16(p - 2 * dn + 2 * ct, w);
-              if (bot && lef) st16_bf16(p + 2 * dn - 2 * ct, w);
-              if (bot && rig) st16_bf16(p + 2 * dn + 2 * ct, w);
-            }
+          *s0 = o0; *s1 = o1;
+        }
+        if (edge & 12u) {                                        // mirrored ring COLUMNS (+ corners): rare, cold
+          const long long dn = (long long)(Wo + 2) * a.ep.out_ct;
+          const int ct = a.ep.out_ct;
+          const bool top = edge & 1u, bot = edge & 2u, lef = edge & 4u, rig = edge & 8u;
+#pragma unroll 1
+          for (uint32_t u = 0; u < 8; ++u) {
+            const uint4 val = *reinterpret_cast<const uint4*>(row + ((u ^ swz) << 4));
+            uint4* p = reinterpret_cast<uint4*>(outp + j * 64 + u * 8);
+            if (lef) *(p - (2 * ct) / 8) = val;
+            if (rig) *(p + (2 * ct) / 8) = val;
+            if (top && lef) *(p - (2 * dn + 2 * ct) / 8) = val;
+            if (top && rig) *(p - (2 * dn - 2 * ct) / 8) = val;
+            if (bot && lef) *(p + (2 * dn - 2 * ct) / 8) = val;
+            if (bot && rig) *(p + (2 * dn + 2 * ct) / 8) = val;
           }
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
@@ -675,6 +693,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
         __syncwarp();
       }
     }
+    if (quarter == 0 && lane == 0) dbg_stamp(a, it, 7);
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
 }
@@ -756,7 +775,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         for (int kb = 0; kb < a.kb_total; ++kb)
           tma_load_2d(b_base + (uint32_t)kb * B_BYTES, &a.tmB, B_res, 0, kb * a.Npad);
       }
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
+      int il = 0;
+      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++il) {
         const int phase = item / a.items_per_phase;
         const int t0 = (item % a.items_per_phase) * a.MT;
         const int pr = phase / S, ps = phase % S;
@@ -768,6 +788,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (a.a_mode) {
               // ---- one halo box per (source, chunk): all taps come from it
               mbar_wait(A_empty(ra.stage), ra.phase ^ 1, a.err_flag, 1);
+              if (s == 0 && ch == 0) dbg_stamp(a, il, 0);
               mbar_expect_tx(A_full(ra.stage), (uint32_t)(a.MT * A_HALO_BYTES));
               for (int mt = 0; mt < a.MT; ++mt) {
                 const int tt = t0 + mt;
@@ -831,18 +852,22 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         mbar_wait(B_res, 0, a.err_flag, 7);
         tc_fence_after();
       }
+      int mma_il = 0;
       for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
         const int phase = item / a.items_per_phase;
         const int pr = phase / S, ps = phase % S;
         int ky0 = a.ky0, kx0 = a.kx0;
         if (S > 1) { ky0 = (pr >= S / 2) ? 1 : 0; kx0 = (ps >= S / 2) ? 1 : 0; }
+        dbg_stamp(a, mma_il, 1);
         mbar_wait(T_empty(rt.stage), rt.phase ^ 1, a.err_flag, 3);
         tc_fence_after();
+        dbg_stamp(a, mma_il, 2);
         uint32_t kcount = 0;     // 0 only for the first k-block of the item (accumulator overwrite)
         int kb = phase * a.kb_per_phase;
         // One tap = MT x 4 MMAs (K = 64) against one weight k-block.  The issuing thread is the
         // critical resource (an MMA with N = 64 occupies the tensor pipe for only 32 cycles), so all
-        // descriptor arithmetic is 32-bit adds on the low word; the high words are constants.
+        // descriptor arithmetic is 32-bit adds on the low word; the high words are constants, and the
+        // common 3x3 / 2x2 / 1x1 halo cases are fully unrolled so tap offsets become immediates.
         const uint32_t d0 = tmem_base + (uint32_t)(rt.stage * a.MT) * (uint32_t)a.Npad;
         auto issue_tap = [&](uint32_t a_lo, uint32_t a_hi) {
           uint32_t b_lo;
@@ -876,10 +901,25 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
             if (a.a_mode) {
               mbar_wait(A_full(ra.stage), ra.phase, a.err_flag, 4);
               tc_fence_after();
+              if (s == 0 && ch == 0) dbg_stamp(a, mma_il, 4);
               const uint32_t st_lo = a_lo_base + (uint32_t)(ra.stage * a.MT) * aS16 + (uint32_t)(ky0 * HALO_W + kx0) * 8u;
-              for (int kxi = 0; kxi < a.nkx; ++kxi)
-                for (int kyi = 0; kyi < a.nky; ++kyi)
-                  issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
+              if (a.nkx == 3 && a.nky == 3) {
+#pragma unroll
+                for (int kxi = 0; kxi < 3; ++kxi)
+#pragma unroll
+                  for (int kyi = 0; kyi < 3; ++kyi)
+                    issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
+              } else if (a.nkx == 2 && a.nky == 2) {
+#pragma unroll
+                for (int kxi = 0; kxi < 2; ++kxi)
+#pragma unroll
+                  for (int kyi = 0; kyi < 2; ++kyi)
+                    issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
+              } else {
+                for (int kxi = 0; kxi < a.nkx; ++kxi)
+                  for (int kyi = 0; kyi < a.nky; ++kyi)
+                    issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
+              }
               tc_commit(A_empty(ra.stage));
               ra.next();
               continue;
@@ -899,6 +939,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
           }
         }
         tc_commit(T_full(rt.stage));
+        dbg_stamp(a, mma_il, 3);
+        ++mma_il;
         rt.next();
       }
     }
@@ -954,6 +996,8 @@ static EncodeTiledFn get_encode_fn() {
 static int g_a_mode = 1;
 static int g_b_resident = 1;
 static int g_epi_tma = 1;
+static unsigned long long* g_dbg = nullptr;
+void tc_set_debug(unsigned long long* p) { g_dbg = p; }
 void tc_set_mode(int a_mode, int b_resident) {
   g_a_mode = a_mode & 1;
   g_epi_tma = (a_mode & 2) ? 0 : 1;      // bit 1 of a_mode disables the TMA-staged epilogue
@@ -1015,6 +1059,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   a.ep = make_epi(d, nullptr);
   a.head_w = d.head_w; a.head_b = d.head_b;
   a.err_flag = err_flag;
+  a.dbg = g_dbg;
   {
     auto ok8 = [](const void* p, int ct, int coff) { return !p || ((ct % 8) == 0 && (coff % 8) == 0); };
     a.fast = (d.N % 16 == 0) && d.temb_bstride == 0 &&

@@ -109,6 +109,8 @@ int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream);
  * descriptor start offsets (default; validated on B200); +2 disables the TMA-staged epilogue.
  * b_resident: keep all weight k-blocks in shared memory when they fit. */
 int srd_tc_set_mode(int32_t a_mode, int32_t b_resident);
+/* Debug: plans created afterwards record per-item clock64 stamps into buf [grid][64][8] (NULL = off). */
+int srd_tc_set_debug(void* buf);
 /* Non-zero after the tcgen05 pipeline watchdog fired (value = which wait timed out). */
 int srd_watchdog_flag(void);
 
