@@ -7,7 +7,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libsrdiff_b200.so")
+# SRD_LIB_PATH: developer override used to A/B kernel build variants on the GPU box
+LIB_PATH = os.environ.get("SRD_LIB_PATH") or os.path.join(_HERE, "libsrdiff_b200.so")
 
 SRD_MAX_SRC = 3
 F32, BF16 = 0, 1

@@ -27,7 +27,21 @@
 
 namespace srd {
 
-constexpr int TC_THREADS = 320;          // TMA warp + MMA warp + 8 epilogue warps
+#ifndef SRD_EPI_WARPS
+#define SRD_EPI_WARPS 16
+#endif
+#ifndef SRD_ROLES_HIGH
+#define SRD_ROLES_HIGH 1
+#endif
+constexpr int EPI_WARPS = SRD_EPI_WARPS; // groups of 4 warps (one warp per TMEM lane quarter)
+constexpr int EPI_GROUPS = EPI_WARPS / 4;
+constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
+// Warp roles.  The SMSP arbiter prefers the highest warp id, so the two single-thread roles
+// (TMA producer, MMA issuer) sit ABOVE the issue-heavy epilogue warps: an MMA that is ready to
+// issue must never queue behind Mish arithmetic.
+constexpr int WARP_EPI0 = SRD_ROLES_HIGH ? 0 : 2;
+constexpr int WARP_TMA = SRD_ROLES_HIGH ? EPI_WARPS : 0;
+constexpr int WARP_MMA = SRD_ROLES_HIGH ? EPI_WARPS + 1 : 1;
 constexpr int TILE_W = 8, TILE_H = 16;
 constexpr int BOX_ROWS = TILE_H + 2;
 constexpr int A_BYTES = BOX_ROWS * TILE_W * 128;   // 18432: one {64ch x 8px x 18rows} bf16 box
@@ -36,7 +50,7 @@ constexpr int A_HALO_BYTES = BOX_ROWS * HALO_W * 128;      // 23040: one {64ch x
 constexpr int A_HALO_STAGE = (A_HALO_BYTES + 1023) / 1024 * 1024;
 constexpr int MAX_STAGES = 8;
 constexpr int DBG_ITEMS = 64;
-constexpr int BAR_BYTES = 512;           // mbarriers + TMEM slot
+constexpr int BAR_BYTES = 1024;          // mbarriers + TMEM slot
 constexpr int VEC_BYTES = (512 + 1024 + 4 + 2 * 128 * 4) * 4;   // epilogue vectors (see conv_tc_kernel)
 
 struct TcArgs {
@@ -68,7 +82,9 @@ struct TcArgs {
   int kb_total;
   int b_region_bytes;      // bytes of the weight region (ring or resident)
   int epi_tma;             // TMA-staged epilogue (see epilogue_tma)
-  int epi_nbuf;            // staging buffers per epilogue half (1 | 2)
+  int epi_nbuf;            // staging buffers per epilogue warp (1)
+  int n_stages;            // TMEM accumulator stages (2 | 4); epilogue group g owns stage g % n_stages
+  int n_share;             // epilogue groups sharing one stage (4 / n_stages); they split the sub-tiles
   unsigned long long* dbg; // optional timeline buffer [cta][DBG_ITEMS][8] of clock64 stamps (debug)
 };
 
@@ -383,27 +399,30 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
                                               uint32_t t_full0, uint32_t t_empty0, int warp, int lane) {
   const int S = a.up;
   const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
-  const int half = (warp - 2) >> 2;
+  const int group = (warp - WARP_EPI0) >> 2;    // epilogue group
+  const int stage = group % a.n_stages, share = group / a.n_stages;
   const int m = quarter * 32 + lane;
   const int g = m >> 3, px = m & 7;
   const int nchunks = a.Npad >> 4;
   const bool has_head = es.head_w != nullptr;
   const int Ho = a.ep.H_out, Wo = a.ep.W_out;
-  const uint32_t t_full = t_full0 + 8u * half, t_empty = t_empty0 + 8u * half;
-  for (int it = half;; it += 2) {
+  const uint32_t t_full = t_full0 + 8u * stage, t_empty = t_empty0 + 8u * stage;
+  // groups sharing a stage split the 16-column chunks round-robin
+  const int c_first = share, c_step = a.n_share;
+  for (int it = stage;; it += a.n_stages) {
     const int item = blockIdx.x + it * gridDim.x;
     if (item >= a.n_items) break;
     const int phase = item / a.items_per_phase;
     const int t0 = (item % a.items_per_phase) * a.MT;
     const int pr = phase / S, ps = phase % S;
-    mbar_wait(t_full, (uint32_t)(it >> 1) & 1u, a.err_flag, 6);
+    mbar_wait(t_full, (uint32_t)(it / a.n_stages) & 1u, a.err_flag, 6);
     tc_fence_after();
     bool released = false;
     for (int mt = 0; mt < a.MT; ++mt) {
       const TileGeo tg = tile_geo(a, t0 + mt, g, px);
       const bool valid = tg.valid;
       const int b = tg.b, oy = tg.y * S + pr, ox = tg.x * S + ps;
-      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((half * a.MT + mt) * a.Npad);
+      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((stage * a.MT + mt) * a.Npad);
       float head[4] = {0.f, 0.f, 0.f, 0.f};
       const bool last_tile = (mt == a.MT - 1);
       if (a.fast) {
@@ -418,40 +437,29 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
         tp.r1 = (a.ep.res1 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res1) + pix * a.ep.res1_ct + a.ep.res1_coff : nullptr;
         tp.r2 = (a.ep.res2 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
         const long long wp = (long long)(Wo + 2);
-        // two residual register sets (A/B), alternated so prefetching needs no copies
-        uint4 A1[2] = {}, A2[2] = {}, B1[2] = {}, B2[2] = {};
-        auto ldres = [&](int c, uint4 (&x1)[2], uint4 (&x2)[2]) {
-          if (tp.r1) ld16_bf16(tp.r1 + 16 * c, x1);
-          if (tp.r2) ld16_bf16(tp.r2 + 16 * c, x2);
-        };
-        auto one = [&](int c, const uint4 (&c1)[2], const uint4 (&c2)[2], uint4 (&n1)[2], uint4 (&n2)[2]) {
+#pragma unroll 1
+        for (int c = c_first; c < nchunks; c += c_step) {
           uint32_t r[16];
           tc_ld16(tbase + (uint32_t)(c * 16), r);
-          if (c + 1 < nchunks) ldres(c + 1, n1, n2);             // prefetch behind this chunk's math
+          uint4 q1[2] = {}, q2[2] = {};
+          if (tp.r1) ld16_bf16(tp.r1 + 16 * c, q1);
+          if (tp.r2) ld16_bf16(tp.r2 + 16 * c, q2);
           tc_ld_wait();
-          if (last_tile && c + 1 >= nchunks) {                   // accumulator fully read: release the TMEM stage
+          if (last_tile && c + c_step >= nchunks) {              // accumulator fully read: release the TMEM stage
             tc_fence_before();
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty);
             released = true;
           }
-          epi_chunk_fast<ACT>(a, es, c * 16, r, tp, wp, c1, c2, head);
-        };
-        int c = 0;
-        ldres(0, A1, A2);
-        while (c < nchunks) {
-          one(c, A1, A2, B1, B2);
-          if (++c >= nchunks) break;
-          one(c, B1, B2, A1, A2);
-          ++c;
+          epi_chunk_fast<ACT>(a, es, c * 16, r, tp, wp, q1, q2, head);
         }
         if (has_head && valid) {
           for (int jh = 0; jh < a.ep.planar_c; ++jh)
             a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
         }
       } else {
-        // generic path (ragged N, per-image temb rows, planar output)
-        for (int c0 = 0; c0 < a.Npad; c0 += 16) {
+        // generic path (ragged N, per-image temb rows, planar output): one group per stage does all chunks
+        for (int c0 = 0; c0 < (share == 0 ? a.Npad : 0); c0 += 16) {
           uint32_t r[16];
           tc_ld16(tbase + (uint32_t)c0, r);
           tc_ld_wait();
@@ -473,7 +481,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
             }
           }
         }
-        if (has_head && valid) {
+        if (has_head && valid && share == 0) {
           for (int jh = 0; jh < a.ep.planar_c; ++jh)
             a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
         }
@@ -526,26 +534,29 @@ template <int ACT>
 __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es, const StageSmem& sg,
                                              uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0,
                                              int warp, int lane) {
-  const int quarter = warp & 3, half = (warp - 2) >> 2;
+  const int quarter = warp & 3, group = (warp - WARP_EPI0) >> 2;
+  const int stage = group % a.n_stages, share = group / a.n_stages;
   const int m = quarter * 32 + lane;
   const int g = m >> 3, px = m & 7;
   const int nsj = a.Npad >> 6;                   // 64-channel sub-tiles per tile
   const int n_sub = a.MT * nsj;                  // sub-tiles per item
+  const int n_q = (n_sub - share + a.n_share - 1) / a.n_share;   // sub-tiles of an item handled by this group
   const int nbuf = a.epi_nbuf;
   const int Ho = a.ep.H_out, Wo = a.ep.W_out;
   const bool reflect = (a.ep.border == SRD_BORDER_REFLECT);
   const bool has_r1 = a.ep.res1 != nullptr;
-  const uint32_t t_full = t_full0 + 8u * half, t_empty = t_empty0 + 8u * half;
+  const uint32_t t_full = t_full0 + 8u * stage, t_empty = t_empty0 + 8u * stage;
   const uint32_t swz = (uint32_t)(lane & 7);     // == m & 7
   uint8_t* my_row = sg.gen + lane * 128;         // this pixel's 128 B row inside a staging buffer
   const int g0 = quarter * 4;                    // first tile row of this warp
 
   // lane 0: make buffer (kn % nbuf) ready for this warp's rows of sub-tile kn
   auto prepare = [&](uint32_t kn) {
-    const int itn = half + 2 * (int)(kn / (uint32_t)n_sub);
+    if (n_q == 0) return;
+    const int itn = stage + a.n_stages * (int)(kn / (uint32_t)n_q);
     const int item = blockIdx.x + itn * gridDim.x;
     if (item >= a.n_items) return;
-    const int rem = (int)(kn % (uint32_t)n_sub);
+    const int rem = share + a.n_share * (int)(kn % (uint32_t)n_q);
     const int mt = rem / nsj, j = rem - mt * nsj;
     const int tt = (item % a.items_per_phase) * a.MT + mt;
     const int rowblk = tt / a.n_colblk, colblk = tt - rowblk * a.n_colblk;
@@ -561,30 +572,40 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
 
   uint32_t k = 0;
   if (lane == 0) prepare(0);
-  for (int it = half;; it += 2) {
+  for (int it = stage;; it += a.n_stages) {
     const int item = blockIdx.x + it * gridDim.x;
     if (item >= a.n_items) break;
     const int t0 = (item % a.items_per_phase) * a.MT;
-    mbar_wait(t_full, (uint32_t)(it >> 1) & 1u, a.err_flag, 6);
+    mbar_wait(t_full, (uint32_t)(it / a.n_stages) & 1u, a.err_flag, 6);
     tc_fence_after();
     if (quarter == 0 && lane == 0) dbg_stamp(a, it, 5);
-    for (int mt = 0; mt < a.MT; ++mt) {
-      const TileGeo tg = tile_geo(a, t0 + mt, g, px);
-      const bool valid = tg.valid;
-      const int b = tg.b, oy = tg.y, ox = tg.x;
-      const size_t pix = valid ? ((size_t)(b * (Ho + 2) + oy + 1) * (Wo + 2) + ox + 1) : 0;
-      uint32_t edge = 0;
-      if (valid && reflect)
-        edge = (oy == 1 ? 1u : 0u) | (oy == Ho - 2 ? 2u : 0u) | (ox == 1 ? 4u : 0u) | (ox == Wo - 2 ? 8u : 0u);
-      __nv_bfloat16* outp = static_cast<__nv_bfloat16*>(a.ep.out) + pix * a.ep.out_ct + a.ep.out_coff;
-      const __nv_bfloat16* r2p = (a.ep.res2 && valid)
-          ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
-      const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((half * a.MT + mt) * a.Npad);
-      for (int j = 0; j < nsj; ++j, ++k) {
+    bool released = false;
+    int mt_cur = -1;
+    TileGeo tg;
+    bool valid = false;
+    size_t pix = 0;
+    uint32_t edge = 0, tbase = 0;
+    __nv_bfloat16* outp = nullptr;
+    const __nv_bfloat16* r2p = nullptr;
+    {
+      for (int qq = share; qq < n_sub; qq += a.n_share, ++k) {
+        const int mt = qq / nsj, j = qq - mt * nsj;
+        if (mt != mt_cur) {
+          mt_cur = mt;
+          tg = tile_geo(a, t0 + mt, g, px);
+          valid = tg.valid;
+          pix = valid ? ((size_t)(tg.b * (Ho + 2) + tg.y + 1) * (Wo + 2) + tg.x + 1) : 0;
+          edge = 0;
+          if (valid && reflect)
+            edge = (tg.y == 1 ? 1u : 0u) | (tg.y == Ho - 2 ? 2u : 0u) | (tg.x == 1 ? 4u : 0u) | (tg.x == Wo - 2 ? 8u : 0u);
+          outp = static_cast<__nv_bfloat16*>(a.ep.out) + pix * a.ep.out_ct + a.ep.out_coff;
+          r2p = (a.ep.res2 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
+          tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((stage * a.MT + mt) * a.Npad);
+        }
         const uint32_t buf = k % (uint32_t)nbuf;
         uint8_t* row = my_row + buf * 4096u;
         mbar_wait(sg.r_full0 + 8u * buf, (k / (uint32_t)nbuf) & 1u, a.err_flag, 8);   // buffer free / residual landed
-        const bool last_sub = (mt == a.MT - 1 && j == nsj - 1);
+        const bool last_sub = (qq + a.n_share >= n_sub);
         // Compact hot loop (one 16-channel chunk per iteration, NOT unrolled: the body must stay
         // resident in the instruction cache; rare ring / second-residual work lives outside).
 #pragma unroll 1
@@ -603,6 +624,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
             __syncwarp();
             if (lane == 0) mbar_arrive(t_empty);
             if (quarter == 0 && lane == 0) dbg_stamp(a, it, 6);
+            released = true;
           }
           float v[16];
 #pragma unroll
@@ -693,6 +715,11 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
         __syncwarp();
       }
     }
+    if (!released) {                                             // this group had no sub-tile in the item
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(t_empty);
+    }
     if (quarter == 0 && lane == 0) dbg_stamp(a, it, 7);
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -705,8 +732,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const int B_BYTES = a.Npad * 128;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)a.a_stages * a.MT * a.a_stage_bytes;
-  const uint32_t stg_base = b_base + (uint32_t)a.b_region_bytes;        // staging: [half][buf][16 KB]
-  const uint32_t stg_bytes = a.epi_tma ? (uint32_t)(2 * a.epi_nbuf) * 16384u : 0u;
+  const uint32_t stg_base = b_base + (uint32_t)a.b_region_bytes;        // staging: [epilogue warp][buf][4 KB]
+  const uint32_t stg_bytes = a.epi_tma ? (uint32_t)(EPI_WARPS * a.epi_nbuf) * 4096u : 0u;
   const uint32_t bar_base = stg_base + stg_bytes;
   // barrier layout (8 B each): A_full[8] A_empty[8] B_full[8] B_empty[8] T_full[2] T_empty[2]
   auto A_full = [&](int s) { return bar_base + 8u * s; };
@@ -714,12 +741,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   auto B_full = [&](int s) { return bar_base + 8u * (2 * MAX_STAGES + s); };
   auto B_empty = [&](int s) { return bar_base + 8u * (3 * MAX_STAGES + s); };
   auto T_full = [&](int s) { return bar_base + 8u * (4 * MAX_STAGES + s); };
-  auto T_empty = [&](int s) { return bar_base + 8u * (4 * MAX_STAGES + 2 + s); };
-  const uint32_t tmem_slot = bar_base + 8u * (4 * MAX_STAGES + 4);
-  const uint32_t B_res = bar_base + 8u * (4 * MAX_STAGES + 5);
-  const uint32_t R_full0 = bar_base + 8u * (4 * MAX_STAGES + 6);        // [epilogue warp][buf] -> 16 barriers
+  auto T_empty = [&](int s) { return bar_base + 8u * (4 * MAX_STAGES + 4 + s); };
+  const uint32_t tmem_slot = bar_base + 8u * (4 * MAX_STAGES + 8);
+  const uint32_t B_res = bar_base + 8u * (4 * MAX_STAGES + 9);
+  const uint32_t R_full0 = bar_base + 8u * (4 * MAX_STAGES + 10);       // [epilogue warp][2] -> 32 barriers
   uint8_t* gen_base = smem_raw + (bar_base - smem_u32(smem_raw));       // generic pointer to bar_base
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + 8 * (4 * MAX_STAGES + 4));
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + 8 * (4 * MAX_STAGES + 8));
   float* vec = reinterpret_cast<float*>(gen_base + BAR_BYTES);
   float* s_bias = vec;                 // [256]
   float* s_temb = vec + 256;           // [256]
@@ -727,12 +754,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   float* s_headb = vec + 512 + 1024;   // [4]
   float* s_hpart = vec + 512 + 1024 + 4;   // [2][128][4]
 
-  if (warp == 0 && lane == 0) {
+  if (warp == WARP_TMA && lane == 0) {
     for (int s = 0; s < a.a_stages; ++s) { mbar_init(A_full(s), 1); mbar_init(A_empty(s), 1); }
     for (int s = 0; s < a.b_stages; ++s) { mbar_init(B_full(s), 1); mbar_init(B_empty(s), 1); }
-    for (int s = 0; s < 2; ++s) { mbar_init(T_full(s), 1); mbar_init(T_empty(s), 4); }
+    for (int s = 0; s < 4; ++s) { mbar_init(T_full(s), 1); mbar_init(T_empty(s), (uint32_t)(4 * a.n_share)); }
     mbar_init(B_res, 1);
-    for (int s = 0; s < 16; ++s) mbar_init(R_full0 + 8u * s, 1);
+    for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(R_full0 + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int s = 0; s < a.n_src; ++s)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA[s]) : "memory");
@@ -743,7 +770,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       if (a.ep.res1) asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmR) : "memory");
     }
   }
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
                  : "memory");
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
@@ -766,7 +793,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   const int S = a.up;
-  if (warp == 0) {
+  if (warp == WARP_TMA) {
     // ================================================================= TMA producer
     if (elect_one_sync()) {
       Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages};
@@ -842,10 +869,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == WARP_MMA) {
     // ================================================================= MMA issuer
     if (elect_one_sync()) {
-      Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages}, rt{0, 0, 2};
+      Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages}, rt{0, 0, a.n_stages};
       const uint32_t bB16 = (uint32_t)B_BYTES >> 4, aS16 = (uint32_t)a.a_stage_bytes >> 4;
       const uint32_t a_lo_base = a_base >> 4, b_lo_base = b_base >> 4;
       if (a.b_resident) {
@@ -950,7 +977,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     es.bias = s_bias; es.temb = s_temb;
     es.head_w = a.head_w ? s_head : nullptr; es.head_b = s_headb; es.hpart = s_hpart;
     if (a.epi_tma) {
-      const int ew = warp - 2;                         // epilogue warp 0..7
+      const int ew = warp - WARP_EPI0;                 // epilogue warp index
       StageSmem sg;
       sg.base = stg_base + (uint32_t)(ew * a.epi_nbuf) * 4096u;
       sg.gen = smem_raw + (sg.base - smem_u32(smem_raw));
@@ -969,7 +996,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 
   tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == WARP_MMA) {
     tc_fence_after();
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
@@ -1077,12 +1104,13 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   const long long res_bytes = (long long)a.kb_total * B_BYTES;
   const long long n_tiles_all = (long long)n_phase * a.tiles_per_phase;
   const bool mt2_ok = (2 * 2 * a.Npad <= 512) && n_tiles_all >= 2LL * n_sm;
+  const int nbuf_max = EPI_WARPS <= 8 ? 2 : 1;   // 4 KB staging buffers per epilogue warp
   bool planned = false;
   int b_bytes_total = 0, stage_bytes = 0;
   // preference: staging depth 2 before 1; resident weights (MT = 1: nothing is re-streamed) before a ring;
   // for rings MT = 2 (each weight tile shared by two M tiles) before MT = 1.
-  for (int nbuf = a.epi_tma ? 2 : 0; !planned; --nbuf) {
-    const int stg = 2 * nbuf * 16384;
+  for (int nbuf = a.epi_tma ? nbuf_max : 0; !planned; --nbuf) {
+    const int stg = EPI_WARPS * nbuf * 4096;
     for (int pass = 0; pass < 3 && !planned; ++pass) {
       const bool resident = (pass == 0);
       const int MT = resident ? 1 : (pass == 1 ? 2 : 1);
@@ -1123,7 +1151,10 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   a.items_per_phase = (a.tiles_per_phase + a.MT - 1) / a.MT;
   a.n_items = n_phase * a.items_per_phase;
   a.b_region_bytes = b_bytes_total;
-  const int stg_total = a.epi_tma ? 2 * a.epi_nbuf * 16384 : 0;
+  const int stg_total = a.epi_tma ? EPI_WARPS * a.epi_nbuf * 4096 : 0;
+  a.n_stages = (EPI_GROUPS * a.MT * a.Npad <= 512) ? EPI_GROUPS : 2;
+  a.n_share = EPI_GROUPS / a.n_stages;
+  SRD_CHECK(!d.head_w || a.n_share == 1, "conv_tc: fused head needs N * MT <= 128");
   plan->smem = a.a_stages * stage_bytes + b_bytes_total + stg_total + BAR_BYTES + VEC_BYTES + 1024;
   plan->grid = a.n_items < n_sm ? a.n_items : n_sm;
 
