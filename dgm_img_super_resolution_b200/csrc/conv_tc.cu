@@ -53,6 +53,23 @@ constexpr int DBG_ITEMS = 64;
 constexpr int BAR_BYTES = 1024;          // mbarriers + TMEM slot
 constexpr int VEC_BYTES = (512 + 1024 + 4 + 2 * 128 * 4) * 4;   // epilogue vectors (see conv_tc_kernel)
 
+// Exact n / d for n < 2^24 as one 32x32->64 multiply and a shift (the single-thread roles and the
+// per-tile epilogue decode must not run ~40-instruction integer divisions).
+struct FastDiv {
+  uint32_t mul, shr;
+};
+__host__ inline FastDiv make_fastdiv(uint32_t d) {
+  uint32_t s = 0;
+  while ((1u << s) < d) ++s;
+  FastDiv f;
+  f.shr = 24 + s;
+  f.mul = (uint32_t)((((uint64_t)1 << f.shr) + d - 1) / d);
+  return f;
+}
+__device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
+  return (int)(((uint64_t)(uint32_t)n * f.mul) >> f.shr);
+}
+
 struct TcArgs {
   CUtensorMap tmA[SRD_MAX_SRC];
   CUtensorMap tmB;
@@ -64,6 +81,8 @@ struct TcArgs {
   int H_m, W_m;            // output positions per image (per phase)
   int period, voff, vstart, n_vrows;
   int n_colblk, tiles_per_phase, items_per_phase, n_items;
+  FastDiv fd_ipp, fd_colblk, fd_period, fd_up;   // dividers by items_per_phase, n_colblk, period, up
+  int n_chunks;            // 64-channel K chunks per item over all sources
   int stride, nky, nkx, ky0, kx0, up;
   int Npad, MT;
   int a_stages, b_stages;
@@ -192,9 +211,15 @@ __device__ __forceinline__ bool elect_one_sync() {
   return pred != 0;
 }
 
+// Debug timeline (tools/timeline_conv.py); compiled in only with -DSRD_TC_DEBUG so the role loops
+// of the product build carry no extra code.
 __device__ __forceinline__ void dbg_stamp(const TcArgs& a, int item_local, int ev) {
+#ifdef SRD_TC_DEBUG
   if (a.dbg && item_local < DBG_ITEMS)
     a.dbg[((size_t)blockIdx.x * DBG_ITEMS + item_local) * 8 + ev] = (unsigned long long)clock64();
+#else
+  (void)a; (void)item_local; (void)ev;
+#endif
 }
 
 struct Ring {
@@ -375,10 +400,10 @@ struct TileGeo {
 };
 __device__ __forceinline__ TileGeo tile_geo(const TcArgs& a, int tt, int g, int px) {
   TileGeo t;
-  const int rowblk = tt / a.n_colblk, colblk = tt - rowblk * a.n_colblk;
+  const int rowblk = fdiv(tt, a.fd_colblk), colblk = tt - rowblk * a.n_colblk;
   t.V0 = rowblk * TILE_H + a.vstart;
   t.x0 = colblk * TILE_W;
-  int b = t.V0 / a.period;
+  int b = fdiv(t.V0, a.fd_period);
   int vv = t.V0 - b * a.period + g;
   while (vv >= a.period) { vv -= a.period; ++b; }
   t.b = b;
@@ -409,13 +434,14 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
   const uint32_t t_full = t_full0 + 8u * stage, t_empty = t_empty0 + 8u * stage;
   // groups sharing a stage split the 16-column chunks round-robin
   const int c_first = share, c_step = a.n_share;
-  for (int it = stage;; it += a.n_stages) {
+  uint32_t round = 0;                           // it / n_stages: parity of this TMEM stage
+  for (int it = stage;; it += a.n_stages, ++round) {
     const int item = blockIdx.x + it * gridDim.x;
     if (item >= a.n_items) break;
-    const int phase = item / a.items_per_phase;
-    const int t0 = (item % a.items_per_phase) * a.MT;
-    const int pr = phase / S, ps = phase % S;
-    mbar_wait(t_full, (uint32_t)(it / a.n_stages) & 1u, a.err_flag, 6);
+    const int phase = fdiv(item, a.fd_ipp);
+    const int t0 = (item - phase * a.items_per_phase) * a.MT;
+    const int pr = fdiv(phase, a.fd_up), ps = phase - pr * S;
+    mbar_wait(t_full, round & 1u, a.err_flag, 6);
     tc_fence_after();
     bool released = false;
     for (int mt = 0; mt < a.MT; ++mt) {
@@ -540,7 +566,6 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   const int g = m >> 3, px = m & 7;
   const int nsj = a.Npad >> 6;                   // 64-channel sub-tiles per tile
   const int n_sub = a.MT * nsj;                  // sub-tiles per item
-  const int n_q = (n_sub - share + a.n_share - 1) / a.n_share;   // sub-tiles of an item handled by this group
   const int nbuf = a.epi_nbuf;
   const int Ho = a.ep.H_out, Wo = a.ep.W_out;
   const bool reflect = (a.ep.border == SRD_BORDER_REFLECT);
@@ -550,17 +575,19 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   uint8_t* my_row = sg.gen + lane * 128;         // this pixel's 128 B row inside a staging buffer
   const int g0 = quarter * 4;                    // first tile row of this warp
 
-  // lane 0: make buffer (kn % nbuf) ready for this warp's rows of sub-tile kn
-  auto prepare = [&](uint32_t kn) {
-    if (n_q == 0) return;
-    const int itn = stage + a.n_stages * (int)(kn / (uint32_t)n_q);
+  const uint32_t nbuf_mask = (uint32_t)nbuf - 1u, nbuf_sh = (uint32_t)nbuf >> 1;   // nbuf is 1 or 2
+  // lane 0: make buffer (kn % nbuf) ready for this warp's rows of its kn-th sub-tile, which is
+  // sub-tile qn of local item itn (the successor of the one just finished: no divisions)
+  auto prepare = [&](uint32_t kn, int itn, int qn) {
+    if (qn >= n_sub) { itn += a.n_stages; qn = share; }
+    if (qn >= n_sub) return;                                   // this group never has a sub-tile
     const int item = blockIdx.x + itn * gridDim.x;
     if (item >= a.n_items) return;
-    const int rem = share + a.n_share * (int)(kn % (uint32_t)n_q);
-    const int mt = rem / nsj, j = rem - mt * nsj;
-    const int tt = (item % a.items_per_phase) * a.MT + mt;
-    const int rowblk = tt / a.n_colblk, colblk = tt - rowblk * a.n_colblk;
-    const uint32_t buf = kn % (uint32_t)nbuf;
+    const int mt = (qn >= nsj) ? 1 : 0, j = qn - mt * nsj;     // MT <= 2
+    const int ph = fdiv(item, a.fd_ipp);
+    const int tt = (item - ph * a.items_per_phase) * a.MT + mt;
+    const int rowblk = fdiv(tt, a.fd_colblk), colblk = tt - rowblk * a.n_colblk;
+    const uint32_t buf = kn & nbuf_mask;
     const uint32_t bar = sg.r_full0 + 8u * buf;
     if (has_r1) {
       mbar_expect_tx(bar, 4096u);
@@ -570,13 +597,13 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     }
   };
 
-  uint32_t k = 0;
-  if (lane == 0) prepare(0);
-  for (int it = stage;; it += a.n_stages) {
+  uint32_t k = 0, round = 0;
+  if (lane == 0) prepare(0, stage, share);
+  for (int it = stage;; it += a.n_stages, ++round) {
     const int item = blockIdx.x + it * gridDim.x;
     if (item >= a.n_items) break;
-    const int t0 = (item % a.items_per_phase) * a.MT;
-    mbar_wait(t_full, (uint32_t)(it / a.n_stages) & 1u, a.err_flag, 6);
+    const int t0 = (item - fdiv(item, a.fd_ipp) * a.items_per_phase) * a.MT;
+    mbar_wait(t_full, round & 1u, a.err_flag, 6);
     tc_fence_after();
     if (quarter == 0 && lane == 0) dbg_stamp(a, it, 5);
     bool released = false;
@@ -589,7 +616,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     const __nv_bfloat16* r2p = nullptr;
     {
       for (int qq = share; qq < n_sub; qq += a.n_share, ++k) {
-        const int mt = qq / nsj, j = qq - mt * nsj;
+        const int mt = (qq >= nsj) ? 1 : 0, j = qq - mt * nsj;
         if (mt != mt_cur) {
           mt_cur = mt;
           tg = tile_geo(a, t0 + mt, g, px);
@@ -602,9 +629,9 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
           r2p = (a.ep.res2 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
           tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((stage * a.MT + mt) * a.Npad);
         }
-        const uint32_t buf = k % (uint32_t)nbuf;
+        const uint32_t buf = k & nbuf_mask;
         uint8_t* row = my_row + buf * 4096u;
-        mbar_wait(sg.r_full0 + 8u * buf, (k / (uint32_t)nbuf) & 1u, a.err_flag, 8);   // buffer free / residual landed
+        mbar_wait(sg.r_full0 + 8u * buf, (k >> nbuf_sh) & 1u, a.err_flag, 8);   // buffer free / residual landed
         const bool last_sub = (qq + a.n_share >= n_sub);
         // Compact hot loop (one 16-channel chunk per iteration, NOT unrolled: the body must stay
         // resident in the instruction cache; rare ring / second-residual work lives outside).
@@ -687,7 +714,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
           bool whole = !reflect;
           int yp0 = 0;
           if (reflect) {                                           // stride 1: virtual row == padded stacked row
-            const int b0 = V0 / a.period;
+            const int b0 = fdiv(V0, a.fd_period);
             yp0 = V0 - b0 * a.period;
             whole = (yp0 >= 3) && (yp0 + 3 <= Ho - 2) && (V0 + 4 <= a.n_vrows);
           }
@@ -710,7 +737,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
           // the buffer of sub-tile k+1 was last read by the store of sub-tile k+1-nbuf
           if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          prepare(k + 1);
+          prepare(k + 1, it, qq + a.n_share);
         }
         __syncwarp();
       }
@@ -723,6 +750,226 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     if (quarter == 0 && lane == 0) dbg_stamp(a, it, 7);
   }
   if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+}
+
+
+// ------------------------------------------------------------------------------------------ roles
+// barrier layout (8 B each) at bar_base: A_full[8] A_empty[8] B_full[8] B_empty[8] T_full[4] T_empty[4]
+// tmem_slot B_res R_full[2 * EPI_WARPS]
+struct Bars {
+  uint32_t base;
+  __device__ __forceinline__ uint32_t A_full(int s) const { return base + 8u * s; }
+  __device__ __forceinline__ uint32_t A_empty(int s) const { return base + 8u * (MAX_STAGES + s); }
+  __device__ __forceinline__ uint32_t B_full(int s) const { return base + 8u * (2 * MAX_STAGES + s); }
+  __device__ __forceinline__ uint32_t B_empty(int s) const { return base + 8u * (3 * MAX_STAGES + s); }
+  __device__ __forceinline__ uint32_t T_full(int s) const { return base + 8u * (4 * MAX_STAGES + s); }
+  __device__ __forceinline__ uint32_t T_empty(int s) const { return base + 8u * (4 * MAX_STAGES + 4 + s); }
+  __device__ __forceinline__ uint32_t tmem_slot() const { return base + 8u * (4 * MAX_STAGES + 8); }
+  __device__ __forceinline__ uint32_t B_res() const { return base + 8u * (4 * MAX_STAGES + 9); }
+  __device__ __forceinline__ uint32_t R_full0() const { return base + 8u * (4 * MAX_STAGES + 10); }
+};
+
+// TMA producer (one thread).  Per (source, 64-channel chunk): ONE halo box per M tile (stride 1) or
+// one box per (kx, row parity) (stride 2), plus -- unless the weights are resident -- one weight
+// k-block per tap, in exactly the order the MMA role consumes them.
+__device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, uint32_t b_base, uint32_t bar_base) {
+  const Bars bars{bar_base};
+  const int n_items = a.n_items, G = (int)gridDim.x, MT = a.MT, S = a.up, Npad = a.Npad;
+  const int n_src = a.n_src, n_colblk = a.n_colblk, ipp = a.items_per_phase, vstart = a.vstart;
+  const int a_mode = a.a_mode, b_resident = a.b_resident, ntaps = a.nkx * a.nky, nkx = a.nkx;
+  const int stride = a.stride, kb_per_phase = a.kb_per_phase;
+  const uint32_t B_BYTES = (uint32_t)Npad * 128u, a_stage_bytes = (uint32_t)a.a_stage_bytes;
+  int* err = a.err_flag;
+  Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages};
+  if (b_resident) {
+    mbar_expect_tx(bars.B_res(), (uint32_t)a.kb_total * B_BYTES);
+    for (int kb = 0; kb < a.kb_total; ++kb)
+      tma_load_2d(b_base + (uint32_t)kb * B_BYTES, &a.tmB, bars.B_res(), 0, kb * Npad);
+  }
+  int il = 0;
+  for (int item = blockIdx.x; item < n_items; item += G, ++il) {
+    const int phase = fdiv(item, a.fd_ipp);
+    const int t0 = (item - phase * ipp) * MT;
+    int kx0 = a.kx0;
+    if (S > 1) { const int pr = fdiv(phase, a.fd_up); kx0 = (phase - pr * S >= S / 2) ? 1 : 0; }
+    // tile origins of this item
+    int V0[2], X0[2];
+    for (int mt = 0; mt < MT; ++mt) {
+      const int tt = t0 + mt;
+      const int rowblk = fdiv(tt, a.fd_colblk);
+      V0[mt] = rowblk * TILE_H + vstart;
+      X0[mt] = (tt - rowblk * n_colblk) * TILE_W;
+    }
+    int kb = phase * kb_per_phase;
+    for (int s = 0; s < n_src; ++s) {
+      const CUtensorMap* tm = &a.tmA[s];
+      const int nch = a.nchunk[s];
+      for (int ch = 0; ch < nch; ++ch) {
+        if (a_mode) {
+          mbar_wait(bars.A_empty(ra.stage), ra.phase ^ 1, err, 1);
+          if (s == 0 && ch == 0) dbg_stamp(a, il, 0);
+          mbar_expect_tx(bars.A_full(ra.stage), (uint32_t)(MT * A_HALO_BYTES));
+          for (int mt = 0; mt < MT; ++mt)
+            tma_load_3d(a_base + (uint32_t)(ra.stage * MT + mt) * a_stage_bytes, tm, bars.A_full(ra.stage),
+                        ch * 64, X0[mt], V0[mt] - 1);
+          ra.next();
+          if (!b_resident) {
+            for (int j = 0; j < ntaps; ++j) {
+              mbar_wait(bars.B_empty(rb.stage), rb.phase ^ 1, err, 2);
+              mbar_expect_tx(bars.B_full(rb.stage), B_BYTES);
+              tma_load_2d(b_base + (uint32_t)rb.stage * B_BYTES, &a.tmB, bars.B_full(rb.stage), 0, kb * Npad);
+              rb.next();
+              ++kb;
+            }
+          }
+          continue;
+        }
+        for (int kxi = 0; kxi < nkx; ++kxi) {
+          const int kxp = kx0 + kxi;
+          for (int ld = 0; ld < n_loads(a); ++ld) {
+            mbar_wait(bars.A_empty(ra.stage), ra.phase ^ 1, err, 1);
+            mbar_expect_tx(bars.A_full(ra.stage), (uint32_t)(MT * A_BYTES));
+            for (int mt = 0; mt < MT; ++mt) {
+              const uint32_t dst = a_base + (uint32_t)(ra.stage * MT + mt) * a_stage_bytes;
+              if (stride == 1)
+                tma_load_3d(dst, tm, bars.A_full(ra.stage), ch * 64, X0[mt] + kxp, V0[mt] - 1);
+              else
+                tma_load_5d(dst, tm, bars.A_full(ra.stage), ch * 64, kxp & 1, X0[mt] + (kxp >> 1), ld, V0[mt]);
+            }
+            ra.next();
+            if (!b_resident) {
+              const int nt = n_taps(a, ld, 0);
+              for (int j = 0; j < nt; ++j) {
+                mbar_wait(bars.B_empty(rb.stage), rb.phase ^ 1, err, 2);
+                mbar_expect_tx(bars.B_full(rb.stage), B_BYTES);
+                tma_load_2d(b_base + (uint32_t)rb.stage * B_BYTES, &a.tmB, bars.B_full(rb.stage), 0, kb * Npad);
+                rb.next();
+                ++kb;
+              }
+            }
+          }
+        }
+      }
+    }
+  }
+}
+
+// MMA issuer (one thread).  One tap = MT x 4 MMAs (K = 64) against one weight k-block.  The issuing
+// thread is a critical resource: a K = 16 MMA occupies the tensor pipe for only max(N/2, 32 + N/4)
+// cycles (measured, tools/umma_issue.cu), and this thread shares its scheduler with four epilogue
+// warps.  So: every launch constant lives in a register, descriptor arithmetic is 32-bit adds on
+// the low word (high words are constants), and for the 3x3 / 2x2 / 1x1 halo cases (TAPS = 9/4/1)
+// the tap loops are unrolled so tap offsets are immediates.  TAPS = 0: generic runtime loops
+// (stride 2, validation modes).
+template <int TAPS, int MT, bool BRES>
+__device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, uint32_t a_base, uint32_t b_base,
+                                         uint32_t bar_base) {
+  const Bars bars{bar_base};
+  const int n_items = a.n_items, G = (int)gridDim.x, S = a.up, n_chunks = a.n_chunks;
+  const uint32_t Npad = (uint32_t)a.Npad, idesc = a.idesc;
+  const uint32_t bB16 = Npad * 8u, aS16 = (uint32_t)a.a_stage_bytes >> 4;
+  const uint32_t a_lo_base = a_base >> 4, b_lo_base = b_base >> 4;
+  const uint32_t kbpp16 = (uint32_t)a.kb_per_phase * bB16;
+  int* err = a.err_flag;
+  Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages}, rt{0, 0, a.n_stages};
+  if (BRES) {
+    mbar_wait(bars.B_res(), 0, err, 7);
+    tc_fence_after();
+  }
+  int mma_il = 0;
+  for (int item = blockIdx.x; item < n_items; item += G) {
+    int ky0 = a.ky0, kx0 = a.kx0;
+    uint32_t b_cur = b_lo_base;
+    if (S > 1) {
+      const int phase = fdiv(item, a.fd_ipp);
+      const int pr = fdiv(phase, a.fd_up), ps = phase - pr * S;
+      ky0 = (pr >= S / 2) ? 1 : 0;
+      kx0 = (ps >= S / 2) ? 1 : 0;
+      b_cur += (uint32_t)phase * kbpp16;
+    }
+    dbg_stamp(a, mma_il, 1);
+    mbar_wait(bars.T_empty(rt.stage), rt.phase ^ 1, err, 3);
+    tc_fence_after();
+    dbg_stamp(a, mma_il, 2);
+    const uint32_t d0 = tmem_base + (uint32_t)(rt.stage * MT) * Npad;
+    uint32_t kcount = 0;     // 0 only for the first k-block of the item (accumulator overwrite)
+    auto issue_tap = [&](uint32_t a_lo, uint32_t a_hi) {
+      uint32_t b_lo;
+      if (BRES) {
+        b_lo = b_cur;
+        b_cur += bB16;
+      } else {
+        mbar_wait(bars.B_full(rb.stage), rb.phase, err, 5);
+        tc_fence_after();
+        b_lo = b_lo_base + (uint32_t)rb.stage * bB16;
+      }
+      tc_mma_bf16(d0, mk_desc(a_lo, a_hi), mk_desc(b_lo, DESC_HI_1024), idesc, kcount);
+      tc_mma_bf16(d0, mk_desc(a_lo + 2, a_hi), mk_desc(b_lo + 2, DESC_HI_1024), idesc, 1u);
+      tc_mma_bf16(d0, mk_desc(a_lo + 4, a_hi), mk_desc(b_lo + 4, DESC_HI_1024), idesc, 1u);
+      tc_mma_bf16(d0, mk_desc(a_lo + 6, a_hi), mk_desc(b_lo + 6, DESC_HI_1024), idesc, 1u);
+      if (MT == 2) {
+        const uint32_t d1 = d0 + Npad, a1 = a_lo + aS16;
+        tc_mma_bf16(d1, mk_desc(a1, a_hi), mk_desc(b_lo, DESC_HI_1024), idesc, kcount);
+        tc_mma_bf16(d1, mk_desc(a1 + 2, a_hi), mk_desc(b_lo + 2, DESC_HI_1024), idesc, 1u);
+        tc_mma_bf16(d1, mk_desc(a1 + 4, a_hi), mk_desc(b_lo + 4, DESC_HI_1024), idesc, 1u);
+        tc_mma_bf16(d1, mk_desc(a1 + 6, a_hi), mk_desc(b_lo + 6, DESC_HI_1024), idesc, 1u);
+      }
+      if (!BRES) {
+        tc_commit(bars.B_empty(rb.stage));
+        rb.next();
+      }
+      kcount = 1u;
+    };
+    if (TAPS > 0) {
+      constexpr int NK = TAPS == 9 ? 3 : (TAPS == 4 ? 2 : 1);
+      const uint32_t tap0 = (uint32_t)(ky0 * HALO_W + kx0) * 8u;
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) {
+        mbar_wait(bars.A_full(ra.stage), ra.phase, err, 4);
+        tc_fence_after();
+        if (c == 0) dbg_stamp(a, mma_il, 4);
+        const uint32_t st_lo = a_lo_base + (uint32_t)(ra.stage * MT) * aS16 + tap0;
+#pragma unroll
+        for (int kxi = 0; kxi < NK; ++kxi)
+#pragma unroll
+          for (int kyi = 0; kyi < NK; ++kyi)
+            issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
+        tc_commit(bars.A_empty(ra.stage));
+        ra.next();
+      }
+    } else {
+      const int a_mode = a.a_mode, nkx = a.nkx, nky = a.nky;
+      for (int c = 0; c < n_chunks; ++c) {
+        if (a_mode) {
+          mbar_wait(bars.A_full(ra.stage), ra.phase, err, 4);
+          tc_fence_after();
+          const uint32_t st_lo = a_lo_base + (uint32_t)(ra.stage * MT) * aS16 + (uint32_t)(ky0 * HALO_W + kx0) * 8u;
+          for (int kxi = 0; kxi < nkx; ++kxi)
+            for (int kyi = 0; kyi < nky; ++kyi)
+              issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
+          tc_commit(bars.A_empty(ra.stage));
+          ra.next();
+          continue;
+        }
+        for (int kxi = 0; kxi < nkx; ++kxi) {
+          for (int ld = 0; ld < n_loads(a); ++ld) {
+            mbar_wait(bars.A_full(ra.stage), ra.phase, err, 4);
+            tc_fence_after();
+            const uint32_t st_lo = a_lo_base + (uint32_t)(ra.stage * MT) * aS16;
+            const int nt = n_taps(a, ld, ky0);
+            for (int j = 0; j < nt; ++j)
+              issue_tap(st_lo + (uint32_t)tap_off(a, ld, j, ky0) * (TILE_W * 8u), DESC_HI_1024);
+            tc_commit(bars.A_empty(ra.stage));
+            ra.next();
+          }
+        }
+      }
+    }
+    tc_commit(bars.T_full(rt.stage));
+    dbg_stamp(a, mma_il, 3);
+    ++mma_il;
+    rt.next();
+  }
 }
 
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
@@ -792,184 +1039,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
-  const int S = a.up;
   if (warp == WARP_TMA) {
-    // ================================================================= TMA producer
-    if (elect_one_sync()) {
-      Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages};
-      if (a.b_resident) {
-        mbar_expect_tx(B_res, (uint32_t)(a.kb_total * B_BYTES));
-        for (int kb = 0; kb < a.kb_total; ++kb)
-          tma_load_2d(b_base + (uint32_t)kb * B_BYTES, &a.tmB, B_res, 0, kb * a.Npad);
-      }
-      int il = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x, ++il) {
-        const int phase = item / a.items_per_phase;
-        const int t0 = (item % a.items_per_phase) * a.MT;
-        const int pr = phase / S, ps = phase % S;
-        int ky0 = a.ky0, kx0 = a.kx0;
-        if (S > 1) { ky0 = (pr >= S / 2) ? 1 : 0; kx0 = (ps >= S / 2) ? 1 : 0; }
-        int kb = phase * a.kb_per_phase;
-        for (int s = 0; s < a.n_src; ++s) {
-          for (int ch = 0; ch < a.nchunk[s]; ++ch) {
-            if (a.a_mode) {
-              // ---- one halo box per (source, chunk): all taps come from it
-              mbar_wait(A_empty(ra.stage), ra.phase ^ 1, a.err_flag, 1);
-              if (s == 0 && ch == 0) dbg_stamp(a, il, 0);
-              mbar_expect_tx(A_full(ra.stage), (uint32_t)(a.MT * A_HALO_BYTES));
-              for (int mt = 0; mt < a.MT; ++mt) {
-                const int tt = t0 + mt;
-                const int rowblk = tt / a.n_colblk, colblk = tt % a.n_colblk;
-                const int V0 = rowblk * TILE_H + a.vstart, x0 = colblk * TILE_W;
-                tma_load_3d(a_base + (uint32_t)(ra.stage * a.MT + mt) * a.a_stage_bytes, &a.tmA[s],
-                            A_full(ra.stage), ch * 64, x0, V0 - 1);
-              }
-              ra.next();
-              if (!a.b_resident) {
-                for (int j = 0; j < a.nkx * a.nky; ++j) {
-                  mbar_wait(B_empty(rb.stage), rb.phase ^ 1, a.err_flag, 2);
-                  mbar_expect_tx(B_full(rb.stage), (uint32_t)B_BYTES);
-                  tma_load_2d(b_base + (uint32_t)rb.stage * B_BYTES, &a.tmB, B_full(rb.stage), 0, kb * a.Npad);
-                  rb.next();
-                  ++kb;
-                }
-              }
-              continue;
-            }
-            for (int kxi = 0; kxi < a.nkx; ++kxi) {
-              const int kxp = kx0 + kxi;
-              for (int ld = 0; ld < n_loads(a); ++ld) {
-                mbar_wait(A_empty(ra.stage), ra.phase ^ 1, a.err_flag, 1);
-                mbar_expect_tx(A_full(ra.stage), (uint32_t)(a.MT * A_BYTES));
-                for (int mt = 0; mt < a.MT; ++mt) {
-                  const int tt = t0 + mt;
-                  const int rowblk = tt / a.n_colblk, colblk = tt % a.n_colblk;
-                  const int V0 = rowblk * TILE_H + a.vstart, x0 = colblk * TILE_W;
-                  const uint32_t dst = a_base + (uint32_t)(ra.stage * a.MT + mt) * a.a_stage_bytes;
-                  if (a.stride == 1)
-                    tma_load_3d(dst, &a.tmA[s], A_full(ra.stage), ch * 64, x0 + kxp, V0 - 1);
-                  else
-                    tma_load_5d(dst, &a.tmA[s], A_full(ra.stage), ch * 64, kxp & 1, x0 + (kxp >> 1),
-                                ld, V0);
-                }
-                ra.next();
-                if (!a.b_resident) {
-                  const int nt = n_taps(a, ld, ky0);
-                  for (int j = 0; j < nt; ++j) {
-                    mbar_wait(B_empty(rb.stage), rb.phase ^ 1, a.err_flag, 2);
-                    mbar_expect_tx(B_full(rb.stage), (uint32_t)B_BYTES);
-                    tma_load_2d(b_base + (uint32_t)rb.stage * B_BYTES, &a.tmB, B_full(rb.stage), 0, kb * a.Npad);
-                    rb.next();
-                    ++kb;
-                  }
-                }
-              }
-            }
-          }
-        }
-      }
-    }
+    if (elect_one_sync()) producer_role(a, a_base, b_base, bar_base);
   } else if (warp == WARP_MMA) {
-    // ================================================================= MMA issuer
     if (elect_one_sync()) {
-      Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages}, rt{0, 0, a.n_stages};
-      const uint32_t bB16 = (uint32_t)B_BYTES >> 4, aS16 = (uint32_t)a.a_stage_bytes >> 4;
-      const uint32_t a_lo_base = a_base >> 4, b_lo_base = b_base >> 4;
-      if (a.b_resident) {
-        mbar_wait(B_res, 0, a.err_flag, 7);
-        tc_fence_after();
-      }
-      int mma_il = 0;
-      for (int item = blockIdx.x; item < a.n_items; item += gridDim.x) {
-        const int phase = item / a.items_per_phase;
-        const int pr = phase / S, ps = phase % S;
-        int ky0 = a.ky0, kx0 = a.kx0;
-        if (S > 1) { ky0 = (pr >= S / 2) ? 1 : 0; kx0 = (ps >= S / 2) ? 1 : 0; }
-        dbg_stamp(a, mma_il, 1);
-        mbar_wait(T_empty(rt.stage), rt.phase ^ 1, a.err_flag, 3);
-        tc_fence_after();
-        dbg_stamp(a, mma_il, 2);
-        uint32_t kcount = 0;     // 0 only for the first k-block of the item (accumulator overwrite)
-        int kb = phase * a.kb_per_phase;
-        // One tap = MT x 4 MMAs (K = 64) against one weight k-block.  The issuing thread is the
-        // critical resource (an MMA with N = 64 occupies the tensor pipe for only 32 cycles), so all
-        // descriptor arithmetic is 32-bit adds on the low word; the high words are constants, and the
-        // common 3x3 / 2x2 / 1x1 halo cases are fully unrolled so tap offsets become immediates.
-        const uint32_t d0 = tmem_base + (uint32_t)(rt.stage * a.MT) * (uint32_t)a.Npad;
-        auto issue_tap = [&](uint32_t a_lo, uint32_t a_hi) {
-          uint32_t b_lo;
-          if (a.b_resident) {
-            b_lo = b_lo_base + (uint32_t)kb * bB16;
-          } else {
-            mbar_wait(B_full(rb.stage), rb.phase, a.err_flag, 5);
-            tc_fence_after();
-            b_lo = b_lo_base + (uint32_t)rb.stage * bB16;
-          }
-          tc_mma_bf16(d0, mk_desc(a_lo, a_hi), mk_desc(b_lo, DESC_HI_1024), a.idesc, kcount);
-          tc_mma_bf16(d0, mk_desc(a_lo + 2, a_hi), mk_desc(b_lo + 2, DESC_HI_1024), a.idesc, 1u);
-          tc_mma_bf16(d0, mk_desc(a_lo + 4, a_hi), mk_desc(b_lo + 4, DESC_HI_1024), a.idesc, 1u);
-          tc_mma_bf16(d0, mk_desc(a_lo + 6, a_hi), mk_desc(b_lo + 6, DESC_HI_1024), a.idesc, 1u);
-          if (a.MT == 2) {
-            const uint32_t d1 = d0 + (uint32_t)a.Npad, a1 = a_lo + aS16;
-            tc_mma_bf16(d1, mk_desc(a1, a_hi), mk_desc(b_lo, DESC_HI_1024), a.idesc, kcount);
-            tc_mma_bf16(d1, mk_desc(a1 + 2, a_hi), mk_desc(b_lo + 2, DESC_HI_1024), a.idesc, 1u);
-            tc_mma_bf16(d1, mk_desc(a1 + 4, a_hi), mk_desc(b_lo + 4, DESC_HI_1024), a.idesc, 1u);
-            tc_mma_bf16(d1, mk_desc(a1 + 6, a_hi), mk_desc(b_lo + 6, DESC_HI_1024), a.idesc, 1u);
-          }
-          if (!a.b_resident) {
-            tc_commit(B_empty(rb.stage));
-            rb.next();
-          }
-          ++kb;
-          kcount = 1u;
-        };
-        for (int s = 0; s < a.n_src; ++s) {
-          for (int ch = 0; ch < a.nchunk[s]; ++ch) {
-            if (a.a_mode) {
-              mbar_wait(A_full(ra.stage), ra.phase, a.err_flag, 4);
-              tc_fence_after();
-              if (s == 0 && ch == 0) dbg_stamp(a, mma_il, 4);
-              const uint32_t st_lo = a_lo_base + (uint32_t)(ra.stage * a.MT) * aS16 + (uint32_t)(ky0 * HALO_W + kx0) * 8u;
-              if (a.nkx == 3 && a.nky == 3) {
-#pragma unroll
-                for (int kxi = 0; kxi < 3; ++kxi)
-#pragma unroll
-                  for (int kyi = 0; kyi < 3; ++kyi)
-                    issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
-              } else if (a.nkx == 2 && a.nky == 2) {
-#pragma unroll
-                for (int kxi = 0; kxi < 2; ++kxi)
-#pragma unroll
-                  for (int kyi = 0; kyi < 2; ++kyi)
-                    issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
-              } else {
-                for (int kxi = 0; kxi < a.nkx; ++kxi)
-                  for (int kyi = 0; kyi < a.nky; ++kyi)
-                    issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
-              }
-              tc_commit(A_empty(ra.stage));
-              ra.next();
-              continue;
-            }
-            for (int kxi = 0; kxi < a.nkx; ++kxi) {
-              for (int ld = 0; ld < n_loads(a); ++ld) {
-                mbar_wait(A_full(ra.stage), ra.phase, a.err_flag, 4);
-                tc_fence_after();
-                const uint32_t st_lo = a_lo_base + (uint32_t)(ra.stage * a.MT) * aS16;
-                const int nt = n_taps(a, ld, ky0);
-                for (int j = 0; j < nt; ++j)
-                  issue_tap(st_lo + (uint32_t)tap_off(a, ld, j, ky0) * (TILE_W * 8u), DESC_HI_1024);
-                tc_commit(A_empty(ra.stage));
-                ra.next();
-              }
-            }
-          }
-        }
-        tc_commit(T_full(rt.stage));
-        dbg_stamp(a, mma_il, 3);
-        ++mma_il;
-        rt.next();
-      }
+      // specialised issue loops: taps unrolled (descriptor offsets become immediates), MT and the weight
+      // mode resolved at compile time
+      const int taps = a.a_mode ? a.nkx * a.nky : 0;
+#define SRD_MMA_CASE(T)                                                                      \
+  do {                                                                                       \
+    if (a.b_resident) mma_role<T, 1, true>(a, tmem_base, a_base, b_base, bar_base);          \
+    else if (a.MT == 2) mma_role<T, 2, false>(a, tmem_base, a_base, b_base, bar_base);       \
+    else mma_role<T, 1, false>(a, tmem_base, a_base, b_base, bar_base);                      \
+  } while (0)
+      if (taps == 9 && a.nkx == 3) SRD_MMA_CASE(9);
+      else if (taps == 4 && a.nkx == 2) SRD_MMA_CASE(4);
+      else if (taps == 1) SRD_MMA_CASE(1);
+      else SRD_MMA_CASE(0);
+#undef SRD_MMA_CASE
     }
   } else {
     // ================================================================= epilogue (warps 2..9)
@@ -1150,6 +1237,13 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   SRD_CHECK(planned, "conv_tc: no shared-memory plan fits (N=%d)", d.N);
   a.items_per_phase = (a.tiles_per_phase + a.MT - 1) / a.MT;
   a.n_items = n_phase * a.items_per_phase;
+  SRD_CHECK(a.n_items < (1 << 24) && a.n_vrows < (1 << 24), "conv_tc: problem too large for the 24-bit tile decode");
+  a.fd_ipp = make_fastdiv((uint32_t)a.items_per_phase);
+  a.fd_colblk = make_fastdiv((uint32_t)a.n_colblk);
+  a.fd_period = make_fastdiv((uint32_t)a.period);
+  a.fd_up = make_fastdiv((uint32_t)d.up);
+  a.n_chunks = 0;
+  for (int i = 0; i < d.n_src; ++i) a.n_chunks += a.nchunk[i];
   a.b_region_bytes = b_bytes_total;
   const int stg_total = a.epi_tma ? EPI_WARPS * a.epi_nbuf * 4096 : 0;
   a.n_stages = (EPI_GROUPS * a.MT * a.Npad <= 512) ? EPI_GROUPS : 2;

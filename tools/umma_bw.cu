@@ -31,7 +31,7 @@ __device__ __forceinline__ void mma(uint32_t d, uint64_t a, uint64_t b, uint32_t
 }
 
 template <int CG>
-__global__ void __launch_bounds__(192, 1) umma_bw(int N, int iters, int noise, int a_stages,
+__global__ void __launch_bounds__(192, 1) umma_bw(int N, int iters, int noise, int a_stages, int d_stages, int M,
                                                   unsigned long long* out) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t base = (smem_u32(smem_raw) + 1023u) & ~1023u;
@@ -67,18 +67,21 @@ __global__ void __launch_bounds__(192, 1) umma_bw(int N, int iters, int noise, i
   }
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   const uint32_t tmem = *reinterpret_cast<volatile uint32_t*>(gen + (slot - base));
-  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((128 * CG) >> 4) << 24);
+  const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)((M * CG) >> 4) << 24);
 
   if (warp == 1 && rank == 0) {
     if (lane == 0) {
       const long long t0 = clock64();
+      // each iteration: 4 K-steps x d_stages independent accumulators, interleaved so that consecutive
+      // MMAs never target the same accumulator when d_stages > 1
       for (int it = 0; it < iters; ++it) {
         const uint32_t a_lo = (a_base + (uint32_t)(it % a_stages) * 16384u) >> 4;
         const uint32_t b_lo = (b_base + (uint32_t)(it & 1) * 32768u) >> 4;
-        const uint32_t d = tmem + (uint32_t)(it & 1) * (uint32_t)N;
 #pragma unroll
         for (int k = 0; k < 4; ++k)
-          mma<CG>(d, mk_desc(a_lo + 2 * k, DESC_HI), mk_desc(b_lo + 2 * k, DESC_HI), idesc, (uint32_t)(k | (it > 1)));
+          for (int s = 0; s < d_stages; ++s)
+            mma<CG>(tmem + (uint32_t)(s * N), mk_desc(a_lo + 2 * k, DESC_HI), mk_desc(b_lo + 2 * k, DESC_HI), idesc,
+                    (uint32_t)(k | it));
       }
       if (CG == 1)
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -130,7 +133,7 @@ __global__ void __launch_bounds__(192, 1) umma_bw(int N, int iters, int noise, i
 }
 
 template <int CG>
-static double run(int N, int iters, int noise, int a_stages, unsigned long long* d_out, double* lds_bpc) {
+static double run(int N, int iters, int noise, int a_stages, int d_stages, int M, unsigned long long* d_out, double* lds_bpc) {
   const int smem = 8 * 16384 + 4 * 16384 + 2048;
   cudaFuncSetAttribute(umma_bw<CG>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
   cudaLaunchConfig_t cfg{};
@@ -143,7 +146,7 @@ static double run(int N, int iters, int noise, int a_stages, unsigned long long*
   cfg.attrs = at; cfg.numAttrs = 1;
   cudaMemset(d_out, 0, 2048 * 8);
   for (int rep = 0; rep < 2; ++rep) {
-    cudaError_t e = cudaLaunchKernelEx(&cfg, umma_bw<CG>, N, iters, noise, a_stages, d_out);
+    cudaError_t e = cudaLaunchKernelEx(&cfg, umma_bw<CG>, N, iters, noise, a_stages, d_stages, M, d_out);
     if (e != cudaSuccess) { printf("launch failed: %s\n", cudaGetErrorString(e)); exit(1); }
     e = cudaDeviceSynchronize();
     if (e != cudaSuccess) { printf("kernel failed: %s\n", cudaGetErrorString(e)); exit(1); }
@@ -153,26 +156,29 @@ static double run(int N, int iters, int noise, int a_stages, unsigned long long*
   double s = 0, l = 0; int n = 0;
   for (int i = 0; i < 148; ++i) if (h[i]) { s += (double)h[i]; l += (double)h[256 + i] * 512.0 * noise / (double)h[i]; ++n; }
   *lds_bpc = l / n;
-  return s / n / (iters * 4.0);
+  return s / n / (iters * 4.0 * d_stages);
 }
 
 int main() {
   unsigned long long* d_out;
   cudaMalloc(&d_out, 2048 * 8);
-  const int iters = 2000;
-  printf("cycles per tcgen05.mma (M=128/CTA, K=16, bf16, SS) ; operand bytes/cycle/SM = (4096 + 32*N/CG) / cycles\n");
-  printf("%4s %3s %6s %8s | %10s %10s %12s %12s\n", "CG", "N", "noise", "a_stages", "cyc/MMA", "ideal N/2", "opB/clk/SM", "ldsB/clk/SM");
-  const int Ns[4] = {64, 128, 192, 256};
+  const int iters = 1000;
+  printf("cycles per tcgen05.mma (K=16, bf16, SS); d_st = independent accumulators interleaved\n");
+  printf("%3s %4s %4s %5s %5s | %9s %9s %11s %11s\n", "CG", "M", "N", "d_st", "noise", "cyc/MMA", "ideal", "opB/clk/SM", "ldsB/clk/SM");
+  const int Ns[6] = {32, 64, 96, 128, 192, 256};
   for (int cg = 1; cg <= 2; ++cg)
-    for (int ni = 0; ni < 4; ++ni)
-      for (int noise = 0; noise <= 4; noise = noise ? noise * 2 : 1) {
-        for (int ast = 8; ast >= 1; ast -= 7) {
-          if (ast == 1 && noise) continue;
+    for (int M = (cg == 1 ? 64 : 128); M <= 128; M += 64)
+      for (int ni = 0; ni < 6; ++ni)
+        for (int ds = 1; ds <= 8; ds *= 2) {
           const int N = Ns[ni];
-          double lds = 0;
-          const double c = cg == 1 ? run<1>(N, iters, noise, ast, d_out, &lds) : run<2>(N, iters, noise, ast, d_out, &lds);
-          printf("%4d %3d %6d %8d | %10.1f %10.1f %12.1f %12.1f\n", cg, N, noise, ast, c, N / 2.0, (4096.0 + 32.0 * N / cg) / c, lds);
+          if (ds * N > 512) continue;
+          for (int noise = 0; noise <= 4; noise += 4) {
+            if (noise && !(ds == 1 || ds * N == 512 || ds == 4)) continue;
+            double lds = 0;
+            const double c = cg == 1 ? run<1>(N, iters, noise, 8, ds, M, d_out, &lds) : run<2>(N, iters, noise, 8, ds, M, d_out, &lds);
+            printf("%3d %4d %4d %5d %5d | %9.1f %9.1f %11.1f %11.1f\n", cg, M, N, ds, noise, c, (M < 128 ? 128 : M) * N / 256.0,
+                   (M * 32.0 + 32.0 * N / cg) / c, lds);
+          }
         }
-      }
   return 0;
 }
