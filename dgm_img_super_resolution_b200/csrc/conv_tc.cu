@@ -35,13 +35,14 @@ namespace srd {
 #endif
 constexpr int EPI_WARPS = SRD_EPI_WARPS; // groups of 4 warps (one warp per TMEM lane quarter)
 constexpr int EPI_GROUPS = EPI_WARPS / 4;
-constexpr int TC_THREADS = 64 + 32 * EPI_WARPS;   // TMA warp + MMA warp + epilogue warps
+constexpr int TC_THREADS = 96 + 32 * EPI_WARPS;   // activation-TMA warp + weight-TMA warp + MMA warp + epilogue warps
 // Warp roles.  The SMSP arbiter prefers the highest warp id, so the two single-thread roles
 // (TMA producer, MMA issuer) sit ABOVE the issue-heavy epilogue warps: an MMA that is ready to
 // issue must never queue behind Mish arithmetic.
-constexpr int WARP_EPI0 = SRD_ROLES_HIGH ? 0 : 2;
-constexpr int WARP_TMA = SRD_ROLES_HIGH ? EPI_WARPS : 0;
-constexpr int WARP_MMA = SRD_ROLES_HIGH ? EPI_WARPS + 1 : 1;
+constexpr int WARP_EPI0 = SRD_ROLES_HIGH ? 0 : 3;
+constexpr int WARP_TMA = SRD_ROLES_HIGH ? EPI_WARPS : 0;        // activation (A operand) producer
+constexpr int WARP_TMB = SRD_ROLES_HIGH ? EPI_WARPS + 1 : 1;    // weight (B operand) producer
+constexpr int WARP_MMA = SRD_ROLES_HIGH ? EPI_WARPS + 2 : 2;
 constexpr int TILE_W = 8, TILE_H = 16;
 constexpr int BOX_ROWS = TILE_H + 2;
 constexpr int A_BYTES = BOX_ROWS * TILE_W * 128;   // 18432: one {64ch x 8px x 18rows} bf16 box
@@ -83,6 +84,7 @@ struct TcArgs {
   int n_colblk, tiles_per_phase, items_per_phase, n_items;
   FastDiv fd_ipp, fd_colblk, fd_period, fd_up;   // dividers by items_per_phase, n_colblk, period, up
   int n_chunks;            // 64-channel K chunks per item over all sources
+  int cg;                  // CTAs per MMA (1, or 2 = cta_group::2 pair: M = 256, each CTA holds half of every weight tile)
   int stride, nky, nkx, ky0, kx0, up;
   int Npad, MT;
   int a_stages, b_stages;
@@ -139,34 +141,88 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
+// In a CTA pair (CG == 2) the shared::cluster address of a CTA-local object carries the CTA rank in
+// bit 24; clearing it names the same offset in the LEADER (even) CTA.  The pair's operand loads
+// (.cta_group::2) complete on the leader's mbarrier, where the single MMA-issuing thread waits.
+constexpr uint32_t PEER_BIT_MASK = 0xFEFFFFFFu;
+template <int CG = 1>
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+  if (CG == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1) : "memory");
 }
+template <int CG = 1>
 __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2) {
-  asm volatile(
-      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  if (CG == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+template <int CG = 1>
 __device__ __forceinline__ void tma_load_5d(uint32_t dst, const CUtensorMap* tm, uint32_t bar, int c0, int c1, int c2,
                                             int c3, int c4) {
-  asm volatile(
-      "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
-      ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+  if (CG == 1)
+    asm volatile(
+        "cp.async.bulk.tensor.5d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+  else
+    asm volatile(
+        "cp.async.bulk.tensor.5d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6, %7}], [%2];"
+        ::"r"(dst), "l"(tm), "r"(bar & PEER_BIT_MASK), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
+// arrive on the LEADER CTA's copy of a barrier (epilogue warps of both CTAs release the pair's accumulators)
+template <int CG>
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
+  if (CG == 1)
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+  else
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+// CG == 2: the commit arrives on the barrier at the same offset in BOTH CTAs of the pair (each CTA's
+// producer / epilogue waits on its own copy).
+template <int CG = 1>
 __device__ __forceinline__ void tc_commit(uint32_t bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  if (CG == 1)
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+  else
+    asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
+template <int CG = 1>
 __device__ __forceinline__ void tc_mma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                             uint32_t accumulate) {
-  asm volatile(
-      "{\n\t.reg .pred p;\n\t"
-      "setp.ne.b32 p, %4, 0;\n\t"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  if (CG == 1)
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
+  else
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate) : "memory");
 }
 __device__ __forceinline__ void tc_ld16(uint32_t taddr, uint32_t (&r)[16]) {
   asm volatile(
@@ -226,6 +282,19 @@ struct Ring {
   int stage, phase, n;
   __device__ __forceinline__ void next() { if (++stage == n) { stage = 0; phase ^= 1; } }
 };
+
+// Where this CTA sits: work items are dealt to CTA pairs (CG == 2) or single CTAs (CG == 1); item i of
+// a phase covers tiles [i*MT*CG, (i+1)*MT*CG), of which CTA `rank` owns tiles i*MT*CG + mt*CG + rank.
+struct PairId {
+  int rank, pair, n_pairs;
+};
+template <int CG>
+__device__ __forceinline__ PairId pair_id() {
+  PairId p;
+  if (CG == 1) { p.rank = 0; p.pair = (int)blockIdx.x; p.n_pairs = (int)gridDim.x; }
+  else { p.rank = (int)cluster_ctarank(); p.pair = (int)blockIdx.x >> 1; p.n_pairs = (int)gridDim.x >> 1; }
+  return p;
+}
 
 // taps served by one A box load: stride 1 -> all nky taps at row offset ky0+j;
 // stride 2 -> load 0 = even input rows (ky 0 -> off 0, ky 2 -> off 1), load 1 = odd rows (ky 1).
@@ -419,10 +488,11 @@ __device__ __forceinline__ TileGeo tile_geo(const TcArgs& a, int tt, int g, int 
 // The two epilogue warpgroups (halves) ping-pong on the two TMEM accumulator stages: half h owns
 // the items with local index = h (mod 2), i.e. TMEM stage h.
 // ---------------------------------------------------------------------------------------------
-template <int ACT>
+template <int ACT, int CG>
 __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es, uint32_t tmem_base,
                                               uint32_t t_full0, uint32_t t_empty0, int warp, int lane) {
   const int S = a.up;
+  const PairId pid = pair_id<CG>();
   const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
   const int group = (warp - WARP_EPI0) >> 2;    // epilogue group
   const int stage = group % a.n_stages, share = group / a.n_stages;
@@ -436,16 +506,16 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
   const int c_first = share, c_step = a.n_share;
   uint32_t round = 0;                           // it / n_stages: parity of this TMEM stage
   for (int it = stage;; it += a.n_stages, ++round) {
-    const int item = blockIdx.x + it * gridDim.x;
+    const int item = pid.pair + it * pid.n_pairs;
     if (item >= a.n_items) break;
     const int phase = fdiv(item, a.fd_ipp);
-    const int t0 = (item - phase * a.items_per_phase) * a.MT;
+    const int t0 = (item - phase * a.items_per_phase) * (a.MT * CG) + pid.rank;
     const int pr = fdiv(phase, a.fd_up), ps = phase - pr * S;
     mbar_wait(t_full, round & 1u, a.err_flag, 6);
     tc_fence_after();
     bool released = false;
     for (int mt = 0; mt < a.MT; ++mt) {
-      const TileGeo tg = tile_geo(a, t0 + mt, g, px);
+      const TileGeo tg = tile_geo(a, t0 + mt * CG, g, px);
       const bool valid = tg.valid;
       const int b = tg.b, oy = tg.y * S + pr, ox = tg.x * S + ps;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((stage * a.MT + mt) * a.Npad);
@@ -474,7 +544,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
           if (last_tile && c + c_step >= nchunks) {              // accumulator fully read: release the TMEM stage
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty);
+            if (lane == 0) mbar_arrive_leader<CG>(t_empty);
             released = true;
           }
           epi_chunk_fast<ACT>(a, es, c * 16, r, tp, wp, q1, q2, head);
@@ -516,7 +586,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
     if (!released) {
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty);
+      if (lane == 0) mbar_arrive_leader<CG>(t_empty);
     }
   }
 }
@@ -556,10 +626,11 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // Each epilogue WARP owns 32 TMEM lanes = 4 tile rows x 8 px and stages them in its own 4 KB
 // swizzled buffer(s): no cross-warp synchronisation, one lane issues the warp's TMA traffic.
-template <int ACT>
+template <int ACT, int CG>
 __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es, const StageSmem& sg,
                                              uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0,
                                              int warp, int lane) {
+  const PairId pid = pair_id<CG>();
   const int quarter = warp & 3, group = (warp - WARP_EPI0) >> 2;
   const int stage = group % a.n_stages, share = group / a.n_stages;
   const int m = quarter * 32 + lane;
@@ -581,11 +652,11 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   auto prepare = [&](uint32_t kn, int itn, int qn) {
     if (qn >= n_sub) { itn += a.n_stages; qn = share; }
     if (qn >= n_sub) return;                                   // this group never has a sub-tile
-    const int item = blockIdx.x + itn * gridDim.x;
+    const int item = pid.pair + itn * pid.n_pairs;
     if (item >= a.n_items) return;
     const int mt = (qn >= nsj) ? 1 : 0, j = qn - mt * nsj;     // MT <= 2
     const int ph = fdiv(item, a.fd_ipp);
-    const int tt = (item - ph * a.items_per_phase) * a.MT + mt;
+    const int tt = (item - ph * a.items_per_phase) * (a.MT * CG) + mt * CG + pid.rank;
     const int rowblk = fdiv(tt, a.fd_colblk), colblk = tt - rowblk * a.n_colblk;
     const uint32_t buf = kn & nbuf_mask;
     const uint32_t bar = sg.r_full0 + 8u * buf;
@@ -600,9 +671,9 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   uint32_t k = 0, round = 0;
   if (lane == 0) prepare(0, stage, share);
   for (int it = stage;; it += a.n_stages, ++round) {
-    const int item = blockIdx.x + it * gridDim.x;
+    const int item = pid.pair + it * pid.n_pairs;
     if (item >= a.n_items) break;
-    const int t0 = (item - fdiv(item, a.fd_ipp) * a.items_per_phase) * a.MT;
+    const int t0 = (item - fdiv(item, a.fd_ipp) * a.items_per_phase) * (a.MT * CG) + pid.rank;
     mbar_wait(t_full, round & 1u, a.err_flag, 6);
     tc_fence_after();
     if (quarter == 0 && lane == 0) dbg_stamp(a, it, 5);
@@ -619,7 +690,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
         const int mt = (qq >= nsj) ? 1 : 0, j = qq - mt * nsj;
         if (mt != mt_cur) {
           mt_cur = mt;
-          tg = tile_geo(a, t0 + mt, g, px);
+          tg = tile_geo(a, t0 + mt * CG, g, px);
           valid = tg.valid;
           pix = valid ? ((size_t)(tg.b * (Ho + 2) + tg.y + 1) * (Wo + 2) + tg.x + 1) : 0;
           edge = 0;
@@ -649,7 +720,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
           if (last_sub && cc == 3) {                             // accumulator fully read: release the TMEM stage
             tc_fence_before();
             __syncwarp();
-            if (lane == 0) mbar_arrive(t_empty);
+            if (lane == 0) mbar_arrive_leader<CG>(t_empty);
             if (quarter == 0 && lane == 0) dbg_stamp(a, it, 6);
             released = true;
           }
@@ -745,7 +816,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     if (!released) {                                             // this group had no sub-tile in the item
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(t_empty);
+      if (lane == 0) mbar_arrive_leader<CG>(t_empty);
     }
     if (quarter == 0 && lane == 0) dbg_stamp(a, it, 7);
   }
@@ -769,38 +840,35 @@ struct Bars {
   __device__ __forceinline__ uint32_t R_full0() const { return base + 8u * (4 * MAX_STAGES + 10); }
 };
 
-// TMA producer (one thread).  Per (source, 64-channel chunk): ONE halo box per M tile (stride 1) or
-// one box per (kx, row parity) (stride 2), plus -- unless the weights are resident -- one weight
-// k-block per tap, in exactly the order the MMA role consumes them.
-__device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, uint32_t b_base, uint32_t bar_base) {
+// Activation producer (one thread).  Per (source, 64-channel chunk): ONE halo box per M tile
+// (stride 1) or one box per (kx, row parity) (stride 2), in the order the MMA role consumes them.
+// Weights have their own producer thread (below): a single in-order thread would park the next
+// activation box behind the weight ring's back-pressure and expose its full HBM latency.
+template <int CG>
+__device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, uint32_t bar_base) {
   const Bars bars{bar_base};
-  const int n_items = a.n_items, G = (int)gridDim.x, MT = a.MT, S = a.up, Npad = a.Npad;
+  const PairId pid = pair_id<CG>();
+  const bool leader = (pid.rank == 0);
+  const int n_items = a.n_items, G = pid.n_pairs, MT = a.MT, S = a.up;
   const int n_src = a.n_src, n_colblk = a.n_colblk, ipp = a.items_per_phase, vstart = a.vstart;
-  const int a_mode = a.a_mode, b_resident = a.b_resident, ntaps = a.nkx * a.nky, nkx = a.nkx;
-  const int stride = a.stride, kb_per_phase = a.kb_per_phase;
-  const uint32_t B_BYTES = (uint32_t)Npad * 128u, a_stage_bytes = (uint32_t)a.a_stage_bytes;
+  const int a_mode = a.a_mode, nkx = a.nkx, stride = a.stride;
+  const uint32_t a_stage_bytes = (uint32_t)a.a_stage_bytes;
   int* err = a.err_flag;
-  Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages};
-  if (b_resident) {
-    mbar_expect_tx(bars.B_res(), (uint32_t)a.kb_total * B_BYTES);
-    for (int kb = 0; kb < a.kb_total; ++kb)
-      tma_load_2d(b_base + (uint32_t)kb * B_BYTES, &a.tmB, bars.B_res(), 0, kb * Npad);
-  }
+  Ring ra{0, 0, a.a_stages};
   int il = 0;
-  for (int item = blockIdx.x; item < n_items; item += G, ++il) {
+  for (int item = pid.pair; item < n_items; item += G, ++il) {
     const int phase = fdiv(item, a.fd_ipp);
-    const int t0 = (item - phase * ipp) * MT;
+    const int t0 = (item - phase * ipp) * (MT * CG) + pid.rank;
     int kx0 = a.kx0;
     if (S > 1) { const int pr = fdiv(phase, a.fd_up); kx0 = (phase - pr * S >= S / 2) ? 1 : 0; }
     // tile origins of this item
     int V0[2], X0[2];
     for (int mt = 0; mt < MT; ++mt) {
-      const int tt = t0 + mt;
+      const int tt = t0 + mt * CG;
       const int rowblk = fdiv(tt, a.fd_colblk);
       V0[mt] = rowblk * TILE_H + vstart;
       X0[mt] = (tt - rowblk * n_colblk) * TILE_W;
     }
-    int kb = phase * kb_per_phase;
     for (int s = 0; s < n_src; ++s) {
       const CUtensorMap* tm = &a.tmA[s];
       const int nch = a.nchunk[s];
@@ -808,48 +876,59 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, 
         if (a_mode) {
           mbar_wait(bars.A_empty(ra.stage), ra.phase ^ 1, err, 1);
           if (s == 0 && ch == 0) dbg_stamp(a, il, 0);
-          mbar_expect_tx(bars.A_full(ra.stage), (uint32_t)(MT * A_HALO_BYTES));
+          if (leader) mbar_expect_tx(bars.A_full(ra.stage), (uint32_t)(CG * MT * A_HALO_BYTES));
           for (int mt = 0; mt < MT; ++mt)
-            tma_load_3d(a_base + (uint32_t)(ra.stage * MT + mt) * a_stage_bytes, tm, bars.A_full(ra.stage),
-                        ch * 64, X0[mt], V0[mt] - 1);
+            tma_load_3d<CG>(a_base + (uint32_t)(ra.stage * MT + mt) * a_stage_bytes, tm, bars.A_full(ra.stage),
+                            ch * 64, X0[mt], V0[mt] - 1);
           ra.next();
-          if (!b_resident) {
-            for (int j = 0; j < ntaps; ++j) {
-              mbar_wait(bars.B_empty(rb.stage), rb.phase ^ 1, err, 2);
-              mbar_expect_tx(bars.B_full(rb.stage), B_BYTES);
-              tma_load_2d(b_base + (uint32_t)rb.stage * B_BYTES, &a.tmB, bars.B_full(rb.stage), 0, kb * Npad);
-              rb.next();
-              ++kb;
-            }
-          }
           continue;
         }
         for (int kxi = 0; kxi < nkx; ++kxi) {
           const int kxp = kx0 + kxi;
           for (int ld = 0; ld < n_loads(a); ++ld) {
             mbar_wait(bars.A_empty(ra.stage), ra.phase ^ 1, err, 1);
-            mbar_expect_tx(bars.A_full(ra.stage), (uint32_t)(MT * A_BYTES));
+            if (leader) mbar_expect_tx(bars.A_full(ra.stage), (uint32_t)(CG * MT * A_BYTES));
             for (int mt = 0; mt < MT; ++mt) {
               const uint32_t dst = a_base + (uint32_t)(ra.stage * MT + mt) * a_stage_bytes;
               if (stride == 1)
-                tma_load_3d(dst, tm, bars.A_full(ra.stage), ch * 64, X0[mt] + kxp, V0[mt] - 1);
+                tma_load_3d<CG>(dst, tm, bars.A_full(ra.stage), ch * 64, X0[mt] + kxp, V0[mt] - 1);
               else
-                tma_load_5d(dst, tm, bars.A_full(ra.stage), ch * 64, kxp & 1, X0[mt] + (kxp >> 1), ld, V0[mt]);
+                tma_load_5d<CG>(dst, tm, bars.A_full(ra.stage), ch * 64, kxp & 1, X0[mt] + (kxp >> 1), ld, V0[mt]);
             }
             ra.next();
-            if (!b_resident) {
-              const int nt = n_taps(a, ld, 0);
-              for (int j = 0; j < nt; ++j) {
-                mbar_wait(bars.B_empty(rb.stage), rb.phase ^ 1, err, 2);
-                mbar_expect_tx(bars.B_full(rb.stage), B_BYTES);
-                tma_load_2d(b_base + (uint32_t)rb.stage * B_BYTES, &a.tmB, bars.B_full(rb.stage), 0, kb * Npad);
-                rb.next();
-                ++kb;
-              }
-            }
           }
         }
       }
+    }
+  }
+}
+
+// Weight producer (one thread): either all k-blocks once (resident) or, per item, kb_per_phase
+// k-blocks of the item's phase streamed through the weight ring.  Each CTA of a pair holds
+// Npad / CG rows of every k-block; the leader's barriers count the bytes of BOTH CTAs.
+template <int CG>
+__device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b_base, uint32_t bar_base) {
+  const Bars bars{bar_base};
+  const PairId pid = pair_id<CG>();
+  const bool leader = (pid.rank == 0);
+  const int Npad = a.Npad, b_rows = Npad / CG, b_row0 = pid.rank * b_rows;
+  const uint32_t B_BYTES = (uint32_t)b_rows * 128u;
+  int* err = a.err_flag;
+  if (a.b_resident) {
+    if (leader) mbar_expect_tx(bars.B_res(), (uint32_t)a.kb_total * B_BYTES * CG);
+    for (int kb = 0; kb < a.kb_total; ++kb)
+      tma_load_2d<CG>(b_base + (uint32_t)kb * B_BYTES, &a.tmB, bars.B_res(), 0, kb * Npad + b_row0);
+    return;
+  }
+  const int n_items = a.n_items, G = pid.n_pairs, kb_per_phase = a.kb_per_phase;
+  Ring rb{0, 0, a.b_stages};
+  for (int item = pid.pair; item < n_items; item += G) {
+    int kb = (a.up > 1) ? fdiv(item, a.fd_ipp) * kb_per_phase : 0;
+    for (int j = 0; j < kb_per_phase; ++j, ++kb) {
+      mbar_wait(bars.B_empty(rb.stage), rb.phase ^ 1, err, 2);
+      if (leader) mbar_expect_tx(bars.B_full(rb.stage), B_BYTES * CG);
+      tma_load_2d<CG>(b_base + (uint32_t)rb.stage * B_BYTES, &a.tmB, bars.B_full(rb.stage), 0, kb * Npad + b_row0);
+      rb.next();
     }
   }
 }
@@ -861,13 +940,14 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, 
 // the low word (high words are constants), and for the 3x3 / 2x2 / 1x1 halo cases (TAPS = 9/4/1)
 // the tap loops are unrolled so tap offsets are immediates.  TAPS = 0: generic runtime loops
 // (stride 2, validation modes).
-template <int TAPS, int MT, bool BRES>
+template <int TAPS, int MT, bool BRES, int CG>
 __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, uint32_t a_base, uint32_t b_base,
                                          uint32_t bar_base) {
   const Bars bars{bar_base};
-  const int n_items = a.n_items, G = (int)gridDim.x, S = a.up, n_chunks = a.n_chunks;
+  const PairId pid = pair_id<CG>();                  // only the leader CTA of a pair runs this role
+  const int n_items = a.n_items, G = pid.n_pairs, S = a.up, n_chunks = a.n_chunks;
   const uint32_t Npad = (uint32_t)a.Npad, idesc = a.idesc;
-  const uint32_t bB16 = Npad * 8u, aS16 = (uint32_t)a.a_stage_bytes >> 4;
+  const uint32_t bB16 = Npad * 8u / CG, aS16 = (uint32_t)a.a_stage_bytes >> 4;   // per-CTA weight tile = Npad/CG rows
   const uint32_t a_lo_base = a_base >> 4, b_lo_base = b_base >> 4;
   const uint32_t kbpp16 = (uint32_t)a.kb_per_phase * bB16;
   int* err = a.err_flag;
@@ -877,7 +957,7 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
     tc_fence_after();
   }
   int mma_il = 0;
-  for (int item = blockIdx.x; item < n_items; item += G) {
+  for (int item = pid.pair; item < n_items; item += G) {
     int ky0 = a.ky0, kx0 = a.kx0;
     uint32_t b_cur = b_lo_base;
     if (S > 1) {
@@ -903,19 +983,19 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
         tc_fence_after();
         b_lo = b_lo_base + (uint32_t)rb.stage * bB16;
       }
-      tc_mma_bf16(d0, mk_desc(a_lo, a_hi), mk_desc(b_lo, DESC_HI_1024), idesc, kcount);
-      tc_mma_bf16(d0, mk_desc(a_lo + 2, a_hi), mk_desc(b_lo + 2, DESC_HI_1024), idesc, 1u);
-      tc_mma_bf16(d0, mk_desc(a_lo + 4, a_hi), mk_desc(b_lo + 4, DESC_HI_1024), idesc, 1u);
-      tc_mma_bf16(d0, mk_desc(a_lo + 6, a_hi), mk_desc(b_lo + 6, DESC_HI_1024), idesc, 1u);
+      tc_mma_bf16<CG>(d0, mk_desc(a_lo, a_hi), mk_desc(b_lo, DESC_HI_1024), idesc, kcount);
+      tc_mma_bf16<CG>(d0, mk_desc(a_lo + 2, a_hi), mk_desc(b_lo + 2, DESC_HI_1024), idesc, 1u);
+      tc_mma_bf16<CG>(d0, mk_desc(a_lo + 4, a_hi), mk_desc(b_lo + 4, DESC_HI_1024), idesc, 1u);
+      tc_mma_bf16<CG>(d0, mk_desc(a_lo + 6, a_hi), mk_desc(b_lo + 6, DESC_HI_1024), idesc, 1u);
       if (MT == 2) {
         const uint32_t d1 = d0 + Npad, a1 = a_lo + aS16;
-        tc_mma_bf16(d1, mk_desc(a1, a_hi), mk_desc(b_lo, DESC_HI_1024), idesc, kcount);
-        tc_mma_bf16(d1, mk_desc(a1 + 2, a_hi), mk_desc(b_lo + 2, DESC_HI_1024), idesc, 1u);
-        tc_mma_bf16(d1, mk_desc(a1 + 4, a_hi), mk_desc(b_lo + 4, DESC_HI_1024), idesc, 1u);
-        tc_mma_bf16(d1, mk_desc(a1 + 6, a_hi), mk_desc(b_lo + 6, DESC_HI_1024), idesc, 1u);
+        tc_mma_bf16<CG>(d1, mk_desc(a1, a_hi), mk_desc(b_lo, DESC_HI_1024), idesc, kcount);
+        tc_mma_bf16<CG>(d1, mk_desc(a1 + 2, a_hi), mk_desc(b_lo + 2, DESC_HI_1024), idesc, 1u);
+        tc_mma_bf16<CG>(d1, mk_desc(a1 + 4, a_hi), mk_desc(b_lo + 4, DESC_HI_1024), idesc, 1u);
+        tc_mma_bf16<CG>(d1, mk_desc(a1 + 6, a_hi), mk_desc(b_lo + 6, DESC_HI_1024), idesc, 1u);
       }
       if (!BRES) {
-        tc_commit(bars.B_empty(rb.stage));
+        tc_commit<CG>(bars.B_empty(rb.stage));
         rb.next();
       }
       kcount = 1u;
@@ -934,7 +1014,7 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
 #pragma unroll
           for (int kyi = 0; kyi < NK; ++kyi)
             issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
-        tc_commit(bars.A_empty(ra.stage));
+        tc_commit<CG>(bars.A_empty(ra.stage));
         ra.next();
       }
     } else {
@@ -947,7 +1027,7 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
           for (int kxi = 0; kxi < nkx; ++kxi)
             for (int kyi = 0; kyi < nky; ++kyi)
               issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
-          tc_commit(bars.A_empty(ra.stage));
+          tc_commit<CG>(bars.A_empty(ra.stage));
           ra.next();
           continue;
         }
@@ -959,24 +1039,24 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
             const int nt = n_taps(a, ld, ky0);
             for (int j = 0; j < nt; ++j)
               issue_tap(st_lo + (uint32_t)tap_off(a, ld, j, ky0) * (TILE_W * 8u), DESC_HI_1024);
-            tc_commit(bars.A_empty(ra.stage));
+            tc_commit<CG>(bars.A_empty(ra.stage));
             ra.next();
           }
         }
       }
     }
-    tc_commit(bars.T_full(rt.stage));
+    tc_commit<CG>(bars.T_full(rt.stage));
     dbg_stamp(a, mma_il, 3);
     ++mma_il;
     rt.next();
   }
 }
 
+template <int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int B_BYTES = a.Npad * 128;
   const uint32_t a_base = smem_base;
   const uint32_t b_base = a_base + (uint32_t)a.a_stages * a.MT * a.a_stage_bytes;
   const uint32_t stg_base = b_base + (uint32_t)a.b_region_bytes;        // staging: [epilogue warp][buf][4 KB]
@@ -1004,7 +1084,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if (warp == WARP_TMA && lane == 0) {
     for (int s = 0; s < a.a_stages; ++s) { mbar_init(A_full(s), 1); mbar_init(A_empty(s), 1); }
     for (int s = 0; s < a.b_stages; ++s) { mbar_init(B_full(s), 1); mbar_init(B_empty(s), 1); }
-    for (int s = 0; s < 4; ++s) { mbar_init(T_full(s), 1); mbar_init(T_empty(s), (uint32_t)(4 * a.n_share)); }
+    for (int s = 0; s < 4; ++s) { mbar_init(T_full(s), 1); mbar_init(T_empty(s), (uint32_t)(4 * a.n_share * CG)); }
     mbar_init(B_res, 1);
     for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(R_full0 + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1018,9 +1098,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   }
   if (warp == WARP_MMA) {
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
-                 : "memory");
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {      // issued by the same warp of both CTAs of the pair
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(512u)
+                   : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
   }
   // stage the per-channel epilogue vectors
   for (int i = threadIdx.x; i < a.Npad; i += TC_THREADS) {
@@ -1036,21 +1122,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   }
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();      // both CTAs' barriers are initialised before any remote arrive / TMA lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
   if (warp == WARP_TMA) {
-    if (elect_one_sync()) producer_role(a, a_base, b_base, bar_base);
+    if (elect_one_sync()) producer_role<CG>(a, a_base, bar_base);
+  } else if (warp == WARP_TMB) {
+    if (elect_one_sync()) weight_producer_role<CG>(a, b_base, bar_base);
   } else if (warp == WARP_MMA) {
-    if (elect_one_sync()) {
+    if ((CG == 1 || cluster_ctarank() == 0) && elect_one_sync()) {
       // specialised issue loops: taps unrolled (descriptor offsets become immediates), MT and the weight
       // mode resolved at compile time
       const int taps = a.a_mode ? a.nkx * a.nky : 0;
 #define SRD_MMA_CASE(T)                                                                      \
   do {                                                                                       \
-    if (a.b_resident) mma_role<T, 1, true>(a, tmem_base, a_base, b_base, bar_base);          \
-    else if (a.MT == 2) mma_role<T, 2, false>(a, tmem_base, a_base, b_base, bar_base);       \
-    else mma_role<T, 1, false>(a, tmem_base, a_base, b_base, bar_base);                      \
+    if (a.b_resident) mma_role<T, 1, true, CG>(a, tmem_base, a_base, b_base, bar_base);      \
+    else if (a.MT == 2) mma_role<T, 2, false, CG>(a, tmem_base, a_base, b_base, bar_base);   \
+    else mma_role<T, 1, false, CG>(a, tmem_base, a_base, b_base, bar_base);                  \
   } while (0)
       if (taps == 9 && a.nkx == 3) SRD_MMA_CASE(9);
       else if (taps == 4 && a.nkx == 2) SRD_MMA_CASE(4);
@@ -1070,22 +1159,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       sg.gen = smem_raw + (sg.base - smem_u32(smem_raw));
       sg.r_full0 = R_full0 + 8u * (uint32_t)(ew * 2);
       if (a.ep.act == SRD_ACT_MISH)
-        epilogue_tma<SRD_ACT_MISH>(a, es, sg, tmem_base, T_full(0), T_empty(0), warp, lane);
+        epilogue_tma<SRD_ACT_MISH, CG>(a, es, sg, tmem_base, T_full(0), T_empty(0), warp, lane);
       else
-        epilogue_tma<SRD_ACT_NONE>(a, es, sg, tmem_base, T_full(0), T_empty(0), warp, lane);
+        epilogue_tma<SRD_ACT_NONE, CG>(a, es, sg, tmem_base, T_full(0), T_empty(0), warp, lane);
     } else if (a.ep.act == SRD_ACT_MISH)
-      epilogue_role<SRD_ACT_MISH>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
+      epilogue_role<SRD_ACT_MISH, CG>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
     else if (a.ep.act == SRD_ACT_LRELU02)
-      epilogue_role<SRD_ACT_LRELU02>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
+      epilogue_role<SRD_ACT_LRELU02, CG>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
     else
-      epilogue_role<SRD_ACT_NONE>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
+      epilogue_role<SRD_ACT_NONE, CG>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
   }
 
   tc_fence_before();
   __syncthreads();
+  if (CG == 2) cluster_sync_all();      // the peer's shared memory / TMEM stay alive until the pair's MMAs are done
   if (warp == WARP_MMA) {
     tc_fence_after();
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    if (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
 }
 
@@ -1110,11 +1203,13 @@ static EncodeTiledFn get_encode_fn() {
 static int g_a_mode = 1;
 static int g_b_resident = 1;
 static int g_epi_tma = 1;
+static int g_cg = 2;                     // CTAs per MMA: 2 = cta_group::2 pairs (default), 1 = single-CTA MMAs
 static unsigned long long* g_dbg = nullptr;
 void tc_set_debug(unsigned long long* p) { g_dbg = p; }
 void tc_set_mode(int a_mode, int b_resident) {
   g_a_mode = a_mode & 1;
   g_epi_tma = (a_mode & 2) ? 0 : 1;      // bit 1 of a_mode disables the TMA-staged epilogue
+  g_cg = (a_mode & 4) ? 1 : 2;           // bit 2 of a_mode: single-CTA MMAs instead of CTA pairs
   g_b_resident = b_resident;
 }
 
@@ -1169,7 +1264,9 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   for (int i = 0; i < d.n_src; ++i) { a.nchunk[i] = (d.src[i].cin + 63) / 64; kb += a.nchunk[i] * taps; }
   a.kb_per_phase = kb;
   a.kb_total = n_phase * kb;
-  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.Npad >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  const int cg = (n_sm % 2 == 0) ? g_cg : 1;
+  a.cg = cg;
+  a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.Npad >> 3) << 17) | ((uint32_t)((128 * cg) >> 4) << 24);
   a.ep = make_epi(d, nullptr);
   a.head_w = d.head_w; a.head_b = d.head_b;
   a.err_flag = err_flag;
@@ -1184,7 +1281,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   a.epi_tma = g_epi_tma && a.fast && d.stride == 1 && d.up == 1 && (d.N % 64 == 0) && d.out && !d.out2 &&
               !d.planar && !d.head_w && (a.W_m % TILE_W == 0) && d.act != SRD_ACT_LRELU02 && d.H_out >= 4;
   // ---- shared-memory plan: A ring + weights (ring or resident) + staging + barriers + epilogue vectors
-  const int B_BYTES = a.Npad * 128;
+  const int B_BYTES = a.Npad * 128 / cg;      // per CTA: each CTA of a pair holds Npad / cg rows of a weight k-block
   const int budget = 227 * 1024 - BAR_BYTES - VEC_BYTES - 1024;
   a.a_mode = (d.stride == 1) ? g_a_mode : 0;
   a.a_stage_bytes = a.a_mode ? A_HALO_STAGE : A_BYTES;
@@ -1212,14 +1309,17 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
         a.b_stages = 1;
         b_bytes_total = (int)res_bytes;
       } else {
-        const int ast = a.a_mode ? 2 : 3;
+        // deepest A ring that still leaves >= 4 weight stages; at least 2 (halo) / 3 (per-kx) A stages and 3 weight stages
+        const int ast_min = a.a_mode ? 2 : 3;
+        int ast = 4;
+        for (; ast > ast_min; --ast)
+          if (budget - stg - ast * sb >= 4 * B_BYTES) break;
         const int left = budget - stg - ast * sb;
         if (left < 3 * B_BYTES) continue;
         const int bst = left / B_BYTES;
         a.a_stages = ast;
         a.b_stages = bst > MAX_STAGES ? MAX_STAGES : bst;
         b_bytes_total = a.b_stages * B_BYTES;
-        if (budget - stg - b_bytes_total - ast * sb >= sb) a.a_stages = ast + 1;   // spare room: third A stage
       }
       a.b_resident = resident ? 1 : 0;
       a.MT = MT;
@@ -1235,7 +1335,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
     }
   }
   SRD_CHECK(planned, "conv_tc: no shared-memory plan fits (N=%d)", d.N);
-  a.items_per_phase = (a.tiles_per_phase + a.MT - 1) / a.MT;
+  a.items_per_phase = (a.tiles_per_phase + a.MT * cg - 1) / (a.MT * cg);
   a.n_items = n_phase * a.items_per_phase;
   SRD_CHECK(a.n_items < (1 << 24) && a.n_vrows < (1 << 24), "conv_tc: problem too large for the 24-bit tile decode");
   a.fd_ipp = make_fastdiv((uint32_t)a.items_per_phase);
@@ -1250,7 +1350,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   a.n_share = EPI_GROUPS / a.n_stages;
   SRD_CHECK(!d.head_w || a.n_share == 1, "conv_tc: fused head needs N * MT <= 128");
   plan->smem = a.a_stages * stage_bytes + b_bytes_total + stg_total + BAR_BYTES + VEC_BYTES + 1024;
-  plan->grid = a.n_items < n_sm ? a.n_items : n_sm;
+  plan->grid = (a.n_items < n_sm / cg ? a.n_items : n_sm / cg) * cg;
 
   // ---- tensor maps
   for (int i = 0; i < d.n_src; ++i) {
@@ -1281,7 +1381,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   {
     cuuint64_t dims[2] = {64, (cuuint64_t)n_phase * kb * a.Npad};
     cuuint64_t strides[1] = {128};
-    cuuint32_t box[2] = {64, (cuuint32_t)a.Npad};
+    cuuint32_t box[2] = {64, (cuuint32_t)(a.Npad / cg)};
     cuuint32_t es[2] = {1, 1};
     CUresult r = enc(&a.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d.w_tc, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -1311,7 +1411,8 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   }
   static bool attr_set = false;
   if (!attr_set) {
-    SRD_CUDA(cudaFuncSetAttribute(conv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    SRD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
   return 0;
@@ -1323,8 +1424,22 @@ void tc_plan_delete(TcPlan* p) { delete p; }
 int launch_conv_tc(const TcPlan& plan, const float* temb, cudaStream_t stream) {
   TcArgs a = plan.args;
   if (temb) a.ep.temb = temb;
-  conv_tc_kernel<<<plan.grid, TC_THREADS, plan.smem, stream>>>(a);
-  SRD_CUDA(cudaGetLastError());
+  if (a.cg == 1) {
+    conv_tc_kernel<1><<<plan.grid, TC_THREADS, plan.smem, stream>>>(a);
+    SRD_CUDA(cudaGetLastError());
+  } else {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)plan.grid);
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = (size_t)plan.smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, a));
+  }
   return 0;
 }
 
