@@ -104,8 +104,10 @@ struct TcArgs {
   int b_region_bytes;      // bytes of the weight region (ring or resident)
   int epi_tma;             // TMA-staged epilogue (see epilogue_tma)
   int epi_nbuf;            // staging buffers per epilogue warp (1)
-  int n_stages;            // TMEM accumulator stages (2 | 4); epilogue group g owns stage g % n_stages
-  int n_share;             // epilogue groups sharing one stage (4 / n_stages); they split the sub-tiles
+  int n_stages;            // TMEM accumulator stages (2 | 4, power of two); local item i accumulates in stage i % n_stages
+  int n_share;             // epilogue groups that split ONE item's sub-tiles (1 | 2 | 4); the EPI_GROUPS / n_share
+                           // group sets work on different items concurrently (<= n_stages of them)
+  int stage_shift;         // log2(n_stages)
   unsigned long long* dbg; // optional timeline buffer [cta][DBG_ITEMS][8] of clock64 stamps (debug)
 };
 
@@ -185,7 +187,9 @@ __device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {
   if (CG == 1)
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
   else
-    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
+    // default (.release.cta) semantics: the accumulator hand-over is ordered by tcgen05.wait::ld +
+    // tcgen05.fence::before_thread_sync; a .release.cluster arrive would add a MEMBAR.ALL.CTA per warp per item
+    asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(bar & PEER_BIT_MASK) : "memory");
 }
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
@@ -495,19 +499,21 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
   const PairId pid = pair_id<CG>();
   const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
   const int group = (warp - WARP_EPI0) >> 2;    // epilogue group
-  const int stage = group % a.n_stages, share = group / a.n_stages;
+  const int n_conc = EPI_GROUPS / a.n_share;    // group sets working on different items
+  const int set = group % n_conc, share = group / n_conc;
   const int m = quarter * 32 + lane;
   const int g = m >> 3, px = m & 7;
   const int nchunks = a.Npad >> 4;
   const bool has_head = es.head_w != nullptr;
   const int Ho = a.ep.H_out, Wo = a.ep.W_out;
-  const uint32_t t_full = t_full0 + 8u * stage, t_empty = t_empty0 + 8u * stage;
-  // groups sharing a stage split the 16-column chunks round-robin
+  // groups sharing an item split the 16-column chunks round-robin
   const int c_first = share, c_step = a.n_share;
-  uint32_t round = 0;                           // it / n_stages: parity of this TMEM stage
-  for (int it = stage;; it += a.n_stages, ++round) {
+  for (int it = set;; it += n_conc) {
     const int item = pid.pair + it * pid.n_pairs;
     if (item >= a.n_items) break;
+    const int stage = it & (a.n_stages - 1);
+    const uint32_t round = (uint32_t)(it >> a.stage_shift);   // parity of this TMEM stage
+    const uint32_t t_full = t_full0 + 8u * stage, t_empty = t_empty0 + 8u * stage;
     const int phase = fdiv(item, a.fd_ipp);
     const int t0 = (item - phase * a.items_per_phase) * (a.MT * CG) + pid.rank;
     const int pr = fdiv(phase, a.fd_up), ps = phase - pr * S;
@@ -632,7 +638,8 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
                                              int warp, int lane) {
   const PairId pid = pair_id<CG>();
   const int quarter = warp & 3, group = (warp - WARP_EPI0) >> 2;
-  const int stage = group % a.n_stages, share = group / a.n_stages;
+  const int n_conc = EPI_GROUPS / a.n_share;     // group sets working on different items
+  const int set = group % n_conc, share = group / n_conc;
   const int m = quarter * 32 + lane;
   const int g = m >> 3, px = m & 7;
   const int nsj = a.Npad >> 6;                   // 64-channel sub-tiles per tile
@@ -641,7 +648,6 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   const int Ho = a.ep.H_out, Wo = a.ep.W_out;
   const bool reflect = (a.ep.border == SRD_BORDER_REFLECT);
   const bool has_r1 = a.ep.res1 != nullptr;
-  const uint32_t t_full = t_full0 + 8u * stage, t_empty = t_empty0 + 8u * stage;
   const uint32_t swz = (uint32_t)(lane & 7);     // == m & 7
   uint8_t* my_row = sg.gen + lane * 128;         // this pixel's 128 B row inside a staging buffer
   const int g0 = quarter * 4;                    // first tile row of this warp
@@ -650,7 +656,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   // lane 0: make buffer (kn % nbuf) ready for this warp's rows of its kn-th sub-tile, which is
   // sub-tile qn of local item itn (the successor of the one just finished: no divisions)
   auto prepare = [&](uint32_t kn, int itn, int qn) {
-    if (qn >= n_sub) { itn += a.n_stages; qn = share; }
+    if (qn >= n_sub) { itn += n_conc; qn = share; }
     if (qn >= n_sub) return;                                   // this group never has a sub-tile
     const int item = pid.pair + itn * pid.n_pairs;
     if (item >= a.n_items) return;
@@ -668,11 +674,14 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     }
   };
 
-  uint32_t k = 0, round = 0;
-  if (lane == 0) prepare(0, stage, share);
-  for (int it = stage;; it += a.n_stages, ++round) {
+  uint32_t k = 0;
+  if (lane == 0) prepare(0, set, share);
+  for (int it = set;; it += n_conc) {
     const int item = pid.pair + it * pid.n_pairs;
     if (item >= a.n_items) break;
+    const int stage = it & (a.n_stages - 1);
+    const uint32_t round = (uint32_t)(it >> a.stage_shift);   // parity of this TMEM stage
+    const uint32_t t_full = t_full0 + 8u * stage, t_empty = t_empty0 + 8u * stage;
     const int t0 = (item - fdiv(item, a.fd_ipp) * a.items_per_phase) * (a.MT * CG) + pid.rank;
     mbar_wait(t_full, round & 1u, a.err_flag, 6);
     tc_fence_after();
@@ -1346,8 +1355,18 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   for (int i = 0; i < d.n_src; ++i) a.n_chunks += a.nchunk[i];
   a.b_region_bytes = b_bytes_total;
   const int stg_total = a.epi_tma ? EPI_WARPS * a.epi_nbuf * 4096 : 0;
-  a.n_stages = (EPI_GROUPS * a.MT * a.Npad <= 512) ? EPI_GROUPS : 2;
-  a.n_share = EPI_GROUPS / a.n_stages;
+  // TMEM accumulator stages, and how the epilogue groups are dealt: with >= 3 (2) sub-tiles per item all
+  // (two) groups split one item, so an accumulator stage is drained -- and free for the next MMAs -- in
+  // the time of ONE sub-tile; otherwise every group drains its own item.
+  a.n_stages = (EPI_GROUPS >= 4 && 4 * a.MT * a.Npad <= 512) ? 4 : 2;
+  a.stage_shift = a.n_stages == 4 ? 2 : 1;
+  {
+    const int n_sub = a.MT * ((a.Npad + 63) / 64);
+    int share = d.head_w ? 1 : (n_sub >= 3 ? 4 : n_sub);
+    if (share > EPI_GROUPS) share = EPI_GROUPS;
+    while (EPI_GROUPS / share > a.n_stages) share *= 2;
+    a.n_share = share;
+  }
   SRD_CHECK(!d.head_w || a.n_share == 1, "conv_tc: fused head needs N * MT <= 128");
   plan->smem = a.a_stages * stage_bytes + b_bytes_total + stg_total + BAR_BYTES + VEC_BYTES + 1024;
   plan->grid = (a.n_items < n_sm / cg ? a.n_items : n_sm / cg) * cg;

@@ -4,12 +4,8 @@ timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu --layers > gpurun_out/
 python -c "
 import json;d=json.loads(open('gpurun_out/bench.log').read().strip().splitlines()[-1]);print('cg2',d['value'],d['roofline']['ms_per_pass'],d['roofline']['frac'])"
 cp gpurun_out/layers.json gpurun_out/layers_cg2.json
-SRD_TC_A_MODE=5 timeout 300 python bench.py --steps 2 --warmup 2 --no-cpu --layers > gpurun_out/bench_cg1.log 2>&1; echo "bench cg1 rc=$?"
-python -c "
-import json;d=json.loads(open('gpurun_out/bench_cg1.log').read().strip().splitlines()[-1]);print('cg1',d['value'],d['roofline']['ms_per_pass'],d['roofline']['frac'])"
-cp gpurun_out/layers.json gpurun_out/layers_cg1.json
 export SRD_LIB_PATH=$PWD/dgm_img_super_resolution_b200/variants/lib_dbg.so
-SRD_TC_A_MODE=5 timeout 120 python tools/timeline_conv.py 128 128 80 64 res > gpurun_out/tl_128_cg1.log 2>&1
-SRD_TC_A_MODE=5 timeout 120 python tools/timeline_conv.py 64 64 160 64 res > gpurun_out/tl_64_cg1.log 2>&1
-SRD_TC_A_MODE=5 timeout 120 python tools/timeline_conv.py 256 256 20 64 res > gpurun_out/tl_256_cg1.log 2>&1
-grep -h "kernel\|steady\|mean mma" gpurun_out/tl_64_cg1.log gpurun_out/tl_128_cg1.log gpurun_out/tl_256_cg1.log
+timeout 120 python tools/timeline_conv.py 64 64 160 64 res > gpurun_out/tl_b.log 2>&1
+timeout 120 python tools/timeline_conv.py 128 128 80 64 res > gpurun_out/tl_d.log 2>&1
+timeout 120 python tools/timeline_conv.py 256 256 20 64 res > gpurun_out/tl_e.log 2>&1
+grep -h "kernel\|steady\|mean mma" gpurun_out/tl_b.log | head -3; grep -h "kernel\|steady\|mean mma" gpurun_out/tl_d.log | head -3; grep -h "kernel\|steady\|mean mma" gpurun_out/tl_e.log | head -3
