@@ -103,6 +103,8 @@ struct TcArgs {
   int kb_total;
   int b_region_bytes;      // bytes of the weight region (ring or resident)
   int epi_tma;             // TMA-staged epilogue (see epilogue_tma)
+  int epi_geo;             // 0: stride-1 conv (virtual row == padded output row); 1: stride-2 conv or 2x transposed
+                           //    conv phase: output rows / columns are mapped per tile row (tmOrow is 5-D when up == 2)
   int epi_nbuf;            // staging buffers per epilogue warp (1)
   int n_stages;            // TMEM accumulator stages (2 | 4, power of two); local item i accumulates in stage i % n_stages
   int n_share;             // epilogue groups that split ONE item's sub-tiles (1 | 2 | 4); the EPI_GROUPS / n_share
@@ -611,6 +613,10 @@ __device__ __forceinline__ void tma_store_3d(const CUtensorMap* tm, uint32_t src
   asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];"
                ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2) : "memory");
 }
+__device__ __forceinline__ void tma_store_5d(const CUtensorMap* tm, uint32_t src, int c0, int c1, int c2, int c3, int c4) {
+  asm volatile("cp.async.bulk.tensor.5d.global.shared::cta.bulk_group [%0, {%2, %3, %4, %5, %6}], [%1];"
+               ::"l"(tm), "r"(src), "r"(c0), "r"(c1), "r"(c2), "r"(c3), "r"(c4) : "memory");
+}
 
 struct StageSmem {
   uint32_t base;        // shared address of THIS WARP's staging buffers ([nbuf][4 KB])
@@ -637,6 +643,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
                                              uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0,
                                              int warp, int lane) {
   const PairId pid = pair_id<CG>();
+  const int S = a.up;
   const int quarter = warp & 3, group = (warp - WARP_EPI0) >> 2;
   const int n_conc = EPI_GROUPS / a.n_share;     // group sets working on different items
   const int set = group % n_conc, share = group / n_conc;
@@ -682,7 +689,10 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     const int stage = it & (a.n_stages - 1);
     const uint32_t round = (uint32_t)(it >> a.stage_shift);   // parity of this TMEM stage
     const uint32_t t_full = t_full0 + 8u * stage, t_empty = t_empty0 + 8u * stage;
-    const int t0 = (item - fdiv(item, a.fd_ipp) * a.items_per_phase) * (a.MT * CG) + pid.rank;
+    const int phase = fdiv(item, a.fd_ipp);
+    const int t0 = (item - phase * a.items_per_phase) * (a.MT * CG) + pid.rank;
+    int pr = 0, ps = 0;                                          // sub-pixel phase of a transposed conv
+    if (S > 1) { pr = fdiv(phase, a.fd_up); ps = phase - pr * S; }
     mbar_wait(t_full, round & 1u, a.err_flag, 6);
     tc_fence_after();
     if (quarter == 0 && lane == 0) dbg_stamp(a, it, 5);
@@ -701,10 +711,11 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
           mt_cur = mt;
           tg = tile_geo(a, t0 + mt * CG, g, px);
           valid = tg.valid;
-          pix = valid ? ((size_t)(tg.b * (Ho + 2) + tg.y + 1) * (Wo + 2) + tg.x + 1) : 0;
+          const int oy = tg.y * S + pr, ox = tg.x * S + ps;      // output pixel of this thread
+          pix = valid ? ((size_t)(tg.b * (Ho + 2) + oy + 1) * (Wo + 2) + ox + 1) : 0;
           edge = 0;
           if (valid && reflect)
-            edge = (tg.y == 1 ? 1u : 0u) | (tg.y == Ho - 2 ? 2u : 0u) | (tg.x == 1 ? 4u : 0u) | (tg.x == Wo - 2 ? 8u : 0u);
+            edge = (oy == 1 ? 1u : 0u) | (oy == Ho - 2 ? 2u : 0u) | (ox == 1 ? 4u : 0u) | (ox == Wo - 2 ? 8u : 0u);
           outp = static_cast<__nv_bfloat16*>(a.ep.out) + pix * a.ep.out_ct + a.ep.out_coff;
           r2p = (a.ep.res2 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
           tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((stage * a.MT + mt) * a.Npad);
@@ -791,26 +802,50 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
         if (lane == 0) {
           const uint32_t src = sg.base + buf * 4096u;
           const int V0 = tg.V0 + g0, xc = tg.x0 + 1;               // this warp's 4 rows
-          bool whole = !reflect;
-          int yp0 = 0;
-          if (reflect) {                                           // stride 1: virtual row == padded stacked row
-            const int b0 = fdiv(V0, a.fd_period);
-            yp0 = V0 - b0 * a.period;
-            whole = (yp0 >= 3) && (yp0 + 3 <= Ho - 2) && (V0 + 4 <= a.n_vrows);
-          }
-          if (whole) {
-            tma_store_3d(&a.tmO, src, j * 64, xc, V0);
+          if (a.epi_geo == 0) {
+            bool whole = !reflect;
+            int yp0 = 0;
+            if (reflect) {                                         // stride 1: virtual row == padded stacked row
+              const int b0 = fdiv(V0, a.fd_period);
+              yp0 = V0 - b0 * a.period;
+              whole = (yp0 >= 3) && (yp0 + 3 <= Ho - 2) && (V0 + 4 <= a.n_vrows);
+            }
+            if (whole) {
+              tma_store_3d(&a.tmO, src, j * 64, xc, V0);
+            } else {
+              int yp = yp0;
+              for (int gg = 0; gg < 4; ++gg, ++yp) {
+                if (yp >= a.period) yp -= a.period;
+                const int V = V0 + gg;
+                if (V >= a.n_vrows) break;
+                if (yp < 1 || yp > Ho) continue;                     // ring row: written by its mirror source
+                const uint32_t rs = src + (uint32_t)gg * 1024u;
+                tma_store_3d(&a.tmOrow, rs, j * 64, xc, V);
+                if (yp == 2) tma_store_3d(&a.tmOrow, rs, j * 64, xc, V - 2);          // oy == 1 -> ring row 0
+                if (yp == Ho - 1) tma_store_3d(&a.tmOrow, rs, j * 64, xc, V + 2);     // oy == H-2 -> ring row H+1
+              }
+            }
           } else {
-            int yp = yp0;
-            for (int gg = 0; gg < 4; ++gg, ++yp) {
-              if (yp >= a.period) yp -= a.period;
+            // stride-2 conv / 2x transposed-conv phase: every tile row maps to its own output row
+            const int Cc = tg.x0 * S + ps + 1;                     // first padded output column (step S)
+            const int hp2 = (Ho + 2) >> 1;
+            for (int gg = 0; gg < 4; ++gg) {
               const int V = V0 + gg;
               if (V >= a.n_vrows) break;
-              if (yp < 1 || yp > Ho) continue;                       // ring row: written by its mirror source
+              const int bb = fdiv(V, a.fd_period);
+              const int y = V - bb * a.period - a.voff;
+              if (y < 0 || y >= a.H_m) continue;
+              const int oy = y * S + pr;
               const uint32_t rs = src + (uint32_t)gg * 1024u;
-              tma_store_3d(&a.tmOrow, rs, j * 64, xc, V);
-              if (yp == 2) tma_store_3d(&a.tmOrow, rs, j * 64, xc, V - 2);          // oy == 1 -> ring row 0
-              if (yp == Ho - 1) tma_store_3d(&a.tmOrow, rs, j * 64, xc, V + 2);     // oy == H-2 -> ring row H+1
+              auto put = [&](int Rl) {                               // Rl: padded row inside image bb
+                if (S == 1) tma_store_3d(&a.tmOrow, rs, j * 64, xc, bb * (Ho + 2) + Rl);
+                else tma_store_5d(&a.tmOrow, rs, j * 64, Cc & 1, Cc >> 1, Rl & 1, bb * hp2 + (Rl >> 1));
+              };
+              put(oy + 1);
+              if (reflect) {
+                if (oy == 1) put(0);
+                if (oy == Ho - 2) put(Ho + 1);
+              }
             }
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
@@ -1287,8 +1322,10 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
              ok8(d.res1, d.res1_ct, d.res1_coff) && ok8(d.res2, d.res2_ct, d.res2_coff) &&
              (!d.planar || d.head_w);
   }
-  a.epi_tma = g_epi_tma && a.fast && d.stride == 1 && d.up == 1 && (d.N % 64 == 0) && d.out && !d.out2 &&
-              !d.planar && !d.head_w && (a.W_m % TILE_W == 0) && d.act != SRD_ACT_LRELU02 && d.H_out >= 4;
+  a.epi_geo = (d.stride == 1 && d.up == 1) ? 0 : 1;
+  a.epi_tma = g_epi_tma && a.fast && (d.up == 1 || (d.up == 2 && d.stride == 1)) && (d.N % 64 == 0) && d.out &&
+              !d.out2 && !d.planar && !d.head_w && d.act != SRD_ACT_LRELU02 && d.H_out >= 4 &&
+              (a.epi_geo == 0 || !d.res1) && (d.up == 1 || a.W_m % TILE_W == 0);
   // ---- shared-memory plan: A ring + weights (ring or resident) + staging + barriers + epilogue vectors
   const int B_BYTES = a.Npad * 128 / cg;      // per CTA: each CTA of a pair holds Npad / cg rows of a weight k-block
   const int budget = 227 * 1024 - BAR_BYTES - VEC_BYTES - 1024;
@@ -1409,19 +1446,34 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   }
   if (a.epi_tma) {
     const int Hop = d.H_out + 2, Wop = d.W_out + 2;
+    // The column dimension stops at padded column W_out (the right ring column is excluded): boxes of
+    // the last, ragged column tile are clipped by the TMA unit instead of spilling into the ring.
     auto enc_out = [&](CUtensorMap* tm, const void* ptr, int ct, int coff, int rows) {
       void* base = (void*)((const __nv_bfloat16*)ptr + coff);
-      cuuint64_t dims[3] = {(cuuint64_t)d.N, (cuuint64_t)Wop, (cuuint64_t)d.B * Hop};
+      cuuint64_t dims[3] = {(cuuint64_t)d.N, (cuuint64_t)Wop - 1, (cuuint64_t)d.B * Hop};
       cuuint64_t strides[2] = {(cuuint64_t)ct * 2, (cuuint64_t)Wop * ct * 2};
       cuuint32_t box[3] = {64, TILE_W, (cuuint32_t)rows};
       cuuint32_t es[3] = {1, 1, 1};
       return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
+    // 2x transposed conv: [c][col parity][col pair][row parity][row pair]; one phase writes one parity
+    // plane.  The right ring column shares its pair with the last real column, so it cannot be clipped
+    // away here: this map is only used when W_m % 8 == 0 (no ragged column tile).
+    auto enc_out5 = [&](CUtensorMap* tm, const void* ptr, int ct, int coff) {
+      void* base = (void*)((const __nv_bfloat16*)ptr + coff);
+      cuuint64_t dims[5] = {(cuuint64_t)d.N, 2, (cuuint64_t)Wop / 2, 2, (cuuint64_t)d.B * Hop / 2};
+      cuuint64_t strides[4] = {(cuuint64_t)ct * 2, (cuuint64_t)2 * ct * 2, (cuuint64_t)Wop * ct * 2,
+                               (cuuint64_t)2 * Wop * ct * 2};
+      cuuint32_t box[5] = {64, 1, TILE_W, 1, 1};
+      cuuint32_t es[5] = {1, 1, 1, 1, 1};
+      return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                 CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    };
     SRD_CHECK(((uintptr_t)d.out % 16) == 0, "conv_tc: out must be 16-byte aligned");
     CUresult r = enc_out(&a.tmO, d.out, d.out_ct, d.out_coff, 4);
     SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
-    r = enc_out(&a.tmOrow, d.out, d.out_ct, d.out_coff, 1);
+    r = (d.up == 2) ? enc_out5(&a.tmOrow, d.out, d.out_ct, d.out_coff) : enc_out(&a.tmOrow, d.out, d.out_ct, d.out_coff, 1);
     SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(out row) failed with %d", (int)r);
     if (d.res1) {
       r = enc_out(&a.tmR, d.res1, d.res1_ct, d.res1_coff, 4);
