@@ -392,11 +392,15 @@ __device__ __forceinline__ void store_chunk(__nv_bfloat16* p, int ct, long long 
 template <int ACT>
 __device__ __forceinline__ float act_axpy(float x, float alpha, float t) {
   if (ACT == SRD_ACT_MISH) {
-    // mish(x) = x * (1 - 2 / (n*(n+2) + 2)),  n = e^x   (1 ex2 + 1 rcp; see common.cuh)
+    // mish(x) = x * g,  g = tanh(softplus(x)) = 1 - 2 / (n*(n+2) + 2),  n = e^x  (1 ex2 + 1 rcp).
+    // No clamp on x: n overflows to +inf only where g == 1 anyway (rcp(inf) = 0), and there is no
+    // inf * 0 on the way.  8 instructions per element including the bias add of the caller.
     float n, r;
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(n) : "f"(fminf(x, 20.f) * 1.4426950408889634f));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(n) : "f"(x * 1.4426950408889634f));
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(fmaf(n, n + 2.f, 2.f)));
-    return fmaf(fmaf(-2.f * x, r, x), alpha, t);
+    const float g = fmaf(r, -2.f, 1.f);
+    (void)alpha;                                   // the fast epilogues require alpha == 1 with Mish (tc_plan_build)
+    return fmaf(x, g, t);
   }
   if (ACT == SRD_ACT_LRELU02) return fmaf(fmaxf(x, 0.2f * x), alpha, t);
   return fmaf(x, alpha, t);
@@ -1169,6 +1173,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   if (CG == 2) cluster_sync_all();      // both CTAs' barriers are initialised before any remote arrive / TMA lands
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  // Programmatic dependent launch: everything above (barrier init, TMEM allocation, tensor-map and
+  // epilogue-vector staging) touched only launch constants, so it may overlap the tail of the previous
+  // layer.  From here on activations are read / written: wait for the previous grid -- except the weight
+  // producer, whose loads are layer constants and may pre-fill the weight ring meanwhile.
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp != WARP_TMB) asm volatile("griddepcontrol.wait;" ::: "memory");
 
   if (warp == WARP_TMA) {
     if (elect_one_sync()) producer_role<CG>(a, a_base, bar_base);
@@ -1248,12 +1258,14 @@ static int g_a_mode = 1;
 static int g_b_resident = 1;
 static int g_epi_tma = 1;
 static int g_cg = 2;                     // CTAs per MMA: 2 = cta_group::2 pairs (default), 1 = single-CTA MMAs
+static int g_pdl = 1;                    // programmatic dependent launch of consecutive conv layers
 static unsigned long long* g_dbg = nullptr;
 void tc_set_debug(unsigned long long* p) { g_dbg = p; }
 void tc_set_mode(int a_mode, int b_resident) {
   g_a_mode = a_mode & 1;
   g_epi_tma = (a_mode & 2) ? 0 : 1;      // bit 1 of a_mode disables the TMA-staged epilogue
   g_cg = (a_mode & 4) ? 1 : 2;           // bit 2 of a_mode: single-CTA MMAs instead of CTA pairs
+  g_pdl = (a_mode & 8) ? 0 : 1;          // bit 3 of a_mode: no programmatic dependent launch
   g_b_resident = b_resident;
 }
 
@@ -1320,7 +1332,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
     a.fast = (d.N % 16 == 0) && d.temb_bstride == 0 &&
              ok8(d.out, d.out_ct, d.out_coff) && ok8(d.out2, d.out2_ct, d.out2_coff) &&
              ok8(d.res1, d.res1_ct, d.res1_coff) && ok8(d.res2, d.res2_ct, d.res2_coff) &&
-             (!d.planar || d.head_w);
+             (!d.planar || d.head_w) && (d.act != SRD_ACT_MISH || d.alpha == 1.0f);
   }
   a.epi_geo = (d.stride == 1 && d.up == 1) ? 0 : 1;
   a.epi_tma = g_epi_tma && a.fast && (d.up == 1 || (d.up == 2 && d.stride == 1)) && (d.N % 64 == 0) && d.out &&
@@ -1495,22 +1507,27 @@ void tc_plan_delete(TcPlan* p) { delete p; }
 int launch_conv_tc(const TcPlan& plan, const float* temb, cudaStream_t stream) {
   TcArgs a = plan.args;
   if (temb) a.ep.temb = temb;
-  if (a.cg == 1) {
-    conv_tc_kernel<1><<<plan.grid, TC_THREADS, plan.smem, stream>>>(a);
-    SRD_CUDA(cudaGetLastError());
-  } else {
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)plan.grid);
-    cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = (size_t)plan.smem;
-    cfg.stream = stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, a));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)plan.grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = (size_t)plan.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int n_at = 0;
+  if (g_pdl) {      // this launch may begin while the previous kernel on the stream drains (see griddepcontrol.wait)
+    at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n_at].val.programmaticStreamSerializationAllowed = 1;
+    ++n_at;
   }
+  if (a.cg == 2) {
+    at[n_at].id = cudaLaunchAttributeClusterDimension;
+    at[n_at].val.clusterDim.x = 2; at[n_at].val.clusterDim.y = 1; at[n_at].val.clusterDim.z = 1;
+    ++n_at;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = (unsigned)n_at;
+  if (a.cg == 1) SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, a));
+  else SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, a));
   return 0;
 }
 

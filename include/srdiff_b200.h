@@ -104,9 +104,12 @@ int srd_conv_plan_destroy(SrdConvPlan* plan);
 int srd_conv_plan_kernel(const SrdConvPlan* plan);
 /* Launch.  `temb` overrides desc.temb when non-NULL (per-step row of the time table). */
 int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream);
-/* Tuning switches for plans created afterwards.  a_mode: 0 = one TMA box per (chunk, kx) with
- * 1024 B-aligned UMMA descriptors; 1 = one halo box per chunk, taps addressed by 128 B-granular
- * descriptor start offsets (default; validated on B200); +2 disables the TMA-staged epilogue.
+/* Tuning / validation switches for plans created afterwards (defaults: a_mode = 1, b_resident = 1).
+ * a_mode bit 0: 1 = one halo TMA box per K chunk, taps addressed by 128 B-granular UMMA descriptor
+ *               offsets (default); 0 = one box per (chunk, kx) with 1024 B-aligned descriptors.
+ *        bit 1: disable the TMA-staged epilogue (register epilogue with direct global stores).
+ *        bit 2: single-CTA MMAs (cta_group::1) instead of CTA pairs (cta_group::2, M = 256).
+ *        bit 3: no programmatic dependent launch between consecutive conv layers.
  * b_resident: keep all weight k-blocks in shared memory when they fit. */
 int srd_tc_set_mode(int32_t a_mode, int32_t b_resident);
 /* Debug: plans created afterwards record per-item clock64 stamps into buf [grid][64][8] (NULL = off). */
