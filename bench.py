@@ -348,6 +348,8 @@ def per_layer_timings(plan, torch, E, L):
         us = e0.elapsed_time(e1) * 1000.0 / 5
         cin = sum(d.src[i].cin for i in range(d.n_src))
         taps = d.nky * d.nkx
+        if d.src[0].flags & 1:          # SRD_SRC_WIN8: three K=64 blocks stand for a 3x3 conv over the 3 real channels
+            cin, taps = 3, 9
         flops = 2.0 * d.B * (d.H_out * d.W_out) * d.N * cin * taps
         out.append({"cin": cin, "N": d.N, "H_out": d.H_out, "stride": d.stride, "up": d.up, "taps": taps,
                     "kernel": op.kernel, "us": us, "tflops": flops / us / 1e6})

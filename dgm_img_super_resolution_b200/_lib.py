@@ -15,11 +15,12 @@ F32, BF16 = 0, 1
 KERNEL_AUTO, KERNEL_DIRECT, KERNEL_TC = 0, 1, 2
 ACT_NONE, ACT_MISH, ACT_LRELU02 = 0, 1, 2
 BORDER_KEEP, BORDER_REFLECT = 0, 1
+SRC_WIN8 = 1
 
 
 class SrdSrc(C.Structure):
     _fields_ = [("ptr", C.c_void_p), ("ct", C.c_int32), ("c_off", C.c_int32),
-                ("cin", C.c_int32), ("reserved", C.c_int32)]
+                ("cin", C.c_int32), ("flags", C.c_int32)]
 
 
 class SrdConvDesc(C.Structure):
@@ -39,6 +40,7 @@ class SrdConvDesc(C.Structure):
         ("H_out", C.c_int32), ("W_out", C.c_int32), ("border", C.c_int32),
         ("planar", C.c_void_p), ("planar_c", C.c_int32), ("planar_clamp01", C.c_int32),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p),
+        ("lin_src", C.c_void_p), ("lin_ct", C.c_int32), ("lin_c", C.c_int32), ("lin_w", C.c_void_p),
     ]
 
 
@@ -101,14 +103,15 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        abi = (C.sizeof(SrdConvDesc), C.sizeof(SrdPSampleArgs), SrdConvDesc.head_b.offset,
+        abi = (C.sizeof(SrdConvDesc), C.sizeof(SrdPSampleArgs), SrdConvDesc.lin_w.offset,
                SrdPSampleArgs.seed_ptr.offset)
         got = tuple(L.srd_abi_sizeof(i) for i in range(4))
         if abi != got:
             raise SrdError("ctypes structs disagree with include/srdiff_b200.h: %s vs %s" % (abi, got))
         # tuning / validation switches of the tcgen05 kernel (see srd_tc_set_mode in the header)
         if "SRD_TC_A_MODE" in os.environ or "SRD_TC_B_RESIDENT" in os.environ:
-            L.srd_tc_set_mode(int(os.environ.get("SRD_TC_A_MODE", "0")), int(os.environ.get("SRD_TC_B_RESIDENT", "1")))
+            if L.srd_tc_set_mode(int(os.environ.get("SRD_TC_A_MODE", "1")), int(os.environ.get("SRD_TC_B_RESIDENT", "1"))):
+                raise SrdError("srd_tc_set_mode rejected SRD_TC_A_MODE / SRD_TC_B_RESIDENT: %s" % L.srd_last_error().decode())
         _lib = L
     return _lib
 

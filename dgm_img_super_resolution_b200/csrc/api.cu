@@ -74,6 +74,7 @@ static int validate(const SrdConvDesc& d) {
   SRD_CHECK(d.out || d.out2 || d.planar, "conv: no destination");
   for (int i = 0; i < d.n_src; ++i) {
     SRD_CHECK(d.src[i].ptr != nullptr, "conv: src[%d].ptr is NULL", i);
+    if (d.src[i].flags & SRD_SRC_WIN8) continue;      // 64 = 8 pixels x 8 channels, checked by the tc planner
     SRD_CHECK(d.src[i].cin > 0 && d.src[i].c_off >= 0 && d.src[i].c_off + d.src[i].cin <= d.src[i].ct,
               "conv: src[%d] channel window [%d,+%d) outside ct=%d", i, d.src[i].c_off, d.src[i].cin, d.src[i].ct);
   }
@@ -83,6 +84,8 @@ static int validate(const SrdConvDesc& d) {
   SRD_CHECK(!d.res2 || (d.res2_coff + d.N <= d.res2_ct), "conv: res2 channel window outside res2_ct");
   SRD_CHECK(!d.planar || d.planar_c > 0, "conv: planar_c must be positive");
   SRD_CHECK(!d.head_w || (d.head_b && d.planar), "conv: fused head needs head_b and planar");
+  SRD_CHECK(!d.lin_src || (d.lin_w && d.lin_c >= 1 && d.lin_c <= 4 && d.lin_c <= d.lin_ct),
+            "conv: linear residual needs lin_w and 1 <= lin_c <= min(4, lin_ct)");
   return 0;
 }
 
@@ -96,7 +99,7 @@ int srd_abi_sizeof(int32_t which) {
   switch (which) {
     case 0: return (int)sizeof(SrdConvDesc);
     case 1: return (int)sizeof(SrdPSampleArgs);
-    case 2: return (int)offsetof(SrdConvDesc, head_b);
+    case 2: return (int)offsetof(SrdConvDesc, lin_w);
     case 3: return (int)offsetof(SrdPSampleArgs, seed_ptr);
     default: return -1;
   }
@@ -126,6 +129,9 @@ int srd_conv_plan_create(const SrdConvDesc* desc, SrdConvPlan** out_plan) {
   } else {
     if (!desc->w_direct) { delete p; SRD_CHECK(false, "srd_conv_plan_create: direct kernel needs w_direct"); }
     if (desc->head_w) { delete p; SRD_CHECK(false, "srd_conv_plan_create: fused head needs the tc kernel"); }
+    if (desc->lin_src) { delete p; SRD_CHECK(false, "srd_conv_plan_create: linear residual needs the tc kernel"); }
+    for (int i = 0; i < desc->n_src; ++i)
+      if (desc->src[i].flags & SRD_SRC_WIN8) { delete p; SRD_CHECK(false, "srd_conv_plan_create: SRD_SRC_WIN8 needs the tc kernel"); }
   }
   p->kernel = k;
   *out_plan = p;
@@ -148,7 +154,7 @@ int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream) {
 }
 
 int srd_tc_set_mode(int32_t a_mode, int32_t b_resident) {
-  SRD_CHECK(a_mode >= 0 && a_mode <= 3, "srd_tc_set_mode: a_mode must be in 0..3");
+  SRD_CHECK(a_mode >= 0 && a_mode <= 15, "srd_tc_set_mode: a_mode must be in 0..15");
   tc_set_mode(a_mode, b_resident ? 1 : 0);
   return 0;
 }

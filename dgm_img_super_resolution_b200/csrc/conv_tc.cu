@@ -93,6 +93,9 @@ struct TcArgs {
   Epi ep;
   const float* head_w;
   const float* head_b;
+  const __nv_bfloat16* lin_src;   // linear residual: v += lin_w[n][c] * lin_src[pixel][c], c < lin_c (<= 4)
+  const float* lin_w;
+  int lin_ct, lin_c;
   int* err_flag;
   int fast;                // epilogue fast path eligible (N % 16 == 0, uniform temb, aligned windows)
   int a_mode;              // 0: one box per (chunk, kx), ky by 1024 B row offsets (always-aligned descriptors)
@@ -323,6 +326,7 @@ struct EpiSmem {
   const float* head_w;
   const float* head_b;
   float* hpart;     // [2][128][4]
+  const float* lin_w;   // [4][Npad] (transposed, zero padded) or nullptr; shares the head_w storage
 };
 
 __device__ __forceinline__ void unpack_bf16x8(const uint4& u, float (&f)[8]) {
@@ -708,6 +712,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     uint32_t edge = 0, tbase = 0;
     __nv_bfloat16* outp = nullptr;
     const __nv_bfloat16* r2p = nullptr;
+    float lin[4] = {0.f, 0.f, 0.f, 0.f};                         // this pixel's linear-residual inputs
     {
       for (int qq = share; qq < n_sub; qq += a.n_share, ++k) {
         const int mt = (qq >= nsj) ? 1 : 0, j = qq - mt * nsj;
@@ -723,6 +728,12 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
           outp = static_cast<__nv_bfloat16*>(a.ep.out) + pix * a.ep.out_ct + a.ep.out_coff;
           r2p = (a.ep.res2 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
           tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((stage * a.MT + mt) * a.Npad);
+          if (es.lin_w) {
+            uint2 xv = make_uint2(0u, 0u);                         // 4 bf16 channels of the pixel (buffers have ct % 8 == 0)
+            if (valid) xv = *reinterpret_cast<const uint2*>(a.lin_src + pix * a.lin_ct);
+            lin[0] = __uint_as_float(xv.x << 16); lin[1] = __uint_as_float(xv.x & 0xFFFF0000u);
+            lin[2] = __uint_as_float(xv.y << 16); lin[3] = __uint_as_float(xv.y & 0xFFFF0000u);
+          }
         }
         const uint32_t buf = k & nbuf_mask;
         uint8_t* row = my_row + buf * 4096u;
@@ -765,6 +776,20 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
             unpack_bf16x8(*s1, f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) v[8 + i] = fmaf(a.ep.beta1, f[i], v[8 + i]);
+          }
+          if (es.lin_w) {                                        // 1x1 res_conv over <= 4 channels, weights [c][Npad] in smem
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+              if (c < a.lin_c) {
+                const float4* lw = reinterpret_cast<const float4*>(es.lin_w + c * a.Npad + c0);
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 w4 = lw[q];
+                  v[4 * q + 0] = fmaf(w4.x, lin[c], v[4 * q + 0]); v[4 * q + 1] = fmaf(w4.y, lin[c], v[4 * q + 1]);
+                  v[4 * q + 2] = fmaf(w4.z, lin[c], v[4 * q + 2]); v[4 * q + 3] = fmaf(w4.w, lin[c], v[4 * q + 3]);
+                }
+              }
+            }
           }
           if (r2p) {
             const uint4* q = reinterpret_cast<const uint4*>(r2p + c0);
@@ -1168,6 +1193,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
     if (threadIdx.x < 4) s_headb[threadIdx.x] = (threadIdx.x < a.ep.planar_c) ? __ldg(a.head_b + threadIdx.x) : 0.f;
   }
+  if (a.lin_w) {      // linear-residual weights, transposed to [4][Npad] (shares the head-weight storage)
+    for (int i = threadIdx.x; i < 4 * a.Npad; i += TC_THREADS) {
+      const int c = i / a.Npad, n = i % a.Npad;
+      s_head[i] = (c < a.lin_c && n < a.ep.N) ? __ldg(a.lin_w + (size_t)n * a.lin_c + c) : 0.f;
+    }
+  }
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();      // both CTAs' barriers are initialised before any remote arrive / TMA lands
@@ -1206,6 +1237,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     EpiSmem es;
     es.bias = s_bias; es.temb = s_temb;
     es.head_w = a.head_w ? s_head : nullptr; es.head_b = s_headb; es.hpart = s_hpart;
+    es.lin_w = a.lin_w ? s_head : nullptr;
     if (a.epi_tma) {
       const int ew = warp - WARP_EPI0;                 // epilogue warp index
       StageSmem sg;
@@ -1278,10 +1310,15 @@ int tc_supported(const SrdConvDesc& d, const char** why) {
     w = "stride-2 needs a plain 3x3 on even dims";
   else if (d.stride != 1 && d.stride != 2) w = "stride";
   else if (d.head_w && (d.planar_c > 4 || !d.planar)) w = "head needs planar_c <= 4";
+  else if (d.head_w && d.lin_src) w = "fused head and linear residual are exclusive";
   else {
     for (int i = 0; i < d.n_src; ++i) {
       const SrdSrc& s = d.src[i];
       if ((s.ct % 8) || (s.c_off % 8) || s.cin < 1 || ((uintptr_t)s.ptr % 16)) { w = "source alignment"; break; }
+      if ((s.flags & SRD_SRC_WIN8) && (s.ct != 8 || s.c_off != 0 || s.cin != 64 || d.stride != 1 || d.up != 1 || d.nkx != 1)) {
+        w = "SRD_SRC_WIN8 needs ct == 8, c_off == 0, cin == 64, a plain stride-1 conv and nkx == 1";
+        break;
+      }
     }
   }
   if (why) *why = w;
@@ -1325,6 +1362,8 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   a.idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(a.Npad >> 3) << 17) | ((uint32_t)((128 * cg) >> 4) << 24);
   a.ep = make_epi(d, nullptr);
   a.head_w = d.head_w; a.head_b = d.head_b;
+  a.lin_src = static_cast<const __nv_bfloat16*>(d.lin_src); a.lin_w = d.lin_src ? d.lin_w : nullptr;
+  a.lin_ct = d.lin_ct; a.lin_c = d.lin_c;
   a.err_flag = err_flag;
   a.dbg = g_dbg;
   {
@@ -1417,6 +1456,8 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
     a.n_share = share;
   }
   SRD_CHECK(!d.head_w || a.n_share == 1, "conv_tc: fused head needs N * MT <= 128");
+  SRD_CHECK(!d.lin_src || a.epi_tma, "conv_tc: the linear residual needs the TMA-staged epilogue "
+            "(stride-1 conv, N %% 64 == 0, NHWC output, batch-uniform temb)");
   plan->smem = a.a_stages * stage_bytes + b_bytes_total + stg_total + BAR_BYTES + VEC_BYTES + 1024;
   plan->grid = (a.n_items < n_sm / cg ? a.n_items : n_sm / cg) * cg;
 
@@ -1425,7 +1466,18 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
     const SrdSrc& s = d.src[i];
     void* base = (void*)((const __nv_bfloat16*)s.ptr + s.c_off);
     CUresult r;
-    if (d.stride == 1) {
+    if (s.flags & SRD_SRC_WIN8) {
+      // overlapping windows: element (k, x, row) = buffer[row][x + k / 8][k % 8]; consecutive x positions are
+      // one pixel (16 B) apart while the 64-element inner box spans 8 pixels (128 B)
+      SRD_CHECK(a.a_mode == 1, "conv_tc: SRD_SRC_WIN8 needs the halo A mode");
+      cuuint64_t dims[3] = {64, (cuuint64_t)Wp, (cuuint64_t)d.B * Hp};
+      cuuint64_t strides[2] = {16, (cuuint64_t)Wp * 16};
+      cuuint32_t box[3] = {64, (cuuint32_t)HALO_W, BOX_ROWS};
+      cuuint32_t es[3] = {1, 1, 1};
+      r = enc(&a.tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)s.ptr, dims, strides, box, es,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    } else if (d.stride == 1) {
       cuuint64_t dims[3] = {(cuuint64_t)s.cin, (cuuint64_t)Wp, (cuuint64_t)d.B * Hp};
       cuuint64_t strides[2] = {(cuuint64_t)s.ct * 2, (cuuint64_t)Wp * s.ct * 2};
       cuuint32_t box[3] = {64, (cuuint32_t)(a.a_mode ? HALO_W : TILE_W), BOX_ROWS};

@@ -45,9 +45,12 @@ class Precision:
 class Act:
     """[B][H+2][W+2][ct] buffer; ring zero-initialised (consumers that need zero padding rely on it)."""
 
-    def __init__(self, B, H, W, ct, prec, device):
+    def __init__(self, B, H, W, ct, prec, device, slack=0):
         self.B, self.H, self.W, self.ct = B, H, W, ct
-        self.t = torch.zeros((B, H + 2, W + 2, ct), dtype=prec.torch_dtype, device=device)
+        n = B * (H + 2) * (W + 2) * ct
+        # `slack` extra zero elements after the last pixel (SRD_SRC_WIN8 windows read past the row end)
+        self._flat = torch.zeros(n + slack, dtype=prec.torch_dtype, device=device)
+        self.t = self._flat[:n].view(B, H + 2, W + 2, ct)
 
     @property
     def ptr(self):
@@ -119,6 +122,18 @@ def _pack_convT(weight, src_cins, S):
     return w_direct, w_tc
 
 
+def _pack_conv_win8(weight):
+    """3x3 nn.Conv2d weight [O][I<=8][3][3] for an SRD_SRC_WIN8 source: one K = 64 block per ky whose K
+    index is dx*8 + c (dx = pixel inside the 8-pixel window = kx for dx < 3, zero weights beyond)."""
+    O, I, kh, kw = weight.shape
+    assert kh == 3 and kw == 3 and I <= 8
+    npad = _ceil(O, 16) * 16
+    w = weight.detach().float()
+    blk = torch.zeros((kh, npad, 8, 8), dtype=torch.float32, device=w.device)      # [ky][n][dx][c]
+    blk[:, :O, :kw, :I] = w.permute(2, 0, 3, 1)                                       # [ky][O][kx][I]
+    return blk.reshape(kh, npad, 64).to(torch.bfloat16).contiguous()
+
+
 class PackedConv:
     """Caches the packed forms of one conv layer's parameters, keyed by parameter identity/version."""
 
@@ -134,6 +149,16 @@ class PackedConv:
     @property
     def ksize(self):
         return self.weight.shape[2]
+
+    def get_win8(self):
+        """(w_direct, w_tc_win8, bias) for an SRD_SRC_WIN8 source (see _pack_conv_win8)."""
+        key = ("win8", self.weight.data_ptr(), self.weight._version, self.bias_p.data_ptr(), self.bias_p._version)
+        hit = self._cache.get("w8")
+        if hit is None or hit[0] != key:
+            wd, _ = _pack_conv(self.weight, [self.weight.shape[1]], 1)
+            self._cache["w8"] = (key, wd, _pack_conv_win8(self.weight), self.bias_p.detach().float().contiguous())
+            hit = self._cache["w8"]
+        return hit[1], hit[2], hit[3]
 
     def get(self, src_cins):
         key = (tuple(src_cins), self.weight.data_ptr(), self.weight._version,
@@ -199,9 +224,9 @@ class Builder:
         self.prec = precision if isinstance(precision, Precision) else Precision(precision)
         self.ops = []
 
-    def act(self, B, H, W, C_, ct=None):
+    def act(self, B, H, W, C_, ct=None, slack=0):
         ct = _ceil(C_ if ct is None else ct, 8) * 8
-        return Act(B, H, W, ct, self.prec, self.device)
+        return Act(B, H, W, ct, self.prec, self.device, slack=slack)
 
     def run(self, ctx=None):
         ctx = ctx or RunCtx()
@@ -215,8 +240,11 @@ class Builder:
     # ---- generic conv ----------------------------------------------------------------------
     def conv(self, pw, srcs, out=None, out_coff=0, out2=None, out2_coff=0, act=L.ACT_NONE, alpha=1.0,
              temb_off=None, temb_bstride=0, res1=None, res2=None, border=L.BORDER_KEEP, planar=None,
-             planar_c=0, planar_clamp01=0, head=None, kernel=None):
-        """srcs: list of (Act, c_off, cin); res1/res2: (Act, c_off, beta); head: (w[planar_c][N], b)."""
+             planar_c=0, planar_clamp01=0, head=None, kernel=None, win8=False, lin=None, temb_static=None):
+        """srcs: list of (Act, c_off, cin); res1/res2: (Act, c_off, beta); head: (w[planar_c][N], b).
+        win8: the single source is an 8-channel buffer read through SRD_SRC_WIN8 (3x3 conv as three K=64
+        blocks).  lin: (Act, w[N][c], c) linear residual evaluated in the epilogue; temb_static: fp32 [N]
+        vector added after the activation (e.g. the bias of the folded res_conv)."""
         d = L.SrdConvDesc()
         d.dtype = self.prec.dtype
         d.kernel = self.prec.kernel if kernel is None else kernel
@@ -226,8 +254,17 @@ class Builder:
         for i, (a, coff, cin) in enumerate(srcs):
             assert (a.B, a.H, a.W) == (a0.B, a0.H, a0.W), "conv sources must share B/H/W"
             d.src[i].ptr, d.src[i].ct, d.src[i].c_off, d.src[i].cin = a.ptr, a.ct, coff, cin
-        wd, wt, bias = pw.get([s[2] for s in srcs])
-        if pw.transposed:
+        if win8:
+            assert len(srcs) == 1 and a0.ct == 8 and not pw.transposed and pw.ksize == 3 and pw.stride == 1
+            assert a0._flat.numel() - a0.t.numel() >= 56, "SRD_SRC_WIN8 source needs >= 112 B of slack"
+            wd, wt, bias = pw.get_win8()
+            d.src[0].cin, d.src[0].flags = 64, L.SRC_WIN8
+            d.kernel = L.KERNEL_TC
+        else:
+            wd, wt, bias = pw.get([s[2] for s in srcs])
+        if win8:
+            d.stride, d.nky, d.nkx, d.ky0, d.kx0, d.up = 1, 3, 1, 0, 0, 1
+        elif pw.transposed:
             S = pw.ksize // 2
             d.stride, d.nky, d.nkx, d.ky0, d.kx0, d.up = 1, 2, 2, 0, 0, S
         else:
@@ -239,6 +276,14 @@ class Builder:
         d.act, d.alpha = act, alpha
         d.temb, d.temb_bstride = None, temb_bstride
         keep = [wd, wt, bias, [s[0] for s in srcs], out, out2, planar]
+        if temb_static is not None:
+            assert temb_off is None
+            d.temb = temb_static.data_ptr()
+            keep.append(temb_static)
+        if lin is not None:
+            d.lin_src, d.lin_ct, d.lin_c, d.lin_w = lin[0].ptr, lin[0].ct, lin[2], lin[1].data_ptr()
+            d.kernel = L.KERNEL_TC
+            keep.append(lin)
         if res1 is not None:
             d.res1, d.res1_ct, d.res1_coff, d.beta1 = res1[0].ptr, res1[0].ct, res1[1], res1[2]
             keep.append(res1[0])
@@ -310,6 +355,20 @@ def build_resnet(bld, blk, srcs, dim_out, out, border, temb_off, temb_bstride=0,
     cin = sum(s[2] for s in srcs)
     h1 = bld.act(B, H, W, dim_out)
     use_temb = temb_off is not None
+    # Few-channel input (the Unet's first block, 3 -> 64) on the tcgen05 path: block1 reads the 8-channel
+    # buffer through 8-pixel windows (K = 3 x 64 instead of 9 x 64), and the 1x1 res_conv (:471,480)
+    # is evaluated inside block2's epilogue (3 FMAs per output) instead of a launch of its own.
+    packed = (bld.prec.name == "bf16" and len(srcs) == 1 and cin <= 4 and a0.ct == 8 and srcs[0][1] == 0 and
+              cin != dim_out and dim_out % 64 == 0 and W % 8 == 0 and (temb_bstride == 0 or not use_temb) and
+              extra_res is None and a0._flat.numel() - a0.t.numel() >= 56)
+    if packed:
+        bld.conv(_pc(blk.block1.block[1]), srcs, out=h1, act=L.ACT_MISH, temb_off=temb_off, border=L.BORDER_REFLECT,
+                 win8=True)
+        lw = blk.res_conv.weight.detach().float().reshape(dim_out, cin).contiguous()
+        lb = blk.res_conv.bias.detach().float().contiguous()
+        bld.conv(_pc(blk.block2.block[1]), [(h1, 0, dim_out)], out=out, act=L.ACT_MISH, lin=(a0, lw, cin),
+                 temb_static=lb, border=border)
+        return out
     bld.conv(_pc(blk.block1.block[1]), srcs, out=h1, act=L.ACT_MISH, temb_off=temb_off,
              temb_bstride=temb_bstride if use_temb else 0, border=L.BORDER_REFLECT)
     if cin != dim_out:
@@ -341,7 +400,7 @@ class UnetProgram:
         nlev = len(dims) - 1
         if H % (2 ** (nlev - 1)) or W % (2 ** (nlev - 1)):
             raise ValueError("Unet input %dx%d must be divisible by %d" % (H, W, 2 ** (nlev - 1)))
-        self.xin = bld.act(B, H, W, 3)
+        self.xin = bld.act(B, H, W, 3, slack=64)       # slack: read through SRD_SRC_WIN8 windows
         self.cond = cond_act if cond_act is not None else bld.act(B, H, W, dims[1])
         self.eps = torch.empty((B, unet._out_dim, H, W), dtype=torch.float32, device=device)
         # time-table offsets, in the order of unet.resnet_blocks()

@@ -45,8 +45,16 @@ typedef struct {
   int32_t ct;
   int32_t c_off;
   int32_t cin;
-  int32_t reserved;
+  int32_t flags;          /* SRD_SRC_* */
 } SrdSrc;
+
+/* SRD_SRC_WIN8 (tcgen05 kernel only, stride 1): the buffer has ct == 8 channels per pixel and the
+ * source's 64 "channels" are the 8-pixel window [x, x+8) x 8 channels that starts at the tap's
+ * column, i.e. K index = dx*8 + c.  A 3x3 conv over <= 8 real channels then needs nky = 3, nkx = 1
+ * (three K = 64 blocks instead of nine): this is how the Unet's first conv (3 -> 64, :444-446) runs.
+ * The window of the last pixels of a row runs into the next row (those K slots carry zero weights);
+ * the buffer must therefore be readable for 112 bytes past its last pixel. */
+enum { SRD_SRC_WIN8 = 1 };
 
 /* Convolution descriptor.  Computes, for every output pixel p and channel n < N,
  *   acc      = sum_{src, ky, kx, c} in_src[p*stride + (ky,kx)][c] * W[...][n]
@@ -86,6 +94,11 @@ typedef struct {
   int32_t planar_clamp01; /* 1: planar = clamp(v,0,1)*2-1 (RRDBNet tail :744-745)                */
   const float* head_w;    /* optional fused 1x1 head [planar_c][N] (final_conv.1 :800), tc only  */
   const float* head_b;
+  /* optional linear residual (tc kernel, TMA-staged epilogue): v += sum_{c<lin_c} lin_w[n][c] *
+   * lin_src[p][c] -- a 1x1 res_conv over <= 4 input channels (ResnetBlock.res_conv of the first
+   * block, :471,480) evaluated in the epilogue instead of a separate launch; its bias rides on temb. */
+  const void* lin_src; int32_t lin_ct, lin_c;
+  const float* lin_w;     /* fp32 [N][lin_c] */
 } SrdConvDesc;
 
 typedef struct SrdConvPlan SrdConvPlan;
@@ -93,7 +106,7 @@ typedef struct SrdConvPlan SrdConvPlan;
 const char* srd_last_error(void);
 int srd_version(void);
 /* ABI self-check for FFI bindings: which = 0 -> sizeof(SrdConvDesc), 1 -> sizeof(SrdPSampleArgs),
- * 2 -> offsetof(SrdConvDesc, head_b), 3 -> offsetof(SrdPSampleArgs, seed_ptr). */
+ * 2 -> offsetof(SrdConvDesc, lin_w), 3 -> offsetof(SrdPSampleArgs, seed_ptr). */
 int srd_abi_sizeof(int32_t which);
 /* 1 if the tcgen05/TMA path can serve this descriptor (bf16, channel/stride alignment...). */
 int srd_conv_tc_supported(const SrdConvDesc* desc);
