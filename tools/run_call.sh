@@ -1,9 +1,5 @@
 mkdir -p gpurun_out
-timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest.log
-timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu --layers > gpurun_out/bench.log 2>&1; echo "bench rc=$?"
-python -c "
-import json;d=json.loads(open('gpurun_out/bench.log').read().strip().splitlines()[-1]);print('bench',d['value'],d['roofline']['ms_per_pass'],d['roofline']['frac'],d['e2e']['value'])
-a=json.load(open('gpurun_out/layers.json'))
-for x in a[:6]: print('%4d %4d %4d s%d up%d t%d | %6.1f us %5.0f TF' % (x['cin'],x['N'],x['H_out'],x['stride'],x['up'],x['taps'],x['us'],x['tflops']))
-"
-tail -5 gpurun_out/bench.log | cut -c1-300
+python tools/profile_conv.py 3 64 160 64 conv3 5
+NORES=1 python tools/profile_conv.py 64 64 160 64 conv3 5
+python tools/profile_conv.py 64 64 160 64 conv3 5
+timeout 300 ncu --set full --import-source on --clock-control none -k regex:conv_tc -s 2 -c 1 -o gpurun_out/prof5_c3 -f python tools/profile_conv.py 3 64 160 64 conv3 3 > gpurun_out/ncu5.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu5.log
