@@ -27,13 +27,15 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint32_t quad, uint32_t i
   uint32_t r[4];
   philox4x32_10(quad, image, step, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
   const float k = 2.3283064365386963e-10f;  // 2^-32
+  // Box-Muller on the MUFU pipe (lg2 / sqrt / sin / cos approximations, ~1e-6 absolute error on
+  // arguments in [0, 2*pi]): the libm versions made this HBM-bound kernel ALU-bound.
 #pragma unroll
   for (int i = 0; i < 2; ++i) {
     const float u1 = ((float)r[2 * i] + 1.0f) * k;        // (0, 1]
     const float u2 = (float)r[2 * i + 1] * k;             // [0, 1]
-    const float rad = sqrtf(-2.0f * logf(fminf(u1, 1.0f)));
+    const float rad = sqrtf(-1.3862943611198906f * __log2f(fminf(u1, 1.0f)));   // sqrt(-2 ln u1)
     float s, c;
-    sincospif(2.0f * u2, &s, &c);
+    __sincosf(6.283185307179586f * u2, &s, &c);
     z[2 * i] = rad * c;
     z[2 * i + 1] = rad * s;
   }
@@ -64,7 +66,7 @@ __global__ void randn_kernel(float* out, int B, int chw, uint64_t seed, uint32_t
 // Algorithmic HBM traffic: 16 B/element with a noise tensor (x, eps, z in; x' out), 12 B with
 // in-kernel Philox (+ the small NHWC copy of x' when requested).
 // ------------------------------------------------------------------------------------------
-template <int V, typename T>
+template <int V, typename T, bool SMALLC>
 __global__ void __launch_bounds__(256) p_sample_kernel(const SrdPSampleArgs a) {
   const int HW = a.H * a.W;
   const int nq = HW / V;                       // V divides W (checked on the host)
@@ -86,10 +88,32 @@ __global__ void __launch_bounds__(256) p_sample_kernel(const SrdPSampleArgs a) {
 #pragma unroll
         for (int c = 0; c < 8; ++c) nh[v][c] = 0.f;
     }
-    for (int c = 0; c < a.C; ++c) {
+    // All loads of the pixel group are issued before any store: x_out may alias x (in-place update), so
+    // the compiler cannot hoist the next channel's loads above this channel's stores by itself, and a
+    // thread would have only two 16 B loads in flight.
+    float4 px4[4], pe4[4];
+    if (SMALLC) {
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        if (c < a.C) {
+          const size_t off = ((size_t)b * a.C + c) * HW + pix;
+          px4[c] = __ldg(reinterpret_cast<const float4*>(a.x + off));
+          pe4[c] = __ldg(reinterpret_cast<const float4*>(a.eps + off));
+        }
+      }
+    }
+    // SMALLC (V == 4, C <= 4): four fully unrolled, predicated channel iterations over the preloaded
+    // registers; otherwise one runtime loop over the channels.
+#pragma unroll
+    for (int cu = 0; cu < (SMALLC ? 4 : 1); ++cu)
+    for (int c = SMALLC ? cu : 0; c < (SMALLC ? (cu < a.C ? cu + 1 : 0) : a.C); ++c) {
       const size_t off = ((size_t)b * a.C + c) * HW + pix;
       float xv[V], ev[V], zv[V], ov[V], x0v[V];
-      if (V == 4) {
+      if (SMALLC) {
+        const float4 t0 = px4[cu], t1 = pe4[cu];
+        xv[0] = t0.x; xv[1] = t0.y; xv[2] = t0.z; xv[3] = t0.w;
+        ev[0] = t1.x; ev[1] = t1.y; ev[2] = t1.z; ev[3] = t1.w;
+      } else if (V == 4) {
         const float4 t0 = *reinterpret_cast<const float4*>(a.x + off);
         const float4 t1 = *reinterpret_cast<const float4*>(a.eps + off);
         xv[0] = t0.x; xv[1] = t0.y; xv[2] = t0.z; xv[3] = t0.w;
@@ -315,11 +339,13 @@ int srd_p_sample_step(const SrdPSampleArgs* a, void* stream) {
   const int grid = grid_for(total);
   cudaStream_t s = (cudaStream_t)stream;
   if (a->act_dtype == SRD_BF16) {
-    if (v4) p_sample_kernel<4, __nv_bfloat16><<<grid, 256, 0, s>>>(*a);
-    else p_sample_kernel<1, __nv_bfloat16><<<grid, 256, 0, s>>>(*a);
+    if (v4 && a->C <= 4) p_sample_kernel<4, __nv_bfloat16, true><<<grid, 256, 0, s>>>(*a);
+    else if (v4) p_sample_kernel<4, __nv_bfloat16, false><<<grid, 256, 0, s>>>(*a);
+    else p_sample_kernel<1, __nv_bfloat16, false><<<grid, 256, 0, s>>>(*a);
   } else {
-    if (v4) p_sample_kernel<4, float><<<grid, 256, 0, s>>>(*a);
-    else p_sample_kernel<1, float><<<grid, 256, 0, s>>>(*a);
+    if (v4 && a->C <= 4) p_sample_kernel<4, float, true><<<grid, 256, 0, s>>>(*a);
+    else if (v4) p_sample_kernel<4, float, false><<<grid, 256, 0, s>>>(*a);
+    else p_sample_kernel<1, float, false><<<grid, 256, 0, s>>>(*a);
   }
   SRD_CUDA(cudaGetLastError());
   return 0;

@@ -1,5 +1,6 @@
 mkdir -p gpurun_out
-python tools/profile_conv.py 3 64 160 64 conv3 5
-NORES=1 python tools/profile_conv.py 64 64 160 64 conv3 5
-python tools/profile_conv.py 64 64 160 64 conv3 5
-timeout 300 ncu --set full --import-source on --clock-control none -k regex:conv_tc -s 2 -c 1 -o gpurun_out/prof5_c3 -f python tools/profile_conv.py 3 64 160 64 conv3 3 > gpurun_out/ncu5.log 2>&1; echo "ncu rc=$?"; tail -2 gpurun_out/ncu5.log
+timeout 600 python -m pytest tests -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest.log
+timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu > gpurun_out/bench.log 2>&1; echo "bench rc=$?"
+python -c "
+import json;d=json.loads(open('gpurun_out/bench.log').read().strip().splitlines()[-1]);print('bench',d['value'],d['roofline']['ms_per_pass'],d['roofline']['frac'],d['e2e']['value'],d['roofline_p_sample'])
+"
