@@ -35,6 +35,16 @@ def load_hparams():
     return hp
 
 
+def unet_pass_traffic(B, lr):
+    """DRAM bytes of one Unet pass (dram__bytes_read.sum + dram__bytes_write.sum over its conv launches) from
+    the committed ncu launch list of this very command; only valid for the configuration it was captured on."""
+    p = os.path.join(ROOT, "profiles", "r01", "unet_pass_traffic.json")
+    if B == 64 and lr == 40 and os.path.isfile(p):
+        d = json.load(open(p))
+        return d["dram_bytes_read"] + d["dram_bytes_write"], "profiles/r01/unet_pass_traffic.json"
+    return None, None
+
+
 def measured_peaks():
     p = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.isfile(p):
@@ -267,6 +277,7 @@ def run_ours(args, hp):
     torch.cuda.synchronize()
     ms_unet = e0.elapsed_time(e1) / reps
     peaks = measured_peaks()
+    traffic, traffic_src = unet_pass_traffic(B, lr)
     flops_per_pass = GFLOP_UNET_STEP * (H * H / 25600.0) * B * 1e9
     achieved = flops_per_pass / (ms_unet / 1000.0) / 1e12
 
@@ -325,7 +336,9 @@ def run_ours(args, hp):
             "roofline": {"bound": "tensor", "kernel": "conv_tc_kernel (all %d tcgen05 conv launches of one Unet "
                                                       "pass; %d launches total per pass)" % (n_tc, n_ops),
                          "achieved": achieved, "peak": peaks["tflops"], "unit": "TFLOP/s",
-                         "frac": achieved / peaks["tflops"], "traffic": None,
+                         "frac": achieved / peaks["tflops"], "traffic": traffic, "traffic_unit": "bytes per Unet pass",
+                         "traffic_source": traffic_src,
+                         "algorithmic_bytes_per_pass": 78.3e6 * B * (H * H / 25600.0),
                          "peak_source": peaks["source"] + ", sustained bf16",
                          "flops_per_pass": flops_per_pass, "ms_per_pass": ms_unet},
             "roofline_p_sample": {"bound": "hbm", "achieved": ps_gbs, "peak": peaks["hbm_gbs"], "unit": "GB/s",
