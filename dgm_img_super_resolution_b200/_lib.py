@@ -81,6 +81,12 @@ SYMBOLS = {
     "srd_upsample_nearest2x": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp]),
     "srd_mish_f32": (C.c_int, [_vp, _vp, _i64, _vp]),
     "srd_res2img": (C.c_int, [_vp, _vp, _vp, _i64, _f, _i32, _i32, _vp]),
+    "srd_q_sample": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i64, _vp, _vp]),
+    "srd_axpby": (C.c_int, [_vp, _vp, _f, _f, _i64, _vp, _vp]),
+    "srd_bicubic_upsample": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "srd_u8hwc_to_nchw": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "srd_nchw_to_u8hwc": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "srd_tiles": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
 }
 
 _lib = None

@@ -456,6 +456,49 @@ class GaussianDiffusion(nn.Module):
         """:1127-1134"""
         return self._elementwise(x, img_lr_up, clip_input, 1)
 
+    def q_sample(self, x_start, t, noise=None):
+        """:1041-1048 forward diffusion of x_start to step t (per-sample t; t < 0 returns x_start)."""
+        E._require_cuda(x_start, "q_sample input")
+        x = x_start.contiguous().float()
+        noise = default(noise, lambda: torch.randn_like(x)).contiguous().float()
+        t32 = t.to(device=x.device, dtype=torch.int32).contiguous()
+        out = torch.empty_like(x)
+        L.check(L.lib().srd_q_sample(x.data_ptr(), noise.data_ptr(), self.sqrt_alphas_cumprod.data_ptr(),
+                                     self.sqrt_one_minus_alphas_cumprod.data_ptr(), t32.data_ptr(), x.shape[0],
+                                     x[0].numel(), out.data_ptr(), E._stream()), "srd_q_sample")
+        return out
+
+    @torch.no_grad()
+    def interpolate(self, x1, x2, img_lr, img_lr_up, t=None, lam=0.5):
+        """:1093-1116: diffuse x1 and x2 to step t, blend, and denoise from step t-1 down to 0."""
+        E._require_cuda(x1, "interpolate input")
+        if not hparams['use_rrdb']:
+            raise NotImplementedError("hparams['use_rrdb']=False is outside the hot path")
+        assert x1.shape == x2.shape
+        b = x1.shape[0]
+        device = x1.device
+        t = default(t, self.num_timesteps - 1)
+        B, _, h, w = img_lr.shape
+        plan = self._plan(B, h, w, device)
+        r1, r2 = self.img2res(x1, img_lr_up), self.img2res(x2, img_lr_up)
+        t_batched = torch.full((b,), int(t), device=device, dtype=torch.long)
+        xt1, xt2 = self.q_sample(r1, t=t_batched), self.q_sample(r2, t=t_batched)
+        L.check(L.lib().srd_axpby(xt1.data_ptr(), xt2.data_ptr(), float(1 - lam), float(lam), xt1.numel(),
+                                  plan.x.data_ptr(), E._stream()), "srd_axpby")
+        plan.img_lr.copy_(img_lr)
+        plan.img_lr_up.copy_(img_lr_up)
+        runtime.seed_counter += 1
+        seed = (torch.cuda.default_generators[device.index or 0].initial_seed() * 1000003 + runtime.seed_counter) \
+            & 0x7FFFFFFFFFFFFFFF
+        plan.seed_dev.fill_(seed)
+        plan.encode()
+        plan.load_x()
+        use_torch_noise = runtime.noise == "torch"
+        for k, i in enumerate(reversed(range(0, int(t)))):
+            noise = noise_like(plan.x.shape, device).contiguous().float() if use_torch_noise else None
+            plan.step(i, k, noise, seed, runtime.image_offset, fuse_img=False)
+        return self.res2img(plan.x.clone(), plan.img_lr_up)
+
     @torch.no_grad()
     def p_sample(self, x, t, cond, img_lr_up, noise_pred=None, clip_denoised=True, repeat_noise=False):
         """:1050-1060 stand-alone (arbitrary per-sample t).  Returns (x_prev, x0_pred)."""
@@ -476,8 +519,6 @@ class GaussianDiffusion(nn.Module):
         device = self.betas.device
         E._require_cuda(self.betas, "GaussianDiffusion")
         E._require_cuda(img_lr, "img_lr")
-        if not hparams['res']:
-            raise NotImplementedError("hparams['res']=False start (q_sample of img_lr_up) is a 'next' row (SURVEY 8f-2)")
         if not hparams['use_rrdb']:
             raise NotImplementedError("hparams['use_rrdb']=False is outside the hot path")
         b = shape[0]
@@ -493,15 +534,19 @@ class GaussianDiffusion(nn.Module):
         runtime.seed_counter += 1
         seed = (torch.cuda.default_generators[device.index or 0].initial_seed() * 1000003 + runtime.seed_counter) \
             & 0x7FFFFFFFFFFFFFFF
-        # ---- x_T :1070 (drawn before the RRDB forward, like the reference)
-        if use_torch_noise:
+        # ---- x_T :1066-1070 (drawn before the RRDB forward, like the reference)
+        res = bool(hparams['res'])
+        if not res:         # start from the diffused bicubic image :1066-1068; res2img is the identity then
+            t_last = torch.full((B,), T - 1, device=device, dtype=torch.long)
+            plan.x.copy_(self.q_sample(img_lr_up, t_last))
+        elif use_torch_noise:
             plan.x.copy_(torch.randn(shape, device=device))
         else:
             L.check(L.lib().srd_randn(plan.x.data_ptr(), B, plan.x[0].numel(), seed, 0, runtime.image_offset,
                                       E._stream()), "srd_randn")
         plan.img_lr.copy_(img_lr)
         plan.img_lr_up.copy_(img_lr_up)
-        eager = save_intermediate or not runtime.graph
+        eager = save_intermediate or not runtime.graph or not res
         images = []
         if use_torch_noise and not eager:
             nb = plan.ensure_noise_buf()
@@ -520,13 +565,13 @@ class GaussianDiffusion(nn.Module):
             x0 = torch.empty_like(plan.x) if save_intermediate else None
             for k, i in enumerate(it):
                 noise = noise_like(shape, device).contiguous().float() if use_torch_noise else None
-                plan.step(i, k, noise, seed, runtime.image_offset, x0_out=x0)
+                plan.step(i, k, noise, seed, runtime.image_offset, x0_out=x0, fuse_img=res)
                 if save_intermediate:
                     images.append((self.res2img(plan.x, plan.img_lr_up).cpu(),
                                    self.res2img(x0, plan.img_lr_up).cpu()))
         self.last_stats = {"gpu_launches": plan.n_launches(), "graph": not eager,
                            "noise": "torch" if use_torch_noise else "philox"}
-        img = plan.img.clone()
+        img = plan.img.clone() if res else plan.x.clone()
         rrdb_out = plan.rrdb_prog.out.clone()
         if save_intermediate:
             return img, rrdb_out, images

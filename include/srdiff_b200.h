@@ -185,6 +185,30 @@ int srd_mish_f32(const float* x, float* y, int64_t n, void* stream);
 int srd_res2img(const float* x, const float* img_lr_up, float* out, int64_t n,
                 float res_rescale, int32_t clip, int32_t inverse, void* stream);
 
+/* ---- SURVEY 8f "next" rows: the sampler's remaining arithmetic and the driver's image handling ---- */
+
+/* q_sample :1041-1048 on fp32 [B][chw]: out = (sqrt_ac[t]*x + sqrt_1m_ac[t]*noise) * [t >= 0] + x * [t < 0];
+ * sqrt_ac / sqrt_1m_ac are the GaussianDiffusion buffers sqrt_alphas_cumprod / sqrt_one_minus_alphas_cumprod,
+ * t: [B] int32. */
+int srd_q_sample(const float* x, const float* noise, const float* sqrt_ac, const float* sqrt_1m_ac,
+                 const int32_t* t, int32_t B, int64_t chw, float* out, void* stream);
+/* out = a*x + b*y on fp32 (interpolate() :1109). */
+int srd_axpby(const float* x, const float* y, float a, float b, int64_t n, float* out, void* stream);
+/* F.interpolate(mode='bicubic', align_corners=True) (st_app1.py:1593-1597) on BC planes of H x W -> Ho x Wo. */
+int srd_bicubic_upsample(const float* in, int32_t BC, int32_t H, int32_t W, int32_t Ho, int32_t Wo,
+                         float* out, void* stream);
+/* uint8 HWC [B][H][W][C] -> fp32 NCHW: (u/255 - mean[c]) / std[c] (ToTensor + Normalize, st_app1.py:1585-1589);
+ * mean == std == NULL: u/127.5 - 1. */
+int srd_u8hwc_to_nchw(const uint8_t* in, int32_t B, int32_t H, int32_t W, int32_t C, const float* mean,
+                      const float* stdv, float* out, void* stream);
+/* fp32 NCHW -> uint8 HWC: clamp(-1,1), (x+1)/2, clip(x*255, 0, 255), truncate (st_app1.py:1682-1684,1710-1711). */
+int srd_nchw_to_u8hwc(const float* in, int32_t B, int32_t C, int32_t H, int32_t W, uint8_t* out, void* stream);
+/* Tile split (to_tiles = 1) / ImgMerger-style merge (to_tiles = 0, srdiff/model.py:133-145) between
+ * image [n][C][nx*th][ny*tw] and tiles [n][nx*ny][C][th][tw] (tile (x, y) at index x*ny + y covers rows
+ * [x*th, +th), cols [y*tw, +tw)). */
+int srd_tiles(const float* src, float* dst, int32_t n, int32_t C, int32_t nx, int32_t ny, int32_t th,
+              int32_t tw, int32_t to_tiles, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -267,6 +267,81 @@ def sample(sd, sched, hp, img_lr, img_lr_up, noises, record=None):
     return res2img(x, img_lr_up, hp), rrdb_out
 
 
+
+# ----------------------------------------------------------------------------- SURVEY 8f "next" rows
+def img2res(x, img_lr_up, hp, clip_input=None):
+    """`img2res` :1127-1134."""
+    if clip_input is None:
+        clip_input = hp["clip_input"]
+    if hp["res"]:
+        x = (x - img_lr_up) * hp["res_rescale"]
+        if clip_input:
+            x = x.clamp(-1, 1)
+    return x
+
+
+def q_sample(sched, x_start, t, noise):
+    """`q_sample` :1041-1048 (t < 0 returns x_start)."""
+    nd = x_start.dim()
+    t_cond = (t[:, None, None, None] >= 0).float()
+    tc = t.clamp_min(0)
+    return (_ext(sched["sqrt_alphas_cumprod"], tc, nd) * x_start +
+            _ext(sched["sqrt_one_minus_alphas_cumprod"], tc, nd) * noise) * t_cond + x_start * (1 - t_cond)
+
+
+def interpolate(sd, sched, hp, x1, x2, img_lr, img_lr_up, noises, t, lam):
+    """`interpolate` :1093-1116; noises[0:2] feed the two q_sample calls, noises[2 + k] the k-th p_sample."""
+    b = x1.shape[0]
+    _, cond = rrdb_forward(sd, img_lr, hp)
+    r1, r2 = img2res(x1, img_lr_up, hp), img2res(x2, img_lr_up, hp)
+    tb = torch.full((b,), t, dtype=torch.long)
+    xt1, xt2 = q_sample(sched, r1, tb, noises[0]), q_sample(sched, r2, tb, noises[1])
+    x = (1 - lam) * xt1 + lam * xt2
+    for k, i in enumerate(reversed(range(0, t))):
+        ti = torch.full((b,), i, dtype=torch.long)
+        x, _ = p_sample_update(sched, x, ti, unet_forward(sd, x, ti, cond, hp), noises[2 + k])
+    return res2img(x, img_lr_up, hp)
+
+
+def sample_nores(sd, sched, hp, img_lr, img_lr_up, noises):
+    """`sample` :1062-1091 with hparams['res'] = False: start = q_sample(img_lr_up, T-1) :1066-1068."""
+    T = sched["betas"].shape[0]
+    b = img_lr.shape[0]
+    x = q_sample(sched, img_lr_up, torch.full((b,), T - 1, dtype=torch.long), noises[0])
+    rrdb_out, cond = rrdb_forward(sd, img_lr, hp)
+    for k, i in enumerate(reversed(range(T))):
+        t = torch.full((b,), i, dtype=torch.long)
+        x, _ = p_sample_update(sched, x, t, unet_forward(sd, x, t, cond, hp), noises[1 + k])
+    return res2img(x, img_lr_up, hp), rrdb_out
+
+
+def bicubic_up(x, scale):
+    """`upsample_tensor` st_app1.py:1593-1597 (the same third-party ATen op the reference calls)."""
+    return F.interpolate(x, scale_factor=scale, mode="bicubic", align_corners=True)
+
+
+def merge_tiles(tiles, nx, ny):
+    """`ImgMerger.compute` :133-145 for one image list: tiles[x*ny + y] is [C, th, tw]."""
+    rows = [np.concatenate([tiles[x * ny + y] for y in range(ny)], 2) for x in range(nx)]
+    return np.concatenate(rows, 1)
+
+
+def to_uint8_hwc(img):
+    """st_app1.py:1682-1684, 1710-1711 for a batch [B, C, H, W] in [-1, 1] -> uint8 [B, H, W, C]."""
+    v = (img.clamp(-1, 1) + 1) / 2
+    return torch.from_numpy(np.clip(v.permute(0, 2, 3, 1).numpy() * 255, 0, 255).astype(np.uint8))
+
+
+def normalize_u8(u8_hwc, mean=None, std=None):
+    """ToTensor + Normalize, st_app1.py:1585-1589 ([B, H, W, C] uint8 -> [B, C, H, W] float); without
+    mean/std the [-1, 1] convention u / 127.5 - 1 of srdiff/model.py:95."""
+    x = u8_hwc.permute(0, 3, 1, 2).float()
+    if mean is None:
+        return x / 127.5 - 1
+    m = torch.tensor(mean, dtype=torch.float32).view(1, -1, 1, 1)
+    s_ = torch.tensor(std, dtype=torch.float32).view(1, -1, 1, 1)
+    return (x / 255.0 - m) / s_
+
 # ----------------------------------------------------------------------------- helpers for tests / bench
 def rel_l2(a, b):
     a = a.double().flatten()
