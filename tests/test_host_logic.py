@@ -43,6 +43,31 @@ def test_pack_conv_layouts(cins, O, k, stride, reflect):
     assert wt.shape[-2] % 16 == 0 and wt.shape[-1] == 64 and wt.dtype == torch.bfloat16
 
 
+def test_pack_conv_win8_windows():
+    """SRD_SRC_WIN8: the first Unet conv as three K=64 blocks over 8-pixel windows of the 8-channel buffer
+    (K index = dx*8 + c; the window of the last pixels of a row runs into the next row on zero weights)."""
+    from dgm_img_super_resolution_b200 import engine as E
+    torch.manual_seed(1)
+    x = torch.randn(2, 3, 8, 16)
+    w = torch.randn(64, 3, 3, 3) * 0.2
+    want = F.conv2d(F.pad(x, (1, 1, 1, 1), mode="reflect"), w)
+    wt = E._pack_conv_win8(w).float()                                   # [3 ky][Npad][64]
+    assert wt.shape == (3, 64, 64)
+    xp = EM.to_padded_nhwc(x, True)                                     # [B][H+2][W+2][3] -> pad channels to 8
+    B, Hp, Wp, _ = xp.shape
+    buf = torch.zeros(B, Hp, Wp, 8)
+    buf[..., :3] = xp
+    flat = torch.cat([buf.reshape(-1), torch.zeros(64)])                # + the slack the engine allocates
+    out = torch.zeros(B, 64, 8, 16)
+    for b in range(B):
+        for y in range(8):
+            for xx in range(16):
+                for ky in range(3):
+                    o = ((b * Hp + y + ky) * Wp + xx) * 8               # window starts at the tap's column
+                    out[b, :, y, xx] += wt[ky] @ flat[o:o + 64]
+    assert torch.allclose(out, want, atol=0.08, rtol=0.02)              # weights rounded to bf16
+
+
 @pytest.mark.parametrize("cins,O,S", [([64], 64, 2), ([192], 40, 2), ([32, 32, 32], 64, 4), ([70, 26], 16, 4)])
 def test_pack_conv_transpose_phases(cins, O, S):
     from dgm_img_super_resolution_b200 import engine as E
