@@ -279,7 +279,19 @@ __device__ __forceinline__ bool elect_one_sync() {
 // Debug timeline (tools/timeline_conv.py); compiled in only with -DSRD_TC_DEBUG so the role loops
 // of the product build carry no extra code.
 __device__ __forceinline__ void dbg_stamp(const TcArgs& a, int item_local, int ev) {
-#ifdef SRD_TC_DEBUG
+#if defined(SRD_TC_DEBUG) && SRD_TC_DEBUG != 2
+  if (a.dbg && item_local < DBG_ITEMS)
+    a.dbg[((size_t)blockIdx.x * DBG_ITEMS + item_local) * 8 + ev] = (unsigned long long)clock64();
+#else
+  (void)a; (void)item_local; (void)ev;
+#endif
+}
+
+// -DSRD_TC_DEBUG=2: the eight stamps of an item describe ONE epilogue warp (quarter 0 of the item's group):
+// 0 loop top, 1 T_full acquired, 2 staging buffer ready, 3 chunk loop done, 4 proxy fence done,
+// 5 TMA store(s) issued, 6 store read drained, 7 next buffer prepared.
+__device__ __forceinline__ void epi_stamp(const TcArgs& a, int item_local, int ev) {
+#if defined(SRD_TC_DEBUG) && SRD_TC_DEBUG == 2
   if (a.dbg && item_local < DBG_ITEMS)
     a.dbg[((size_t)blockIdx.x * DBG_ITEMS + item_local) * 8 + ev] = (unsigned long long)clock64();
 #else
@@ -711,8 +723,11 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     const int t0 = (item - phase * a.items_per_phase) * (a.MT * CG) + pid.rank;
     int pr = 0, ps = 0;                                          // sub-pixel phase of a transposed conv
     if (S > 1) { pr = fdiv(phase, a.fd_up); ps = phase - pr * S; }
+    const bool stamp = (quarter == 0 && lane == 0);
+    if (stamp) epi_stamp(a, it, 0);
     mbar_wait(t_full, round & 1u, a.err_flag, 6);
     tc_fence_after();
+    if (stamp) epi_stamp(a, it, 1);
     if (quarter == 0 && lane == 0) dbg_stamp(a, it, 5);
     bool released = false;
     int mt_cur = -1;
@@ -748,6 +763,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
         const uint32_t buf = k & nbuf_mask;
         uint8_t* row = my_row + buf * 4096u;
         mbar_wait(sg.r_full0 + 8u * buf, (k >> nbuf_sh) & 1u, a.err_flag, 8);   // buffer free / residual landed
+        if (stamp && qq == share) epi_stamp(a, it, 2);
         const bool last_sub = (qq + a.n_share >= n_sub);
         // Compact hot loop (one 16-channel chunk per iteration, NOT unrolled: the body must stay
         // resident in the instruction cache; rare ring / second-residual work lives outside).
@@ -845,8 +861,10 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
             if (bot && rig) *(p + (2 * dn + 2 * ct) / 8) = val;
           }
         }
+        if (stamp && last_sub) epi_stamp(a, it, 3);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
         __syncwarp();
+        if (stamp && last_sub) epi_stamp(a, it, 4);
         if (lane == 0) {
           const uint32_t src = sg.base + buf * 4096u;
           const int V0 = tg.V0 + g0, xc = tg.x0 + 1;               // this warp's 4 rows
@@ -877,6 +895,14 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
             // stride-2 conv / 2x transposed-conv phase: every tile row maps to its own output row
             const int Cc = tg.x0 * S + ps + 1;                     // first padded output column (step S)
             const int hp2 = (Ho + 2) >> 1;
+            // common case: the warp's four tile rows are four consecutive valid rows of one image that own no
+            // mirrored ring row -> ONE 4-row store (output rows are consecutive in the row / row-pair dimension)
+            const int bb0 = fdiv(V0, a.fd_period), y0 = V0 - bb0 * a.period - a.voff;
+            const int oy0 = y0 * S + pr, oy3 = (y0 + 3) * S + pr;
+            if (y0 >= 0 && y0 + 3 < a.H_m && V0 + 3 < a.n_vrows && (!reflect || (oy0 > 1 && oy3 < Ho - 2))) {
+              if (S == 1) tma_store_3d(&a.tmO, src, j * 64, xc, bb0 * (Ho + 2) + oy0 + 1);
+              else tma_store_5d(&a.tmO, src, j * 64, Cc & 1, Cc >> 1, (oy0 + 1) & 1, bb0 * hp2 + ((oy0 + 1) >> 1));
+            } else
             for (int gg = 0; gg < 4; ++gg) {
               const int V = V0 + gg;
               if (V >= a.n_vrows) break;
@@ -897,10 +923,13 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
             }
           }
           asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+          if (stamp && last_sub) epi_stamp(a, it, 5);
           // the buffer of sub-tile k+1 was last read by the store of sub-tile k+1-nbuf
           if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (stamp && last_sub) epi_stamp(a, it, 6);
           prepare(k + 1, it, qq + a.n_share);
+          if (stamp && last_sub) epi_stamp(a, it, 7);
         }
         __syncwarp();
       }
@@ -1543,20 +1572,20 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
     // 2x transposed conv: [c][col parity][col pair][row parity][row pair]; one phase writes one parity
     // plane.  The right ring column shares its pair with the last real column, so it cannot be clipped
     // away here: this map is only used when W_m % 8 == 0 (no ragged column tile).
-    auto enc_out5 = [&](CUtensorMap* tm, const void* ptr, int ct, int coff) {
+    auto enc_out5 = [&](CUtensorMap* tm, const void* ptr, int ct, int coff, int rows) {
       void* base = (void*)((const __nv_bfloat16*)ptr + coff);
       cuuint64_t dims[5] = {(cuuint64_t)d.N, 2, (cuuint64_t)Wop / 2, 2, (cuuint64_t)d.B * Hop / 2};
       cuuint64_t strides[4] = {(cuuint64_t)ct * 2, (cuuint64_t)2 * ct * 2, (cuuint64_t)Wop * ct * 2,
                                (cuuint64_t)2 * Wop * ct * 2};
-      cuuint32_t box[5] = {64, 1, TILE_W, 1, 1};
+      cuuint32_t box[5] = {64, 1, TILE_W, 1, (cuuint32_t)rows};
       cuuint32_t es[5] = {1, 1, 1, 1, 1};
       return enc(tm, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es, CU_TENSOR_MAP_INTERLEAVE_NONE,
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
     SRD_CHECK(((uintptr_t)d.out % 16) == 0, "conv_tc: out must be 16-byte aligned");
-    CUresult r = enc_out(&a.tmO, d.out, d.out_ct, d.out_coff, 4);
+    CUresult r = (d.up == 2) ? enc_out5(&a.tmO, d.out, d.out_ct, d.out_coff, 4) : enc_out(&a.tmO, d.out, d.out_ct, d.out_coff, 4);
     SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
-    r = (d.up == 2) ? enc_out5(&a.tmOrow, d.out, d.out_ct, d.out_coff) : enc_out(&a.tmOrow, d.out, d.out_ct, d.out_coff, 1);
+    r = (d.up == 2) ? enc_out5(&a.tmOrow, d.out, d.out_ct, d.out_coff, 1) : enc_out(&a.tmOrow, d.out, d.out_ct, d.out_coff, 1);
     SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(out row) failed with %d", (int)r);
     if (d.res1) {
       r = enc_out(&a.tmR, d.res1, d.res1_ct, d.res1_coff, 4);
