@@ -1270,7 +1270,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       const int taps = a.a_mode ? a.nkx * a.nky : 0;
 #define SRD_MMA_CASE(T)                                                                      \
   do {                                                                                       \
-    if (a.b_resident) mma_role<T, 1, true, CG>(a, tmem_base, a_base, b_base, bar_base);      \
+    if (a.b_resident && a.MT == 2) mma_role<T, 2, true, CG>(a, tmem_base, a_base, b_base, bar_base); \
+    else if (a.b_resident) mma_role<T, 1, true, CG>(a, tmem_base, a_base, b_base, bar_base); \
     else if (a.MT == 2) mma_role<T, 2, false, CG>(a, tmem_base, a_base, b_base, bar_base);   \
     else mma_role<T, 1, false, CG>(a, tmem_base, a_base, b_base, bar_base);                  \
   } while (0)
@@ -1339,6 +1340,7 @@ static int g_b_resident = 1;
 static int g_epi_tma = 1;
 static int g_cg = 2;                     // CTAs per MMA: 2 = cta_group::2 pairs (default), 1 = single-CTA MMAs
 static int g_pdl = 1;                    // programmatic dependent launch of consecutive conv layers
+static int g_res_mt2 = 1;                // MT = 2 also with resident weights
 static unsigned long long* g_dbg = nullptr;
 void tc_set_debug(unsigned long long* p) { g_dbg = p; }
 void tc_set_mode(int a_mode, int b_resident) {
@@ -1346,6 +1348,7 @@ void tc_set_mode(int a_mode, int b_resident) {
   g_epi_tma = (a_mode & 2) ? 0 : 1;      // bit 1 of a_mode disables the TMA-staged epilogue
   g_cg = (a_mode & 4) ? 1 : 2;           // bit 2 of a_mode: single-CTA MMAs instead of CTA pairs
   g_pdl = (a_mode & 8) ? 0 : 1;          // bit 3 of a_mode: no programmatic dependent launch
+  g_res_mt2 = (a_mode & 16) ? 0 : 1;     // bit 4 of a_mode: resident weights always with MT = 1
   g_b_resident = b_resident;
 }
 
@@ -1440,9 +1443,12 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   // for rings MT = 2 (each weight tile shared by two M tiles) before MT = 1.
   for (int nbuf = a.epi_tma ? nbuf_max : 0; !planned; --nbuf) {
     const int stg = EPI_WARPS * nbuf * 4096;
-    for (int pass = 0; pass < 3 && !planned; ++pass) {
-      const bool resident = (pass == 0);
-      const int MT = resident ? 1 : (pass == 1 ? 2 : 1);
+    // passes: resident weights with MT = 2 (large layers: per-item overheads of the MMA thread and of the
+    // epilogue hand-over amortise over twice the work), resident MT = 1, ring MT = 2, ring MT = 1
+    for (int pass = -1; pass < 3 && !planned; ++pass) {
+      const bool resident = (pass <= 0);
+      const int MT = (pass == -1 || pass == 1) ? 2 : 1;
+      if (pass == -1 && !(g_res_mt2 && 4 * 2 * a.Npad <= 512 && n_tiles_all >= 16LL * n_sm)) continue;
       if (resident && !(g_b_resident && res_bytes < (1 << 20))) continue;
       if (pass == 1 && !mt2_ok) continue;
       const int sb = MT * a.a_stage_bytes;
