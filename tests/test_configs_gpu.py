@@ -1,0 +1,89 @@
+"""GPU tests at the shapes of BASELINE.json's other configurations (parity-test cases, not bench lines).
+At these sizes the CPU oracle is too slow, so parity is transitive: the tcgen05 bf16 path must agree with
+this build's fp32 direct-kernel path (itself pinned to the reference at small shapes, test_gpu_kernels.py)
+within the north_star tolerance, plus size-independent properties (determinism, batch / shard invariance,
+tiling = batching)."""
+import pytest
+import torch
+
+from conftest import build_ours, gen_inputs
+from oracle import srdiff_oracle as O
+
+DEV = "cuda:0"
+pytestmark = pytest.mark.gpu
+
+
+def _eps_both(M, diff, B, h, w, hp, seed):
+    img_lr, img_lr_up, g = gen_inputs(B, h, w, hp["sr_scale"], seed)
+    x = torch.randn((B, 3, h * 4, w * 4), generator=g)
+    t = torch.randint(0, diff.num_timesteps, (B,), generator=g)
+    out = {}
+    for prec in ("fp32", "bf16"):
+        M.runtime.precision = prec
+        _, feas = diff.rrdb(img_lr.to(DEV), True)
+        out[prec] = diff.denoise_fn(x.to(DEV), t.to(DEV), feas, img_lr_up.to(DEV)).cpu()
+    M.runtime.precision = "bf16"
+    return out
+
+
+def test_config2_whole_256_image_one_denoiser_call(hp):
+    """configs[2](i): one 256x256 LR image as a whole -> 1024x1024 (what st_app1 does), B = 1."""
+    M, diff = build_ours(hp, device=DEV)
+    out = _eps_both(M, diff, 1, 256, 256, hp, 3)
+    assert out["bf16"].shape == (1, 3, 1024, 1024) and torch.isfinite(out["bf16"]).all()
+    assert O.rel_l2(out["bf16"], out["fp32"]) < 1e-2
+
+
+def test_config1_and_4_batch_shapes(hp):
+    """configs[1]/[3] shape (40x40 -> 160x160) at a reduced batch that still spans several item rounds,
+    plus batch invariance: image k of a batch == the same image alone."""
+    M, diff = build_ours(hp, device=DEV)
+    out = _eps_both(M, diff, 6, 40, 40, hp, 4)
+    assert O.rel_l2(out["bf16"], out["fp32"]) < 1e-2
+    img_lr, img_lr_up, g = gen_inputs(6, 40, 40, hp["sr_scale"], 4)
+    x = torch.randn((6, 3, 160, 160), generator=g)
+    t = torch.randint(0, diff.num_timesteps, (6,), generator=g)
+    _, feas = diff.rrdb(img_lr[4:5].to(DEV), True)
+    one = diff.denoise_fn(x[4:5].to(DEV), t[4:5].to(DEV), feas, img_lr_up[4:5].to(DEV)).cpu()
+    assert torch.equal(one[0], out["bf16"][4])
+
+
+@pytest.mark.parametrize("T", [25, 1000])
+def test_config4_timestep_sweep_graph_loop(hp, T):
+    """configs[4]: 64x64 LR patches, long and short schedules through the CUDA-graph loop (reduced batch)."""
+    M, diff = build_ours(hp, timesteps=T, device=DEV)
+    M.runtime.noise, M.runtime.precision, M.runtime.graph = "philox", "bf16", True
+    try:
+        img_lr, img_lr_up, _ = gen_inputs(2, 64, 64, hp["sr_scale"], 6)
+        M.runtime.seed_counter = 100
+        img, rrdb_out = diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
+        assert img.shape == (2, 3, 256, 256) and torch.isfinite(img).all()
+        assert diff.last_stats["graph"] and diff.last_stats["gpu_launches"] > 45 * T
+        M.runtime.seed_counter = 100                    # same seed -> bit-identical replay of the captured graph
+        img2, _ = diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
+        assert torch.equal(img, img2)
+        if T == 25:                                     # eager loop == graph loop, bit for bit
+            M.runtime.graph = False
+            M.runtime.seed_counter = 100
+            img3, _ = diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
+            assert torch.equal(img, img3)
+    finally:
+        M.runtime.noise, M.runtime.graph = "torch", True
+
+
+def test_smallest_and_ragged_inputs(hp):
+    """Edge cases: the smallest LR size the reference admits (4x4 -> 16x16: the lowest Unet level is 2x2, the
+    minimum of ReflectionPad2d(1)), batch 1, ragged widths; smaller or indivisible sizes raise as upstream."""
+    M, diff = build_ours(hp, timesteps=2, device=DEV)
+    M.runtime.noise = "philox"
+    try:
+        for (B, h, w) in ((1, 4, 4), (1, 4, 6), (3, 10, 4)):
+            img_lr, img_lr_up, _ = gen_inputs(B, h, w, hp["sr_scale"], 8)
+            img, rrdb_out = diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
+            assert img.shape == (B, 3, 4 * h, 4 * w) and torch.isfinite(img).all() and torch.isfinite(rrdb_out).all()
+        for (h, w) in ((3, 3), (2, 2)):        # 12x12 is not divisible by 8; 8x8 reaches a 1x1 level (reflect pad)
+            with pytest.raises(Exception):
+                img_lr, img_lr_up, _ = gen_inputs(1, h, w, hp["sr_scale"], 8)
+                diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
+    finally:
+        M.runtime.noise = "torch"
