@@ -1341,6 +1341,7 @@ static int g_epi_tma = 1;
 static int g_cg = 2;                     // CTAs per MMA: 2 = cta_group::2 pairs (default), 1 = single-CTA MMAs
 static int g_pdl = 1;                    // programmatic dependent launch of consecutive conv layers
 static int g_res_mt2 = 1;                // MT = 2 also with resident weights
+static int g_small_mt2 = 0;              // MT = 2 with a single TMEM stage on small, wide layers (measured slower: off)
 static unsigned long long* g_dbg = nullptr;
 void tc_set_debug(unsigned long long* p) { g_dbg = p; }
 void tc_set_mode(int a_mode, int b_resident) {
@@ -1349,6 +1350,7 @@ void tc_set_mode(int a_mode, int b_resident) {
   g_cg = (a_mode & 4) ? 1 : 2;           // bit 2 of a_mode: single-CTA MMAs instead of CTA pairs
   g_pdl = (a_mode & 8) ? 0 : 1;          // bit 3 of a_mode: no programmatic dependent launch
   g_res_mt2 = (a_mode & 16) ? 0 : 1;     // bit 4 of a_mode: resident weights always with MT = 1
+  g_small_mt2 = (a_mode & 32) ? 1 : 0;   // bit 5 of a_mode: trade the second TMEM stage for MT = 2 on small, wide layers
   g_b_resident = b_resident;
 }
 
@@ -1435,7 +1437,13 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   a.a_stage_bytes = a.a_mode ? A_HALO_STAGE : A_BYTES;
   const long long res_bytes = (long long)a.kb_total * B_BYTES;
   const long long n_tiles_all = (long long)n_phase * a.tiles_per_phase;
-  const bool mt2_ok = (2 * 2 * a.Npad <= 512) && n_tiles_all >= 2LL * n_sm;
+  // MT = 2 halves the weight traffic of an item (two M tiles share every weight k-block).  Normally it needs
+  // two TMEM stages (2 x 2 x Npad <= 512 columns) and enough tiles for every SM; small layers (at most ~2
+  // item rounds, e.g. the 20x20 level) also take it with ONE stage: they are bound by streaming the whole
+  // weight tensor from L2 once per item, and with one round there is no next item to overlap with anyway.
+  const bool small_wide = g_small_mt2 && (2 * a.Npad <= 512) && (2 * 2 * a.Npad > 512) &&
+                          n_tiles_all >= n_sm && n_tiles_all <= 2LL * n_sm;
+  const bool mt2_ok = ((2 * 2 * a.Npad <= 512) && n_tiles_all >= 2LL * n_sm) || small_wide;
   const int nbuf_max = EPI_WARPS <= 8 ? 2 : 1;   // 4 KB staging buffers per epilogue warp
   bool planned = false;
   int b_bytes_total = 0, stage_bytes = 0;
@@ -1500,8 +1508,8 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   // TMEM accumulator stages, and how the epilogue groups are dealt: with >= 3 (2) sub-tiles per item all
   // (two) groups split one item, so an accumulator stage is drained -- and free for the next MMAs -- in
   // the time of ONE sub-tile; otherwise every group drains its own item.
-  a.n_stages = (EPI_GROUPS >= 4 && 4 * a.MT * a.Npad <= 512) ? 4 : 2;
-  a.stage_shift = a.n_stages == 4 ? 2 : 1;
+  a.n_stages = (EPI_GROUPS >= 4 && 4 * a.MT * a.Npad <= 512) ? 4 : (2 * a.MT * a.Npad <= 512 ? 2 : 1);
+  a.stage_shift = a.n_stages == 4 ? 2 : (a.n_stages == 2 ? 1 : 0);
   {
     const int n_sub = a.MT * ((a.Npad + 63) / 64);
     int share = d.head_w ? 1 : (n_sub >= 3 ? 4 : n_sub);

@@ -124,6 +124,7 @@ int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream);
  *        bit 2: single-CTA MMAs (cta_group::1) instead of CTA pairs (cta_group::2, M = 256).
  *        bit 3: no programmatic dependent launch between consecutive conv layers.
  *        bit 4: resident weights always with one M tile per CTA and item (MT = 1).
+ *        bit 5: give up the second TMEM accumulator stage for MT = 2 on small, wide layers (measured slower).
  * b_resident: keep all weight k-blocks in shared memory when they fit. */
 int srd_tc_set_mode(int32_t a_mode, int32_t b_resident);
 /* Debug: plans created afterwards record per-item clock64 stamps into buf [grid][64][8] (NULL = off). */
