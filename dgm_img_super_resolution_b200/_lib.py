@@ -41,6 +41,8 @@ class SrdConvDesc(C.Structure):
         ("planar", C.c_void_p), ("planar_c", C.c_int32), ("planar_clamp01", C.c_int32),
         ("head_w", C.c_void_p), ("head_b", C.c_void_p),
         ("lin_src", C.c_void_p), ("lin_ct", C.c_int32), ("lin_c", C.c_int32), ("lin_w", C.c_void_p),
+        ("N2", C.c_int32), ("dst2_ct", C.c_int32), ("dst2_coff", C.c_int32), ("reserved2", C.c_int32),
+        ("bias2", C.c_void_p), ("dst2", C.c_void_p),
     ]
 
 
@@ -109,7 +111,7 @@ def lib():
             fn = getattr(L, name)
             fn.restype = res
             fn.argtypes = args
-        abi = (C.sizeof(SrdConvDesc), C.sizeof(SrdPSampleArgs), SrdConvDesc.lin_w.offset,
+        abi = (C.sizeof(SrdConvDesc), C.sizeof(SrdPSampleArgs), SrdConvDesc.dst2.offset,
                SrdPSampleArgs.seed_ptr.offset)
         got = tuple(L.srd_abi_sizeof(i) for i in range(4))
         if abi != got:

@@ -84,6 +84,8 @@ static int validate(const SrdConvDesc& d) {
   SRD_CHECK(!d.res2 || (d.res2_coff + d.N <= d.res2_ct), "conv: res2 channel window outside res2_ct");
   SRD_CHECK(!d.planar || d.planar_c > 0, "conv: planar_c must be positive");
   SRD_CHECK(!d.head_w || (d.head_b && d.planar), "conv: fused head needs head_b and planar");
+  SRD_CHECK(d.N2 == 0 || (d.N2 == d.N && d.bias2 && d.dst2 && d.dst2_coff >= 0 && d.dst2_coff + d.N2 <= d.dst2_ct),
+            "conv: second output needs N2 == N, bias2 and a dst2 channel window inside dst2_ct");
   SRD_CHECK(!d.lin_src || (d.lin_w && d.lin_c >= 1 && d.lin_c <= 4 && d.lin_c <= d.lin_ct),
             "conv: linear residual needs lin_w and 1 <= lin_c <= min(4, lin_ct)");
   return 0;
@@ -99,7 +101,7 @@ int srd_abi_sizeof(int32_t which) {
   switch (which) {
     case 0: return (int)sizeof(SrdConvDesc);
     case 1: return (int)sizeof(SrdPSampleArgs);
-    case 2: return (int)offsetof(SrdConvDesc, lin_w);
+    case 2: return (int)offsetof(SrdConvDesc, dst2);
     case 3: return (int)offsetof(SrdPSampleArgs, seed_ptr);
     default: return -1;
   }
@@ -130,6 +132,7 @@ int srd_conv_plan_create(const SrdConvDesc* desc, SrdConvPlan** out_plan) {
     if (!desc->w_direct) { delete p; SRD_CHECK(false, "srd_conv_plan_create: direct kernel needs w_direct"); }
     if (desc->head_w) { delete p; SRD_CHECK(false, "srd_conv_plan_create: fused head needs the tc kernel"); }
     if (desc->lin_src) { delete p; SRD_CHECK(false, "srd_conv_plan_create: linear residual needs the tc kernel"); }
+    if (desc->N2) { delete p; SRD_CHECK(false, "srd_conv_plan_create: the second output needs the tc kernel"); }
     for (int i = 0; i < desc->n_src; ++i)
       if (desc->src[i].flags & SRD_SRC_WIN8) { delete p; SRD_CHECK(false, "srd_conv_plan_create: SRD_SRC_WIN8 needs the tc kernel"); }
   }

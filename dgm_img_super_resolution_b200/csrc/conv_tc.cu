@@ -77,6 +77,7 @@ struct TcArgs {
   CUtensorMap tmO;         // output, box {64 ch, 8 px, 4 rows} = one epilogue warp's rows (TMA-staged epilogue)
   CUtensorMap tmOrow;      // output, box {64 ch, 8 px, 1 row}
   CUtensorMap tmR;         // residual res1, box {64 ch, 8 px, 4 rows}
+  CUtensorMap tmO2;        // second output (dual), box {64 ch, 8 px, 4 rows}
   int n_src;
   int nchunk[SRD_MAX_SRC];
   int H_m, W_m;            // output positions per image (per phase)
@@ -84,6 +85,9 @@ struct TcArgs {
   int n_colblk, tiles_per_phase, items_per_phase, n_items;
   FastDiv fd_ipp, fd_colblk, fd_period, fd_up;   // dividers by items_per_phase, n_colblk, period, up
   int n_chunks;            // 64-channel K chunks per item over all sources
+  int dual;                // 1: second output = 1x1 conv of the same sources (SrdConvDesc.N2): its accumulator sits
+                           //    MT*Npad columns after the first one, its weights are the 10th k-block of every chunk
+  const float* bias2;
   int cg;                  // CTAs per MMA (1, or 2 = cta_group::2 pair: M = 256, each CTA holds half of every weight tile)
   int stride, nky, nkx, ky0, kx0, up;
   int Npad, MT;
@@ -679,7 +683,9 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   const int m = quarter * 32 + lane;
   const int g = m >> 3, px = m & 7;
   const int nsj = a.Npad >> 6;                   // 64-channel sub-tiles per tile
-  const int n_sub = a.MT * nsj;                  // sub-tiles per item
+  const int n_sub1 = a.MT * nsj;                 // sub-tiles of the (first) output per item
+  const int n_sub = n_sub1 * (1 + a.dual);       // + those of the second output (dual)
+  const int stage_cols = a.MT * a.Npad * (1 + a.dual);
   const int nbuf = a.epi_nbuf;
   const int Ho = a.ep.H_out, Wo = a.ep.W_out;
   const bool reflect = (a.ep.border == SRD_BORDER_REFLECT);
@@ -697,6 +703,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     if (qn >= n_sub) return;                                   // this group never has a sub-tile
     const int item = pid.pair + itn * pid.n_pairs;
     if (item >= a.n_items) return;
+    if (qn >= n_sub1) qn -= n_sub1;                            // second output: same tiles again
     const int mt = (qn >= nsj) ? 1 : 0, j = qn - mt * nsj;     // MT <= 2
     const int ph = fdiv(item, a.fd_ipp);
     const int tt = (item - ph * a.items_per_phase) * (a.MT * CG) + mt * CG + pid.rank;
@@ -740,8 +747,10 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     float lin[4] = {0.f, 0.f, 0.f, 0.f};                         // this pixel's linear-residual inputs
     {
       for (int qq = share; qq < n_sub; qq += a.n_share, ++k) {
-        const int mt = (qq >= nsj) ? 1 : 0, j = qq - mt * nsj;
-        if (mt != mt_cur) {
+        const int which = (qq >= n_sub1) ? 1 : 0;                // 0: conv output, 1: second (1x1) output
+        const int q1 = qq - which * n_sub1;
+        const int mt = (q1 >= nsj) ? 1 : 0, j = q1 - mt * nsj;
+        if (mt != mt_cur || which) {
           mt_cur = mt;
           tg = tile_geo(a, t0 + mt * CG, g, px);
           valid = tg.valid;
@@ -752,7 +761,9 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
             edge = (oy == 1 ? 1u : 0u) | (oy == Ho - 2 ? 2u : 0u) | (ox == 1 ? 4u : 0u) | (ox == Wo - 2 ? 8u : 0u);
           outp = static_cast<__nv_bfloat16*>(a.ep.out) + pix * a.ep.out_ct + a.ep.out_coff;
           r2p = (a.ep.res2 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
-          tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((stage * a.MT + mt) * a.Npad);
+          tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) +
+                  (uint32_t)(stage * stage_cols + which * n_sub1 * 64 + mt * a.Npad);
+          if (which) { edge = 0; r2p = nullptr; mt_cur = -1; }     // plain output: no ring mirrors, no residuals
           if (es.lin_w) {
             uint2 xv = make_uint2(0u, 0u);                         // 4 bf16 channels of the pixel (buffers have ct % 8 == 0)
             if (valid) xv = *reinterpret_cast<const uint2*>(a.lin_src + pix * a.lin_ct);
@@ -770,12 +781,13 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           const int c0 = j * 64 + cc * 16;
+          const int cb = c0 + which * a.Npad;                    // bias2 / zero temb are staged after bias / temb
           uint32_t r[16];
           tc_ld16(tbase + (uint32_t)c0, r);
           uint4* s0 = reinterpret_cast<uint4*>(row + (((uint32_t)(2 * cc) ^ swz) << 4));
           uint4* s1 = reinterpret_cast<uint4*>(row + (((uint32_t)(2 * cc + 1) ^ swz) << 4));
-          const float4* sb = reinterpret_cast<const float4*>(es.bias + c0);
-          const float4* st = reinterpret_cast<const float4*>(es.temb + c0);
+          const float4* sb = reinterpret_cast<const float4*>(es.bias + cb);
+          const float4* st = reinterpret_cast<const float4*>(es.temb + cb);
           const float alpha = a.ep.alpha;
           tc_ld_wait();
           if (last_sub && cc == 3) {                             // accumulator fully read: release the TMEM stage
@@ -786,13 +798,22 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
             released = true;
           }
           float v[16];
+          if (which) {                                           // second output: bias only
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float4 b4 = sb[q], t4 = st[q];
-            v[4 * q + 0] = act_axpy<ACT>(__uint_as_float(r[4 * q + 0]) + b4.x, alpha, t4.x);
-            v[4 * q + 1] = act_axpy<ACT>(__uint_as_float(r[4 * q + 1]) + b4.y, alpha, t4.y);
-            v[4 * q + 2] = act_axpy<ACT>(__uint_as_float(r[4 * q + 2]) + b4.z, alpha, t4.z);
-            v[4 * q + 3] = act_axpy<ACT>(__uint_as_float(r[4 * q + 3]) + b4.w, alpha, t4.w);
+            for (int q = 0; q < 4; ++q) {
+              const float4 b4 = sb[q];
+              v[4 * q + 0] = __uint_as_float(r[4 * q + 0]) + b4.x; v[4 * q + 1] = __uint_as_float(r[4 * q + 1]) + b4.y;
+              v[4 * q + 2] = __uint_as_float(r[4 * q + 2]) + b4.z; v[4 * q + 3] = __uint_as_float(r[4 * q + 3]) + b4.w;
+            }
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float4 b4 = sb[q], t4 = st[q];
+              v[4 * q + 0] = act_axpy<ACT>(__uint_as_float(r[4 * q + 0]) + b4.x, alpha, t4.x);
+              v[4 * q + 1] = act_axpy<ACT>(__uint_as_float(r[4 * q + 1]) + b4.y, alpha, t4.y);
+              v[4 * q + 2] = act_axpy<ACT>(__uint_as_float(r[4 * q + 2]) + b4.z, alpha, t4.z);
+              v[4 * q + 3] = act_axpy<ACT>(__uint_as_float(r[4 * q + 3]) + b4.w, alpha, t4.w);
+            }
           }
           // Residuals.  beta == 1 (every Unet residual): packed bf16x2 adds on the already rounded result --
           // one HADD2.BF16 per two channels instead of an unpack + FFMA per channel; the extra rounding is
@@ -868,7 +889,9 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
         if (lane == 0) {
           const uint32_t src = sg.base + buf * 4096u;
           const int V0 = tg.V0 + g0, xc = tg.x0 + 1;               // this warp's 4 rows
-          if (a.epi_geo == 0) {
+          if (which) {                                             // second output: zero ring, one 4-row box
+            tma_store_3d(&a.tmO2, src, j * 64, xc, V0);
+          } else if (a.epi_geo == 0) {
             bool whole = !reflect;
             int yp0 = 0;
             if (reflect) {                                         // stride 1: virtual row == padded stacked row
@@ -1061,7 +1084,7 @@ __device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b
 // the low word (high words are constants), and for the 3x3 / 2x2 / 1x1 halo cases (TAPS = 9/4/1)
 // the tap loops are unrolled so tap offsets are immediates.  TAPS = 0: generic runtime loops
 // (stride 2, validation modes).
-template <int TAPS, int MT, bool BRES, int CG>
+template <int TAPS, int MT, bool BRES, int CG, bool DUAL = false>
 __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, uint32_t a_base, uint32_t b_base,
                                          uint32_t bar_base) {
   const Bars bars{bar_base};
@@ -1092,8 +1115,36 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
     mbar_wait(bars.T_empty(rt.stage), rt.phase ^ 1, err, 3);
     tc_fence_after();
     dbg_stamp(a, mma_il, 2);
-    const uint32_t d0 = tmem_base + (uint32_t)(rt.stage * MT) * Npad;
+    const uint32_t d0 = tmem_base + (uint32_t)(rt.stage * MT * (DUAL ? 2 : 1)) * Npad;
     uint32_t kcount = 0;     // 0 only for the first k-block of the item (accumulator overwrite)
+    uint32_t kcount2 = 0;    // same for the second output's accumulator (DUAL)
+    // DUAL: the chunk's 10th weight k-block (1x1 conv) against the centre tap, into the accumulator
+    // MT*Npad columns further
+    auto issue_tap2 = [&](uint32_t a_lo, uint32_t a_hi) {
+      uint32_t b_lo;
+      if (BRES) {
+        b_lo = b_cur;
+        b_cur += bB16;
+      } else {
+        mbar_wait(bars.B_full(rb.stage), rb.phase, err, 5);
+        tc_fence_after();
+        b_lo = b_lo_base + (uint32_t)rb.stage * bB16;
+      }
+      const uint32_t e0 = d0 + (uint32_t)MT * Npad;
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) {
+        const uint32_t e = e0 + (uint32_t)mt * Npad, am = a_lo + (uint32_t)mt * aS16;
+        tc_mma_bf16<CG>(e, mk_desc(am, a_hi), mk_desc(b_lo, DESC_HI_1024), idesc, kcount2);
+        tc_mma_bf16<CG>(e, mk_desc(am + 2, a_hi), mk_desc(b_lo + 2, DESC_HI_1024), idesc, 1u);
+        tc_mma_bf16<CG>(e, mk_desc(am + 4, a_hi), mk_desc(b_lo + 4, DESC_HI_1024), idesc, 1u);
+        tc_mma_bf16<CG>(e, mk_desc(am + 6, a_hi), mk_desc(b_lo + 6, DESC_HI_1024), idesc, 1u);
+      }
+      if (!BRES) {
+        tc_commit<CG>(bars.B_empty(rb.stage));
+        rb.next();
+      }
+      kcount2 = 1u;
+    };
     auto issue_tap = [&](uint32_t a_lo, uint32_t a_hi) {
       uint32_t b_lo;
       if (BRES) {
@@ -1135,6 +1186,7 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
 #pragma unroll
           for (int kyi = 0; kyi < NK; ++kyi)
             issue_tap(st_lo + (uint32_t)(kyi * HALO_W + kxi) * 8u, DESC_HI_HALO);
+        if (DUAL) issue_tap2(a_lo_base + (uint32_t)(ra.stage * MT) * aS16 + (uint32_t)(HALO_W + 1) * 8u, DESC_HI_HALO);
         tc_commit<CG>(bars.A_empty(ra.stage));
         ra.next();
       }
@@ -1216,6 +1268,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmO) : "memory");
       asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmOrow) : "memory");
       if (a.ep.res1) asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmR) : "memory");
+      if (a.dual) asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmO2) : "memory");
     }
   }
   if (warp == WARP_MMA) {
@@ -1240,6 +1293,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       s_head[i] = (jh < a.ep.planar_c && c < a.ep.N) ? __ldg(a.head_w + (size_t)jh * a.ep.N + c) : 0.f;
     }
     if (threadIdx.x < 4) s_headb[threadIdx.x] = (threadIdx.x < a.ep.planar_c) ? __ldg(a.head_b + threadIdx.x) : 0.f;
+  }
+  if (a.dual) {       // second output: its bias after the first one, no time embedding
+    for (int i = threadIdx.x; i < a.Npad; i += TC_THREADS) {
+      s_bias[a.Npad + i] = (i < a.ep.N) ? __ldg(a.bias2 + i) : 0.f;
+      s_temb[a.Npad + i] = 0.f;
+    }
   }
   if (a.lin_w) {      // linear-residual weights, transposed to [4][Npad] (shares the head-weight storage)
     for (int i = threadIdx.x; i < 4 * a.Npad; i += TC_THREADS) {
@@ -1275,7 +1334,12 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     else if (a.MT == 2) mma_role<T, 2, false, CG>(a, tmem_base, a_base, b_base, bar_base);   \
     else mma_role<T, 1, false, CG>(a, tmem_base, a_base, b_base, bar_base);                  \
   } while (0)
-      if (taps == 9 && a.nkx == 3) SRD_MMA_CASE(9);
+      if (a.dual) {
+        if (a.b_resident && a.MT == 2) mma_role<9, 2, true, CG, true>(a, tmem_base, a_base, b_base, bar_base);
+        else if (a.b_resident) mma_role<9, 1, true, CG, true>(a, tmem_base, a_base, b_base, bar_base);
+        else if (a.MT == 2) mma_role<9, 2, false, CG, true>(a, tmem_base, a_base, b_base, bar_base);
+        else mma_role<9, 1, false, CG, true>(a, tmem_base, a_base, b_base, bar_base);
+      } else if (taps == 9 && a.nkx == 3) SRD_MMA_CASE(9);
       else if (taps == 4 && a.nkx == 2) SRD_MMA_CASE(4);
       else if (taps == 1) SRD_MMA_CASE(1);
       else SRD_MMA_CASE(0);
@@ -1364,6 +1428,10 @@ int tc_supported(const SrdConvDesc& d, const char** why) {
   else if (d.stride != 1 && d.stride != 2) w = "stride";
   else if (d.head_w && (d.planar_c > 4 || !d.planar)) w = "head needs planar_c <= 4";
   else if (d.head_w && d.lin_src) w = "fused head and linear residual are exclusive";
+  else if (d.N2 && (d.N2 != d.N || (d.N % 64) || d.N > 128 || d.stride != 1 || d.up != 1 || d.nky != 3 || d.nkx != 3 ||
+                    d.res1 || d.res2 || d.lin_src || d.head_w || d.out2 || d.planar || !d.out || (d.dst2_ct % 8) ||
+                    (d.dst2_coff % 8)))
+    w = "second output needs a plain 3x3 stride-1 conv with N2 == N in {64, 128}, one NHWC output, no residuals";
   else {
     for (int i = 0; i < d.n_src; ++i) {
       const SrdSrc& s = d.src[i];
@@ -1407,7 +1475,9 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   const int n_phase = d.up * d.up;
   int kb = 0;
   const int taps = d.nky * d.nkx;
-  for (int i = 0; i < d.n_src; ++i) { a.nchunk[i] = (d.src[i].cin + 63) / 64; kb += a.nchunk[i] * taps; }
+  a.dual = d.N2 ? 1 : 0;
+  a.bias2 = d.bias2;
+  for (int i = 0; i < d.n_src; ++i) { a.nchunk[i] = (d.src[i].cin + 63) / 64; kb += a.nchunk[i] * (taps + a.dual); }
   a.kb_per_phase = kb;
   a.kb_total = n_phase * kb;
   const int cg = (n_sm % 2 == 0) ? g_cg : 1;
@@ -1441,9 +1511,10 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   // two TMEM stages (2 x 2 x Npad <= 512 columns) and enough tiles for every SM; small layers (at most ~2
   // item rounds, e.g. the 20x20 level) also take it with ONE stage: they are bound by streaming the whole
   // weight tensor from L2 once per item, and with one round there is no next item to overlap with anyway.
-  const bool small_wide = g_small_mt2 && (2 * a.Npad <= 512) && (2 * 2 * a.Npad > 512) &&
+  const int acc_cols = a.Npad * (1 + a.dual);          // TMEM columns of one M tile's accumulator(s)
+  const bool small_wide = g_small_mt2 && (2 * acc_cols <= 512) && (2 * 2 * acc_cols > 512) &&
                           n_tiles_all >= n_sm && n_tiles_all <= 2LL * n_sm;
-  const bool mt2_ok = ((2 * 2 * a.Npad <= 512) && n_tiles_all >= 2LL * n_sm) || small_wide;
+  const bool mt2_ok = ((2 * 2 * acc_cols <= 512) && n_tiles_all >= 2LL * n_sm) || small_wide;
   const int nbuf_max = EPI_WARPS <= 8 ? 2 : 1;   // 4 KB staging buffers per epilogue warp
   bool planned = false;
   int b_bytes_total = 0, stage_bytes = 0;
@@ -1456,7 +1527,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
     for (int pass = -1; pass < 3 && !planned; ++pass) {
       const bool resident = (pass <= 0);
       const int MT = (pass == -1 || pass == 1) ? 2 : 1;
-      if (pass == -1 && !(g_res_mt2 && 4 * 2 * a.Npad <= 512 && n_tiles_all >= 16LL * n_sm)) continue;
+      if (pass == -1 && !(g_res_mt2 && 4 * 2 * acc_cols <= 512 && n_tiles_all >= 16LL * n_sm)) continue;
       if (resident && !(g_b_resident && res_bytes < (1 << 20))) continue;
       if (pass == 1 && !mt2_ok) continue;
       const int sb = MT * a.a_stage_bytes;
@@ -1508,16 +1579,18 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   // TMEM accumulator stages, and how the epilogue groups are dealt: with >= 3 (2) sub-tiles per item all
   // (two) groups split one item, so an accumulator stage is drained -- and free for the next MMAs -- in
   // the time of ONE sub-tile; otherwise every group drains its own item.
-  a.n_stages = (EPI_GROUPS >= 4 && 4 * a.MT * a.Npad <= 512) ? 4 : (2 * a.MT * a.Npad <= 512 ? 2 : 1);
+  a.n_stages = (EPI_GROUPS >= 4 && 4 * a.MT * acc_cols <= 512) ? 4 : (2 * a.MT * acc_cols <= 512 ? 2 : 1);
   a.stage_shift = a.n_stages == 4 ? 2 : (a.n_stages == 2 ? 1 : 0);
   {
-    const int n_sub = a.MT * ((a.Npad + 63) / 64);
+    const int n_sub = a.MT * ((a.Npad + 63) / 64) * (1 + a.dual);
     int share = d.head_w ? 1 : (n_sub >= 3 ? 4 : n_sub);
     if (share > EPI_GROUPS) share = EPI_GROUPS;
     while (EPI_GROUPS / share > a.n_stages) share *= 2;
     a.n_share = share;
   }
   SRD_CHECK(!d.head_w || a.n_share == 1, "conv_tc: fused head needs N * MT <= 128");
+  SRD_CHECK(!d.N2 || (a.epi_tma && a.a_mode == 1 && a.epi_geo == 0),
+            "conv_tc: the second output needs the halo A mode and the TMA-staged epilogue");
   SRD_CHECK(!d.lin_src || a.epi_tma, "conv_tc: the linear residual needs the TMA-staged epilogue "
             "(stride-1 conv, N %% 64 == 0, NHWC output, batch-uniform temb)");
   plan->smem = a.a_stages * stage_bytes + b_bytes_total + stg_total + BAR_BYTES + VEC_BYTES + 1024;
@@ -1604,6 +1677,11 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
     if (d.res1) {
       r = enc_out(&a.tmR, d.res1, d.res1_ct, d.res1_coff, 4);
       SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(res1) failed with %d", (int)r);
+    }
+    if (d.N2) {
+      SRD_CHECK(((uintptr_t)d.dst2 % 16) == 0, "conv_tc: dst2 must be 16-byte aligned");
+      r = enc_out(&a.tmO2, d.dst2, d.dst2_ct, d.dst2_coff, 4);
+      SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(dst2) failed with %d", (int)r);
     }
   }
   static bool attr_set = false;

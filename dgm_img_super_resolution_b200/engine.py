@@ -6,12 +6,15 @@ and one-time weight re-layout; every per-image / per-step FLOP runs in libsrdiff
 """
 import ctypes as C
 import math
+import os
 
 import torch
 
 from . import _lib as L
 
 PRECISIONS = ("bf16", "fp32", "bf16_direct")
+# developer switch for A/B measurements: res_conv as a second output of block1's launch (SrdConvDesc.N2)
+FUSE_RES_CONV = os.environ.get("SRD_NO_FUSED_RES") != "1"
 
 
 def _ceil(a, b):
@@ -122,6 +125,27 @@ def _pack_convT(weight, src_cins, S):
     return w_direct, w_tc
 
 
+def _pack_conv_dual(w3, w1, src_cins):
+    """w_tc for a launch with a second 1x1 output (SrdConvDesc.N2): per (source, 64-channel chunk) the nine
+    3x3 k-blocks in (kx, ky) order, then ONE k-block of the 1x1 weights [O][I][1][1] for the same channels."""
+    O, I, kh, kw = w3.shape
+    assert (kh, kw) == (3, 3) and tuple(w1.shape) == (O, I, 1, 1) and sum(src_cins) == I
+    npad = _ceil(O, 16) * 16
+    a3, a1 = w3.detach().float(), w1.detach().float()
+    blocks, a = [], 0
+    for cin in src_cins:
+        for ch in range(_ceil(cin, 64)):
+            c0, c1 = a + ch * 64, a + min(cin, ch * 64 + 64)
+            blk = torch.zeros((10, npad, 64), dtype=torch.float32, device=a3.device)
+            for kx in range(3):
+                for ky in range(3):
+                    blk[kx * 3 + ky, :O, :c1 - c0] = a3[:, c0:c1, ky, kx]
+            blk[9, :O, :c1 - c0] = a1[:, c0:c1, 0, 0]
+            blocks.append(blk)
+        a += cin
+    return torch.cat(blocks, 0).to(torch.bfloat16).contiguous()
+
+
 def _pack_conv_win8(weight):
     """3x3 nn.Conv2d weight [O][I<=8][3][3] for an SRD_SRC_WIN8 source: one K = 64 block per ky whose K
     index is dx*8 + c (dx = pixel inside the 8-pixel window = kx for dx < 3, zero weights beyond)."""
@@ -149,6 +173,18 @@ class PackedConv:
     @property
     def ksize(self):
         return self.weight.shape[2]
+
+    def get_dual(self, src_cins, w1, b1):
+        """(w_direct, w_tc with the interleaved 1x1 blocks, bias, bias2) -- see _pack_conv_dual."""
+        key = ("dual", tuple(src_cins), self.weight.data_ptr(), self.weight._version, self.bias_p.data_ptr(),
+               self.bias_p._version, w1.data_ptr(), w1._version, b1.data_ptr(), b1._version)
+        hit = self._cache.get("du")
+        if hit is None or hit[0] != key:
+            wd, _ = _pack_conv(self.weight, src_cins, 1)
+            self._cache["du"] = (key, wd, _pack_conv_dual(self.weight, w1, src_cins),
+                                 self.bias_p.detach().float().contiguous(), b1.detach().float().contiguous())
+            hit = self._cache["du"]
+        return hit[1], hit[2], hit[3], hit[4]
 
     def get_win8(self):
         """(w_direct, w_tc_win8, bias) for an SRD_SRC_WIN8 source (see _pack_conv_win8)."""
@@ -240,11 +276,13 @@ class Builder:
     # ---- generic conv ----------------------------------------------------------------------
     def conv(self, pw, srcs, out=None, out_coff=0, out2=None, out2_coff=0, act=L.ACT_NONE, alpha=1.0,
              temb_off=None, temb_bstride=0, res1=None, res2=None, border=L.BORDER_KEEP, planar=None,
-             planar_c=0, planar_clamp01=0, head=None, kernel=None, win8=False, lin=None, temb_static=None):
+             planar_c=0, planar_clamp01=0, head=None, kernel=None, win8=False, lin=None, temb_static=None,
+             dual=None):
         """srcs: list of (Act, c_off, cin); res1/res2: (Act, c_off, beta); head: (w[planar_c][N], b).
         win8: the single source is an 8-channel buffer read through SRD_SRC_WIN8 (3x3 conv as three K=64
         blocks).  lin: (Act, w[N][c], c) linear residual evaluated in the epilogue; temb_static: fp32 [N]
-        vector added after the activation (e.g. the bias of the folded res_conv)."""
+        vector added after the activation (e.g. the bias of the folded res_conv).  dual: (conv1x1 module, Act)
+        second output of the same launch = conv1x1(srcs) + bias, no activation (ResnetBlock.res_conv)."""
         d = L.SrdConvDesc()
         d.dtype = self.prec.dtype
         d.kernel = self.prec.kernel if kernel is None else kernel
@@ -259,6 +297,12 @@ class Builder:
             assert a0._flat.numel() - a0.t.numel() >= 56, "SRD_SRC_WIN8 source needs >= 112 B of slack"
             wd, wt, bias = pw.get_win8()
             d.src[0].cin, d.src[0].flags = 64, L.SRC_WIN8
+            d.kernel = L.KERNEL_TC
+        elif dual is not None:
+            assert not pw.transposed and pw.ksize == 3 and pw.stride == 1
+            wd, wt, bias, bias2 = pw.get_dual([s[2] for s in srcs], dual[0].weight, dual[0].bias)
+            d.N2, d.bias2 = pw.N, bias2.data_ptr()
+            d.dst2, d.dst2_ct, d.dst2_coff = dual[1].ptr, dual[1].ct, 0
             d.kernel = L.KERNEL_TC
         else:
             wd, wt, bias = pw.get([s[2] for s in srcs])
@@ -275,7 +319,7 @@ class Builder:
         d.w_direct, d.w_tc, d.bias = wd.data_ptr(), wt.data_ptr(), bias.data_ptr()
         d.act, d.alpha = act, alpha
         d.temb, d.temb_bstride = None, temb_bstride
-        keep = [wd, wt, bias, [s[0] for s in srcs], out, out2, planar]
+        keep = [wd, wt, bias, [s[0] for s in srcs], out, out2, planar, dual, bias2 if dual is not None else None]
         if temb_static is not None:
             assert temb_off is None
             d.temb = temb_static.data_ptr()
@@ -369,11 +413,17 @@ def build_resnet(bld, blk, srcs, dim_out, out, border, temb_off, temb_bstride=0,
         bld.conv(_pc(blk.block2.block[1]), [(h1, 0, dim_out)], out=out, act=L.ACT_MISH, lin=(a0, lw, cin),
                  temb_static=lb, border=border)
         return out
+    # channel-changing block on the tcgen05 path: the 1x1 res_conv is a second output of block1's launch
+    # (same activation tiles; SrdConvDesc.N2) when the doubled accumulator still leaves two TMEM stages
+    fused_res = (cin != dim_out and FUSE_RES_CONV and bld.prec.name == "bf16" and dim_out % 64 == 0 and dim_out <= 128 and H >= 4 and
+                 (temb_bstride == 0 or not use_temb) and all(s[0].ct % 8 == 0 and s[1] % 8 == 0 for s in srcs))
+    r = bld.act(B, H, W, dim_out) if cin != dim_out else None
     bld.conv(_pc(blk.block1.block[1]), srcs, out=h1, act=L.ACT_MISH, temb_off=temb_off,
-             temb_bstride=temb_bstride if use_temb else 0, border=L.BORDER_REFLECT)
+             temb_bstride=temb_bstride if use_temb else 0, border=L.BORDER_REFLECT,
+             dual=(blk.res_conv, r) if fused_res else None)
     if cin != dim_out:
-        r = bld.act(B, H, W, dim_out)
-        bld.conv(_pc(blk.res_conv), srcs, out=r, act=L.ACT_NONE, border=L.BORDER_KEEP)
+        if not fused_res:
+            bld.conv(_pc(blk.res_conv), srcs, out=r, act=L.ACT_NONE, border=L.BORDER_KEEP)
         res1 = (r, 0, 1.0)
     else:
         assert len(srcs) == 1

@@ -99,6 +99,15 @@ typedef struct {
    * block, :471,480) evaluated in the epilogue instead of a separate launch; its bias rides on temb. */
   const void* lin_src; int32_t lin_ct, lin_c;
   const float* lin_w;     /* fp32 [N][lin_c] */
+  /* optional SECOND output of the same launch (tc kernel, 3x3 stride-1 conv, TMA-staged epilogue, N % 64 == 0,
+   * N <= 128): dst2 = conv1x1(sources) + bias2 with N2 == N output channels, no activation, zero ring -- the
+   * ResnetBlock's res_conv (:471) computed from the activation tiles block1 (:474) has already loaded.  Its
+   * weights ride in w_tc: per (source, 64-channel chunk) the nine 3x3 k-blocks are followed by ONE k-block
+   * [Npad][64] of the 1x1 conv. */
+  int32_t N2;             /* 0 = no second output */
+  int32_t dst2_ct, dst2_coff, reserved2;
+  const float* bias2;     /* [N2] */
+  void* dst2;
 } SrdConvDesc;
 
 typedef struct SrdConvPlan SrdConvPlan;
@@ -106,7 +115,7 @@ typedef struct SrdConvPlan SrdConvPlan;
 const char* srd_last_error(void);
 int srd_version(void);
 /* ABI self-check for FFI bindings: which = 0 -> sizeof(SrdConvDesc), 1 -> sizeof(SrdPSampleArgs),
- * 2 -> offsetof(SrdConvDesc, lin_w), 3 -> offsetof(SrdPSampleArgs, seed_ptr). */
+ * 2 -> offsetof(SrdConvDesc, dst2), 3 -> offsetof(SrdPSampleArgs, seed_ptr). */
 int srd_abi_sizeof(int32_t which);
 /* 1 if the tcgen05/TMA path can serve this descriptor (bf16, channel/stride alignment...). */
 int srd_conv_tc_supported(const SrdConvDesc* desc);

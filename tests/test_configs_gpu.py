@@ -58,7 +58,7 @@ def test_config4_timestep_sweep_graph_loop(hp, T):
         M.runtime.seed_counter = 100
         img, rrdb_out = diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
         assert img.shape == (2, 3, 256, 256) and torch.isfinite(img).all()
-        assert diff.last_stats["graph"] and diff.last_stats["gpu_launches"] > 45 * T
+        assert diff.last_stats["graph"] and diff.last_stats["gpu_launches"] > 40 * T
         M.runtime.seed_counter = 100                    # same seed -> bit-identical replay of the captured graph
         img2, _ = diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
         assert torch.equal(img, img2)

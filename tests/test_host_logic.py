@@ -43,6 +43,21 @@ def test_pack_conv_layouts(cins, O, k, stride, reflect):
     assert wt.shape[-2] % 16 == 0 and wt.shape[-1] == 64 and wt.dtype == torch.bfloat16
 
 
+def test_pack_conv_dual_interleaves_the_1x1_blocks():
+    """SrdConvDesc.N2: per (source, chunk) nine 3x3 k-blocks then the 1x1 block of the same channels."""
+    from dgm_img_super_resolution_b200 import engine as E
+    torch.manual_seed(2)
+    cins = [100, 64]
+    w3, w1 = torch.randn(64, 164, 3, 3), torch.randn(64, 164, 1, 1)
+    wt = E._pack_conv_dual(w3, w1, cins).float()
+    _, ref3 = E._pack_conv(w3, cins, 1)
+    _, ref1 = E._pack_conv(w1, cins, 1)
+    assert wt.shape == (3 * 10, 64, 64)
+    for ch in range(3):
+        assert torch.equal(wt[ch * 10:ch * 10 + 9], ref3.float()[ch * 9:ch * 9 + 9])
+        assert torch.equal(wt[ch * 10 + 9], ref1.float()[ch])
+
+
 def test_pack_conv_win8_windows():
     """SRD_SRC_WIN8: the first Unet conv as three K=64 blocks over 8-pixel windows of the 8-channel buffer
     (K index = dx*8 + c; the window of the last pixels of a row runs into the next row on zero weights)."""
