@@ -67,7 +67,7 @@ __global__ void randn_kernel(float* out, int B, int chw, uint64_t seed, uint32_t
 // in-kernel Philox (+ the small NHWC copy of x' when requested).
 // ------------------------------------------------------------------------------------------
 template <int V, typename T, bool SMALLC>
-__global__ void __launch_bounds__(256) p_sample_kernel(const SrdPSampleArgs a) {
+__global__ void __launch_bounds__(256, 3) p_sample_kernel(const SrdPSampleArgs a) {
   const int HW = a.H * a.W;
   const int nq = HW / V;                       // V divides W (checked on the host)
   const uint64_t seed = a.seed_ptr ? __ldg(reinterpret_cast<const unsigned long long*>(a.seed_ptr)) : a.seed;
@@ -81,12 +81,13 @@ __global__ void __launch_bounds__(256) p_sample_kernel(const SrdPSampleArgs a) {
     const float sigma = (t == 0) ? 0.f : expf(0.5f * __ldg(cf + 4));   // nonzero_mask * exp(.5 logvar)
     const int pix = q * V;
     const int y = pix / a.W, x0p = pix % a.W;
-    float nh[V][8];
+    constexpr int NHC = SMALLC ? 4 : 8;         // channels kept for the NHWC copy (the rest of the 8 are zero)
+    float nh[V][NHC];
     if (a.nhwc_out) {
 #pragma unroll
       for (int v = 0; v < V; ++v)
 #pragma unroll
-        for (int c = 0; c < 8; ++c) nh[v][c] = 0.f;
+        for (int c = 0; c < NHC; ++c) nh[v][c] = 0.f;
     }
     // All loads of the pixel group are issued before any store: x_out may alias x (in-place update), so
     // the compiler cannot hoist the next channel's loads above this channel's stores by itself, and a
@@ -150,7 +151,7 @@ __global__ void __launch_bounds__(256) p_sample_kernel(const SrdPSampleArgs a) {
         const float mean = __fadd_rn(__fmul_rn(c1, x0), __fmul_rn(c2, xv[v]));
         ov[v] = __fadd_rn(mean, __fmul_rn(sigma, zv[v]));
         x0v[v] = x0;
-        if (a.nhwc_out && c < 8) nh[v][c] = ov[v];
+        if (a.nhwc_out && c < NHC) nh[v][SMALLC ? cu : c] = ov[v];
       }
       if (V == 4) {
         *reinterpret_cast<float4*>(a.x_out + off) = make_float4(ov[0], ov[1], ov[2], ov[3]);
@@ -172,9 +173,13 @@ __global__ void __launch_bounds__(256) p_sample_kernel(const SrdPSampleArgs a) {
     }
     if (a.nhwc_out) {
 #pragma unroll
-      for (int v = 0; v < V; ++v)
+      for (int v = 0; v < V; ++v) {
+        float o8[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) o8[c] = c < NHC ? nh[v][c < NHC ? c : 0] : 0.f;
         store_nhwc<T, 8, (sizeof(T) == 2 ? 8 : 4)>(static_cast<T*>(a.nhwc_out), a.nhwc_ct, 0, b, y,
-                                                   x0p + v, a.H, a.W, 0, 8, SRD_BORDER_REFLECT, nh[v]);
+                                                   x0p + v, a.H, a.W, 0, 8, SRD_BORDER_REFLECT, o8);
+      }
     }
   }
 }
