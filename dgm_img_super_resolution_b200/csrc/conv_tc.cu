@@ -486,7 +486,9 @@ __device__ __forceinline__ void epi_chunk_fast(const TcArgs& a, const EpiSmem& e
     if (tp.out2) store_chunk(tp.out2 + c0, a.ep.out2_ct, dn, tp.edge, v);   // out/out2 share H, W; dn uses out's ct
   }
   if (es.head_w) {
-    for (int jh = 0; jh < a.ep.planar_c; ++jh) {
+#pragma unroll
+    for (int jh = 0; jh < 4; ++jh) {           // static indices: head[] stays in registers
+      if (jh >= a.ep.planar_c) break;
       const float4* hw = reinterpret_cast<const float4*>(es.head_w + jh * a.Npad + c0);
       float acc = head[jh];
 #pragma unroll
@@ -591,8 +593,10 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
           epi_chunk_fast<ACT>(a, es, c * 16, r, tp, wp, q1, q2, head);
         }
         if (has_head && valid) {
-          for (int jh = 0; jh < a.ep.planar_c; ++jh)
-            a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
+#pragma unroll
+          for (int jh = 0; jh < 4; ++jh)
+            if (jh < a.ep.planar_c)
+              a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
         }
       } else {
         // generic path (ragged N, per-image temb rows, planar output): one group per stage does all chunks
@@ -608,7 +612,9 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
             epilogue_store<__nv_bfloat16, 16, 8>(a.ep, b, oy, ox, c0, v, !has_head);
             if (has_head) {
               const int nv = min(16, a.ep.N - c0);
-              for (int jh = 0; jh < a.ep.planar_c; ++jh) {
+#pragma unroll
+              for (int jh = 0; jh < 4; ++jh) {
+                if (jh >= a.ep.planar_c) break;
                 float acc = head[jh];
 #pragma unroll
                 for (int i = 0; i < 16; ++i)
@@ -619,8 +625,10 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
           }
         }
         if (has_head && valid && share == 0) {
-          for (int jh = 0; jh < a.ep.planar_c; ++jh)
-            a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
+#pragma unroll
+          for (int jh = 0; jh < 4; ++jh)
+            if (jh < a.ep.planar_c)
+              a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
         }
       }
     }
