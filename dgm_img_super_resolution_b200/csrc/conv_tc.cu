@@ -35,14 +35,22 @@ namespace srd {
 #endif
 constexpr int EPI_WARPS = SRD_EPI_WARPS; // groups of 4 warps (one warp per TMEM lane quarter)
 constexpr int EPI_GROUPS = EPI_WARPS / 4;
-constexpr int TC_THREADS = 96 + 32 * EPI_WARPS;   // activation-TMA warp + weight-TMA warp + MMA warp + epilogue warps
+// Experiment kept behind a macro: a second MMA-issuing thread taking the odd items of resident-weight
+// layers.  Measured twice on B200: no gain (229 vs 230 images/s) -- those layers are balanced between the
+// MMA thread, the Mish epilogue and HBM, not bound by MMA issue alone.
+#ifndef SRD_DUAL_ISSUE
+#define SRD_DUAL_ISSUE 0
+#endif
+// activation-TMA warp + weight-TMA warp + MMA warp(s) + epilogue warps
+constexpr int TC_THREADS = 96 + 32 * SRD_DUAL_ISSUE + 32 * EPI_WARPS;
 // Warp roles.  The SMSP arbiter prefers the highest warp id, so the two single-thread roles
 // (TMA producer, MMA issuer) sit ABOVE the issue-heavy epilogue warps: an MMA that is ready to
 // issue must never queue behind Mish arithmetic.
-constexpr int WARP_EPI0 = SRD_ROLES_HIGH ? 0 : 3;
+constexpr int WARP_EPI0 = SRD_ROLES_HIGH ? 0 : 3 + SRD_DUAL_ISSUE;
 constexpr int WARP_TMA = SRD_ROLES_HIGH ? EPI_WARPS : 0;        // activation (A operand) producer
 constexpr int WARP_TMB = SRD_ROLES_HIGH ? EPI_WARPS + 1 : 1;    // weight (B operand) producer
-constexpr int WARP_MMA = SRD_ROLES_HIGH ? EPI_WARPS + 2 : 2;
+constexpr int WARP_MMA = SRD_ROLES_HIGH ? EPI_WARPS + 2 : 2;    // MMA issuer (+ TMEM owner)
+constexpr int WARP_MMA2 = WARP_MMA + 1;   // SRD_DUAL_ISSUE: second MMA issuer (odd local items of dual_issue layers)
 constexpr int TILE_W = 8, TILE_H = 16;
 constexpr int BOX_ROWS = TILE_H + 2;
 constexpr int A_BYTES = BOX_ROWS * TILE_W * 128;   // 18432: one {64ch x 8px x 18rows} bf16 box
@@ -85,6 +93,7 @@ struct TcArgs {
   int n_colblk, tiles_per_phase, items_per_phase, n_items;
   FastDiv fd_ipp, fd_colblk, fd_period, fd_up;   // dividers by items_per_phase, n_colblk, period, up
   int n_chunks;            // 64-channel K chunks per item over all sources
+  int dual_issue;          // SRD_DUAL_ISSUE build: two MMA-issuing threads take alternate items (see mma_role)
   int dual;                // 1: second output = 1x1 conv of the same sources (SrdConvDesc.N2): its accumulator sits
                            //    MT*Npad columns after the first one, its weights are the 10th k-block of every chunk
   const float* bias2;
@@ -306,6 +315,10 @@ __device__ __forceinline__ void epi_stamp(const TcArgs& a, int item_local, int e
 struct Ring {
   int stage, phase, n;
   __device__ __forceinline__ void next() { if (++stage == n) { stage = 0; phase ^= 1; } }
+  __device__ __forceinline__ void skip(int k) {          // k slots consumed by another thread
+    stage += k;
+    while (stage >= n) { stage -= n; phase ^= 1; }
+  }
 };
 
 // Where this CTA sits: work items are dealt to CTA pairs (CG == 2) or single CTAs (CG == 1); item i of
@@ -1094,7 +1107,7 @@ __device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b
 // (stride 2, validation modes).
 template <int TAPS, int MT, bool BRES, int CG, bool DUAL = false>
 __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, uint32_t a_base, uint32_t b_base,
-                                         uint32_t bar_base) {
+                                         uint32_t bar_base, int issuer = 0) {
   const Bars bars{bar_base};
   const PairId pid = pair_id<CG>();                  // only the leader CTA of a pair runs this role
   const int n_items = a.n_items, G = pid.n_pairs, S = a.up, n_chunks = a.n_chunks;
@@ -1108,8 +1121,20 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
     mbar_wait(bars.B_res(), 0, err, 7);
     tc_fence_after();
   }
+  // SRD_DUAL_ISSUE: two issuing threads (different schedulers) take alternate items, skipping each other's
+  // ring slots.  Only sound when every slot a thread waits on was last used by the SAME thread (a parity
+  // wait must never run a whole phase ahead of its barrier): resident weights, one A slot per item and an
+  // even A ring -- the host sets dual_issue accordingly.
+  const int dual = SRD_DUAL_ISSUE ? a.dual_issue : 0;
+  if (!dual && issuer != 0) return;
   int mma_il = 0;
   for (int item = pid.pair; item < n_items; item += G) {
+    if (dual && (mma_il & 1) != issuer) {
+      ra.skip(n_chunks);
+      rt.next();
+      ++mma_il;
+      continue;
+    }
     int ky0 = a.ky0, kx0 = a.kx0;
     uint32_t b_cur = b_lo_base;
     if (S > 1) {
@@ -1330,23 +1355,24 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if (elect_one_sync()) producer_role<CG>(a, a_base, bar_base);
   } else if (warp == WARP_TMB) {
     if (elect_one_sync()) weight_producer_role<CG>(a, b_base, bar_base);
-  } else if (warp == WARP_MMA) {
+  } else if (warp == WARP_MMA || (SRD_DUAL_ISSUE && warp == WARP_MMA2)) {
+    const int issuer = warp - WARP_MMA;
     if ((CG == 1 || cluster_ctarank() == 0) && elect_one_sync()) {
       // specialised issue loops: taps unrolled (descriptor offsets become immediates), MT and the weight
       // mode resolved at compile time
       const int taps = a.a_mode ? a.nkx * a.nky : 0;
 #define SRD_MMA_CASE(T)                                                                      \
   do {                                                                                       \
-    if (a.b_resident && a.MT == 2) mma_role<T, 2, true, CG>(a, tmem_base, a_base, b_base, bar_base); \
-    else if (a.b_resident) mma_role<T, 1, true, CG>(a, tmem_base, a_base, b_base, bar_base); \
-    else if (a.MT == 2) mma_role<T, 2, false, CG>(a, tmem_base, a_base, b_base, bar_base);   \
-    else mma_role<T, 1, false, CG>(a, tmem_base, a_base, b_base, bar_base);                  \
+    if (a.b_resident && a.MT == 2) mma_role<T, 2, true, CG>(a, tmem_base, a_base, b_base, bar_base, issuer); \
+    else if (a.b_resident) mma_role<T, 1, true, CG>(a, tmem_base, a_base, b_base, bar_base, issuer); \
+    else if (a.MT == 2) mma_role<T, 2, false, CG>(a, tmem_base, a_base, b_base, bar_base, issuer);   \
+    else mma_role<T, 1, false, CG>(a, tmem_base, a_base, b_base, bar_base, issuer);                  \
   } while (0)
       if (a.dual) {
-        if (a.b_resident && a.MT == 2) mma_role<9, 2, true, CG, true>(a, tmem_base, a_base, b_base, bar_base);
-        else if (a.b_resident) mma_role<9, 1, true, CG, true>(a, tmem_base, a_base, b_base, bar_base);
-        else if (a.MT == 2) mma_role<9, 2, false, CG, true>(a, tmem_base, a_base, b_base, bar_base);
-        else mma_role<9, 1, false, CG, true>(a, tmem_base, a_base, b_base, bar_base);
+        if (a.b_resident && a.MT == 2) mma_role<9, 2, true, CG, true>(a, tmem_base, a_base, b_base, bar_base, issuer);
+        else if (a.b_resident) mma_role<9, 1, true, CG, true>(a, tmem_base, a_base, b_base, bar_base, issuer);
+        else if (a.MT == 2) mma_role<9, 2, false, CG, true>(a, tmem_base, a_base, b_base, bar_base, issuer);
+        else mma_role<9, 1, false, CG, true>(a, tmem_base, a_base, b_base, bar_base, issuer);
       } else if (taps == 9 && a.nkx == 3) SRD_MMA_CASE(9);
       else if (taps == 4 && a.nkx == 2) SRD_MMA_CASE(4);
       else if (taps == 1) SRD_MMA_CASE(1);
@@ -1582,6 +1608,8 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   a.fd_up = make_fastdiv((uint32_t)d.up);
   a.n_chunks = 0;
   for (int i = 0; i < d.n_src; ++i) a.n_chunks += a.nchunk[i];
+  if (SRD_DUAL_ISSUE && a.b_resident && a.a_mode == 1 && a.n_chunks == 1 && a.a_stages == 3) a.a_stages = 2;
+
   a.b_region_bytes = b_bytes_total;
   const int stg_total = a.epi_tma ? EPI_WARPS * a.epi_nbuf * 4096 : 0;
   // TMEM accumulator stages, and how the epilogue groups are dealt: with >= 3 (2) sub-tiles per item all
@@ -1589,6 +1617,8 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   // the time of ONE sub-tile; otherwise every group drains its own item.
   a.n_stages = (EPI_GROUPS >= 4 && 4 * a.MT * acc_cols <= 512) ? 4 : (2 * a.MT * acc_cols <= 512 ? 2 : 1);
   a.stage_shift = a.n_stages == 4 ? 2 : (a.n_stages == 2 ? 1 : 0);
+  a.dual_issue = (SRD_DUAL_ISSUE && a.b_resident && a.a_mode == 1 && a.n_chunks == 1 && a.a_stages % 2 == 0 &&
+                  a.n_stages % 2 == 0) ? 1 : 0;
   {
     const int n_sub = a.MT * ((a.Npad + 63) / 64) * (1 + a.dual);
     int share = d.head_w ? 1 : (n_sub >= 3 ? 4 : n_sub);
