@@ -312,6 +312,22 @@ __device__ __forceinline__ void epi_stamp(const TcArgs& a, int item_local, int e
 #endif
 }
 
+// -DSRD_TC_DEBUG=3: kernel-phase stamps of thread 0 in item slot DBG_ITEMS-1: 0 entry, 1 setup done (after
+// the block / cluster sync), 2 previous grid complete (griddepcontrol.wait), 3 roles done (before the final
+// sync), 4 after the final sync, 5 TMEM freed; plus globaltimer (ns) at entry in 6 and at exit in 7.
+__device__ __forceinline__ void kern_stamp(const TcArgs& a, int ev, bool global_ns = false) {
+#if defined(SRD_TC_DEBUG) && SRD_TC_DEBUG == 3
+  if (a.dbg && threadIdx.x == 0) {
+    unsigned long long v;
+    if (global_ns) asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(v));
+    else v = (unsigned long long)clock64();
+    a.dbg[((size_t)blockIdx.x * DBG_ITEMS + DBG_ITEMS - 1) * 8 + ev] = v;
+  }
+#else
+  (void)a; (void)ev; (void)global_ns;
+#endif
+}
+
 struct Ring {
   int stage, phase, n;
   __device__ __forceinline__ void next() { if (++stage == n) { stage = 0; phase ^= 1; } }
@@ -985,7 +1001,9 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     }
     if (quarter == 0 && lane == 0) dbg_stamp(a, it, 7);
   }
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  // Before the CTA exits the staging buffers must have been READ by the TMA unit; the global writes themselves
+  // complete with the grid (and before a dependent grid's griddepcontrol.wait returns).
+  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
 }
 
 
@@ -1261,6 +1279,8 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
 template <int CG>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
+  kern_stamp(a, 0);
+  kern_stamp(a, 6, true);
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t a_base = smem_base;
@@ -1348,8 +1368,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   // epilogue-vector staging) touched only launch constants, so it may overlap the tail of the previous
   // layer.  From here on activations are read / written: wait for the previous grid -- except the weight
   // producer, whose loads are layer constants and may pre-fill the weight ring meanwhile.
+  kern_stamp(a, 1);
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   if (warp != WARP_TMB) asm volatile("griddepcontrol.wait;" ::: "memory");
+  kern_stamp(a, 2);
 
   if (warp == WARP_TMA) {
     if (elect_one_sync()) producer_role<CG>(a, a_base, bar_base);
@@ -1403,9 +1425,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       epilogue_role<SRD_ACT_NONE, CG>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
   }
 
+  kern_stamp(a, 3);
   tc_fence_before();
   __syncthreads();
   if (CG == 2) cluster_sync_all();      // the peer's shared memory / TMEM stay alive until the pair's MMAs are done
+  kern_stamp(a, 4);
   if (warp == WARP_MMA) {
     tc_fence_after();
     if (CG == 1)
@@ -1413,6 +1437,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     else
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
   }
+  kern_stamp(a, 5);
+  kern_stamp(a, 7, true);
 }
 
 // ------------------------------------------------------------------------------------------ host
