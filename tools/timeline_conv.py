@@ -1,21 +1,27 @@
 """GPU helper: run one conv with the debug timeline enabled and print per-item stage timings (cycles).
-    python tools/timeline_conv.py CIN COUT H B [res]"""
+    python tools/timeline_conv.py CIN COUT H B [res|convT|s2]   (H = input size)"""
 import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from dgm_img_super_resolution_b200 import engine as E, _lib as L
 cin, cout, H, B = [int(v) for v in sys.argv[1:5]]
-use_res = len(sys.argv) > 5 and sys.argv[5] == "res"
+kind = sys.argv[5] if len(sys.argv) > 5 else ""
+use_res = kind == "res"
 dev = "cuda:0"
 torch.manual_seed(0)
-conv = torch.nn.Conv2d(cin, cout, 3).to(dev)
+if kind == "convT":
+    conv, Ho, act = torch.nn.ConvTranspose2d(cin, cout, 4, 2, 1).to(dev), 2 * H, L.ACT_NONE
+elif kind == "s2":
+    conv, Ho, act = torch.nn.Conv2d(cin, cout, 3, 2).to(dev), H // 2, L.ACT_NONE
+else:
+    conv, Ho, act = torch.nn.Conv2d(cin, cout, 3).to(dev), H, L.ACT_MISH
 dbg = torch.zeros((148, 64, 8), dtype=torch.int64, device=dev)
 L.lib().srd_tc_set_debug(dbg.data_ptr())
 bld = E.Builder(dev, "bf16")
 src = bld.act(B, H, H, cin); src.t.normal_()
-out = bld.act(B, H, H, cout); res = bld.act(B, H, H, cout)
+out = bld.act(B, Ho, Ho, cout); res = bld.act(B, Ho, Ho, cout)
 temb = torch.randn(cout, device=dev)
-op = bld.conv(E._pc(conv), [(src, 0, cin)], out=out, act=L.ACT_MISH, res1=(res, 0, 1.0) if use_res else None, border=L.BORDER_REFLECT)
+op = bld.conv(E._pc(conv), [(src, 0, cin)], out=out, act=act, res1=(res, 0, 1.0) if use_res else None, border=L.BORDER_REFLECT)
 L.lib().srd_tc_set_debug(None)
 for _ in range(3):
     bld.run()
