@@ -61,6 +61,21 @@ class SrdPSampleArgs(C.Structure):
     ]
 
 
+class SrdGroupNormArgs(C.Structure):
+    _fields_ = [
+        ("src", C.c_void_p), ("src_ct", C.c_int32), ("src_coff", C.c_int32),
+        ("dtype", C.c_int32),
+        ("out", C.c_void_p), ("out_ct", C.c_int32), ("out_coff", C.c_int32),
+        ("B", C.c_int32), ("H", C.c_int32), ("W", C.c_int32), ("C", C.c_int32), ("groups", C.c_int32),
+        ("act", C.c_int32), ("border", C.c_int32),
+        ("eps", C.c_float), ("temb_bstride", C.c_int32),
+        ("gamma", C.c_void_p), ("beta", C.c_void_p), ("temb", C.c_void_p),
+        ("res", C.c_void_p), ("res_ct", C.c_int32), ("res_coff", C.c_int32),
+        ("reserved", C.c_int32),
+        ("stats", C.c_void_p),
+    ]
+
+
 # every symbol include/srdiff_b200.h declares: name -> (restype, argtypes)
 _vp, _i32, _i64, _f, _u32, _u64 = C.c_void_p, C.c_int32, C.c_int64, C.c_float, C.c_uint32, C.c_uint64
 SYMBOLS = {
@@ -89,6 +104,12 @@ SYMBOLS = {
     "srd_u8hwc_to_nchw": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "srd_nchw_to_u8hwc": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "srd_tiles": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
+    "srd_groupnorm_act": (C.c_int, [C.POINTER(SrdGroupNormArgs), _vp]),
+    "srd_linear_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
+    "srd_ssim_workspace": (C.c_int, [_i32, _i32, _i32, _i32]),
+    "srd_ssim": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _f, _f, _vp, _vp, _vp]),
+    "srd_f32_to_u8_round": (C.c_int, [_vp, _i64, _vp, _vp]),
+    "srd_sq_err_u8": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
 }
 
 _lib = None
@@ -112,8 +133,8 @@ def lib():
             fn.restype = res
             fn.argtypes = args
         abi = (C.sizeof(SrdConvDesc), C.sizeof(SrdPSampleArgs), SrdConvDesc.dst2.offset,
-               SrdPSampleArgs.seed_ptr.offset)
-        got = tuple(L.srd_abi_sizeof(i) for i in range(4))
+               SrdPSampleArgs.seed_ptr.offset, C.sizeof(SrdGroupNormArgs), SrdGroupNormArgs.stats.offset)
+        got = tuple(L.srd_abi_sizeof(i) for i in range(6))
         if abi != got:
             raise SrdError("ctypes structs disagree with include/srdiff_b200.h: %s vs %s" % (abi, got))
         # tuning / validation switches of the tcgen05 kernel (see srd_tc_set_mode in the header)

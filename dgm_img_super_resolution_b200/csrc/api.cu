@@ -61,7 +61,7 @@ static int validate(const SrdConvDesc& d) {
   SRD_CHECK(d.n_src >= 1 && d.n_src <= SRD_MAX_SRC, "conv: n_src %d out of range", d.n_src);
   SRD_CHECK(d.B > 0 && d.H_in > 0 && d.W_in > 0 && d.N > 0, "conv: bad sizes");
   SRD_CHECK(d.stride == 1 || d.stride == 2, "conv: stride must be 1 or 2");
-  SRD_CHECK(d.up == 1 || d.up == 2 || d.up == 4, "conv: up must be 1, 2 or 4");
+  SRD_CHECK(d.up == 1 || d.up == 2 || d.up == 4 || d.up == 8, "conv: up must be 1, 2, 4 or 8");
   SRD_CHECK(d.up == 1 || (d.stride == 1 && d.nky == 2 && d.nkx == 2), "conv: transposed phases are 2x2 taps, stride 1");
   SRD_CHECK(d.nky >= 1 && d.nky <= 3 && d.nkx >= 1 && d.nkx <= 3, "conv: taps out of range");
   SRD_CHECK(d.up > 1 || (d.ky0 >= 0 && d.ky0 + d.nky <= 3 && d.kx0 >= 0 && d.kx0 + d.nkx <= 3),
@@ -103,6 +103,8 @@ int srd_abi_sizeof(int32_t which) {
     case 1: return (int)sizeof(SrdPSampleArgs);
     case 2: return (int)offsetof(SrdConvDesc, dst2);
     case 3: return (int)offsetof(SrdPSampleArgs, seed_ptr);
+    case 4: return (int)sizeof(SrdGroupNormArgs);
+    case 5: return (int)offsetof(SrdGroupNormArgs, stats);
     default: return -1;
   }
 }

@@ -1,0 +1,251 @@
+// SURVEY 8f-3 / 8f-4 "next" rows around the hot path:
+//  * GroupNorm variant of `Block` (srdiff/model.py:448-454): conv -> GroupNorm -> Mish, with the ResnetBlock's
+//    time-embedding / residual adds (:474-480) folded into the same pass;
+//  * the ResnetBlock time MLP `Linear(Mish(time_emb))` (:464-468,476) for stand-alone block calls;
+//  * quality metrics: the torch SSIM (:146-222) and the uint8 PSNR of `Measure` (:1499-1542).
+// All HBM-bound passes over padded NHWC activations / fp32 NCHW images.
+#include "common.cuh"
+
+namespace srd {
+
+static inline int vgrid(long long total, int block = 256) {
+  long long g = (total + block - 1) / block;
+  const long long cap = 148LL * 16;
+  return (int)(g < 1 ? 1 : (g > cap ? cap : g));
+}
+
+__device__ __forceinline__ double block_sum(double v, double* sh) {
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+  __syncthreads();
+  if (l == 0) sh[w] = v;
+  __syncthreads();
+  if (w == 0) {
+    v = (l < (int)(blockDim.x >> 5)) ? sh[l] : 0.0;
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_down_sync(0xffffffffu, v, o);
+  }
+  return v;   // valid in thread 0
+}
+
+// ---------------------------------------------------------------------------- GroupNorm (+ Mish + adds)
+// nn.GroupNorm(groups, C) :452: per (image, group) mean and BIASED variance over (C/groups, H, W), eps inside the
+// square root.  One block per (b, g); fp32 per-thread partial sums, double across the block.
+template <typename T>
+__global__ void gn_stats_kernel(const T* x, int ct, int c_off, int H, int W, int C, int G, float eps, float* stats) {
+  __shared__ double sh[32];
+  const int b = blockIdx.x / G, g = blockIdx.x % G;
+  const int cpg = C / G;
+  const long long n = (long long)H * W * cpg;
+  float s = 0.f, ss = 0.f;
+  int cnt = 0;
+  double ds = 0.0, dss = 0.0;
+  for (long long i = threadIdx.x; i < n; i += blockDim.x) {
+    const int c = (int)(i % cpg);
+    const long long p = i / cpg;
+    const int xx = (int)(p % W), y = (int)(p / W);
+    const float v = Elem<T>::ld(x + ((size_t)(b * (H + 2) + y + 1) * (W + 2) + xx + 1) * ct + c_off + g * cpg + c);
+    s += v; ss += v * v;
+    if (++cnt == 64) { ds += s; dss += ss; s = ss = 0.f; cnt = 0; }   // bound the fp32 run length
+  }
+  ds += s; dss += ss;
+  ds = block_sum(ds, sh);
+  dss = block_sum(dss, sh);
+  if (threadIdx.x == 0) {
+    const double mean = ds / (double)n;
+    double var = dss / (double)n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    stats[2 * blockIdx.x] = (float)mean;
+    stats[2 * blockIdx.x + 1] = (float)(1.0 / sqrt(var + (double)eps));
+  }
+}
+
+// thread = one (padded pixel, channel): y = act((x - mean) * rstd * gamma + beta) + temb[b][c] + res; ring per `border`.
+template <typename T>
+__global__ void gn_apply_kernel(SrdGroupNormArgs a) {
+  const int Hp = a.H + 2, Wp = a.W + 2, C = a.C, cpg = a.C / a.groups;
+  const T* src = static_cast<const T*>(a.src);
+  const T* res = static_cast<const T*>(a.res);
+  T* out = static_cast<T*>(a.out);
+  const long long total = (long long)a.B * Hp * Wp * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C);
+    const long long pp = i / C;
+    const int xp = (int)(pp % Wp), yp = (int)((pp / Wp) % Hp), b = (int)(pp / ((long long)Wp * Hp));
+    int y = yp - 1, x = xp - 1;
+    const bool ring = (y < 0 || y >= a.H || x < 0 || x >= a.W);
+    float v = 0.f;
+    if (!ring || a.border == SRD_BORDER_REFLECT) {
+      if (y < 0) y = 1; if (y >= a.H) y = a.H - 2;
+      if (x < 0) x = 1; if (x >= a.W) x = a.W - 2;
+      const size_t pix = (size_t)(b * Hp + y + 1) * Wp + x + 1;
+      const float* st = a.stats + 2 * (b * a.groups + c / cpg);
+      v = Elem<T>::ld(src + pix * a.src_ct + a.src_coff + c);
+      v = (v - st[0]) * st[1] * a.gamma[c] + a.beta[c];
+      if (a.act == SRD_ACT_MISH) v = mish_precise(v);
+      else if (a.act == SRD_ACT_LRELU02) v = v > 0.f ? v : 0.2f * v;
+      if (a.temb) v += a.temb[(size_t)b * a.temb_bstride + c];
+      if (res) v += Elem<T>::ld(res + pix * a.res_ct + a.res_coff + c);
+    }
+    Elem<T>::st(out + (size_t)pp * a.out_ct + a.out_coff + c, v);
+  }
+}
+
+// ---------------------------------------------------------------------------- time MLP
+// y[b][n] = sum_k f(x[b][k]) * w[n][k] + bias[n], f = Mish when pre_mish (ResnetBlock.mlp :464-468)
+__global__ void linear_kernel(const float* x, const float* w, const float* bias, int B, int K, int N, int pre_mish,
+                              float* y) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * N) return;
+  const int b = i / N, n = i % N;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    float v = x[(size_t)b * K + k];
+    if (pre_mish) v = mish_precise(v);
+    acc = fmaf(v, w[(size_t)n * K + k], acc);
+  }
+  y[i] = acc + (bias ? bias[n] : 0.f);
+}
+
+// ---------------------------------------------------------------------------- SSIM (:146-222)
+// `_ssim`: depthwise Gaussian window (zero padding ws/2) of img, img^2, img1*img2 after x*0.5+0.5; thread = one
+// pixel; each block writes one partial sum of the SSIM map (summed per image by ssim_reduce_kernel).
+__global__ void ssim_map_kernel(const float* img1, const float* img2, int H, int W, int ws, const float* win,
+                                float pre_scale, float pre_shift, int blocks_per_plane, float* partial) {
+  __shared__ double sh[32];
+  const int plane = blockIdx.x / blocks_per_plane, blk = blockIdx.x % blocks_per_plane;
+  const float* p1 = img1 + (size_t)plane * H * W;
+  const float* p2 = img2 + (size_t)plane * H * W;
+  const int half = ws / 2;
+  const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;
+  double acc = 0.0;
+  for (long long i = (long long)blk * blockDim.x + threadIdx.x; i < (long long)H * W;
+       i += (long long)blocks_per_plane * blockDim.x) {
+    const int x = (int)(i % W), y = (int)(i / W);
+    float mu1 = 0.f, mu2 = 0.f, s11 = 0.f, s22 = 0.f, s12 = 0.f;
+    for (int dy = 0; dy < ws; ++dy) {
+      const int yy = y + dy - half;
+      if (yy < 0 || yy >= H) continue;
+      for (int dx = 0; dx < ws; ++dx) {
+        const int xx = x + dx - half;
+        if (xx < 0 || xx >= W) continue;
+        const float w = win[dy] * win[dx];
+        const float a = fmaf(p1[(size_t)yy * W + xx], pre_scale, pre_shift);
+        const float b = fmaf(p2[(size_t)yy * W + xx], pre_scale, pre_shift);
+        mu1 = fmaf(w, a, mu1); mu2 = fmaf(w, b, mu2);
+        s11 = fmaf(w, a * a, s11); s22 = fmaf(w, b * b, s22); s12 = fmaf(w, a * b, s12);
+      }
+    }
+    const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+    const float sg1 = s11 - mu1_sq, sg2 = s22 - mu2_sq, sg12 = s12 - mu12;
+    const float v = ((2.f * mu12 + C1) * (2.f * sg12 + C2)) / ((mu1_sq + mu2_sq + C1) * (sg1 + sg2 + C2));
+    acc += (double)v;
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = (float)acc;
+}
+
+__global__ void ssim_reduce_kernel(const float* partial, int per_image, double inv_count, float* out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < per_image; i += blockDim.x) acc += (double)partial[(size_t)blockIdx.x * per_image + i];
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) out[blockIdx.x] = (float)(acc * inv_count);
+}
+
+// ---------------------------------------------------------------------------- PSNR (Measure :1503-1542)
+// np.round((x + 1) * 127.5).clip(0, 255).astype(np.uint8): fp32 arithmetic, round-half-even
+__global__ void f32_to_u8_round_kernel(const float* x, long long n, uint8_t* out) {
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float v = rintf(__fmul_rn(__fadd_rn(x[i], 1.f), 127.5f));
+    v = fminf(fmaxf(v, 0.f), 255.f);
+    out[i] = (uint8_t)v;
+  }
+}
+
+// exact integer sum of squared differences of two uint8 arrays (one 64-bit atomic per block)
+__global__ void sq_err_u8_kernel(const uint8_t* a, const uint8_t* b, long long n, unsigned long long* out) {
+  unsigned long long acc = 0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    const int d = (int)a[i] - (int)b[i];
+    acc += (unsigned long long)(d * d);
+  }
+  for (int o = 16; o > 0; o >>= 1) acc += __shfl_down_sync(0xffffffffu, acc, o);
+  if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
+}
+
+}  // namespace srd
+
+using namespace srd;
+
+extern "C" {
+
+int srd_groupnorm_act(const SrdGroupNormArgs* args, void* stream) {
+  SRD_CHECK(args, "srd_groupnorm_act: null args");
+  const SrdGroupNormArgs& a = *args;
+  SRD_CHECK(a.src && a.out && a.gamma && a.beta && a.stats, "srd_groupnorm_act: null pointer");
+  SRD_CHECK(a.src != a.out, "srd_groupnorm_act: in-place is not supported (ring pixels re-read the interior)");
+  SRD_CHECK(a.B > 0 && a.H > 0 && a.W > 0 && a.C > 0 && a.groups > 0 && a.C % a.groups == 0,
+            "srd_groupnorm_act: C (%d) must be a positive multiple of groups (%d)", a.C, a.groups);
+  SRD_CHECK(a.src_coff + a.C <= a.src_ct && a.out_coff + a.C <= a.out_ct && (!a.res || a.res_coff + a.C <= a.res_ct),
+            "srd_groupnorm_act: channel window exceeds the buffer");
+  SRD_CHECK(a.border != SRD_BORDER_REFLECT || (a.H >= 2 && a.W >= 2), "srd_groupnorm_act: reflect needs H,W >= 2");
+  SRD_CHECK(a.dtype == SRD_BF16 || a.dtype == SRD_F32, "srd_groupnorm_act: bad dtype");
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long total = (long long)a.B * (a.H + 2) * (a.W + 2) * a.C;
+  if (a.dtype == SRD_BF16) {
+    gn_stats_kernel<__nv_bfloat16><<<a.B * a.groups, 256, 0, s>>>((const __nv_bfloat16*)a.src, a.src_ct, a.src_coff, a.H,
+                                                                a.W, a.C, a.groups, a.eps, a.stats);
+    gn_apply_kernel<__nv_bfloat16><<<vgrid(total), 256, 0, s>>>(a);
+  } else {
+    gn_stats_kernel<float><<<a.B * a.groups, 256, 0, s>>>((const float*)a.src, a.src_ct, a.src_coff, a.H, a.W, a.C,
+                                                        a.groups, a.eps, a.stats);
+    gn_apply_kernel<float><<<vgrid(total), 256, 0, s>>>(a);
+  }
+  SRD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int srd_linear_f32(const float* x, const float* w, const float* bias, int32_t B, int32_t K, int32_t N,
+                   int32_t pre_mish, float* y, void* stream) {
+  SRD_CHECK(x && w && y && B > 0 && K > 0 && N > 0, "srd_linear_f32: bad arguments");
+  linear_kernel<<<(B * N + 127) / 128, 128, 0, (cudaStream_t)stream>>>(x, w, bias, B, K, N, pre_mish, y);
+  SRD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int srd_ssim_workspace(int32_t B, int32_t C, int32_t H, int32_t W) {
+  (void)H; (void)W;
+  return B * C * 64;     // floats: 64 partial sums per plane
+}
+
+int srd_ssim(const float* img1, const float* img2, int32_t B, int32_t C, int32_t H, int32_t W, int32_t window_size,
+             const float* window1d, float pre_scale, float pre_shift, float* workspace, float* out, void* stream) {
+  SRD_CHECK(img1 && img2 && window1d && workspace && out, "srd_ssim: null pointer");
+  SRD_CHECK(B > 0 && C > 0 && H > 0 && W > 0 && window_size > 0 && (window_size & 1), "srd_ssim: bad shape / even window");
+  const int bpp = 64;
+  ssim_map_kernel<<<B * C * bpp, 256, 0, (cudaStream_t)stream>>>(img1, img2, H, W, window_size, window1d, pre_scale,
+                                                               pre_shift, bpp, workspace);
+  ssim_reduce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(workspace, C * bpp, 1.0 / ((double)C * H * W), out);
+  SRD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int srd_f32_to_u8_round(const float* x, int64_t n, uint8_t* out, void* stream) {
+  SRD_CHECK(x && out && n >= 0, "srd_f32_to_u8_round: bad arguments");
+  if (n == 0) return 0;
+  f32_to_u8_round_kernel<<<vgrid(n), 256, 0, (cudaStream_t)stream>>>(x, n, out);
+  SRD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int srd_sq_err_u8(const uint8_t* a, const uint8_t* b, int64_t n, uint64_t* out_sum, void* stream) {
+  SRD_CHECK(a && b && out_sum && n >= 0, "srd_sq_err_u8: bad arguments");
+  SRD_CUDA(cudaMemsetAsync(out_sum, 0, sizeof(uint64_t), (cudaStream_t)stream));
+  if (n == 0) return 0;
+  sq_err_u8_kernel<<<vgrid(n), 256, 0, (cudaStream_t)stream>>>(a, b, n, (unsigned long long*)out_sum);
+  SRD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+}  // extern "C"

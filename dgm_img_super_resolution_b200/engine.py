@@ -300,7 +300,7 @@ class Builder:
             d.kernel = L.KERNEL_TC
         elif dual is not None:
             assert not pw.transposed and pw.ksize == 3 and pw.stride == 1
-            wd, wt, bias, bias2 = pw.get_dual([s[2] for s in srcs], dual[0].weight, dual[0].bias)
+            wd, wt, bias, bias2 = pw.get_dual([s[2] for s in srcs], eff_weight(dual[0]), dual[0].bias)
             d.N2, d.bias2 = pw.N, bias2.data_ptr()
             d.dst2, d.dst2_ct, d.dst2_coff = dual[1].ptr, dual[1].ct, 0
             d.kernel = L.KERNEL_TC
@@ -368,6 +368,26 @@ class Builder:
                                             act_buf.H, act_buf.W, out.data_ptr(), _stream()), "srd_act_to_nchw")
         self.ops.append(FnOp(f, (act_buf, out)))
 
+    def groupnorm(self, src, C_, gn, out, act=L.ACT_MISH, temb_off=None, temb_bstride=0, res=None,
+                  border=L.BORDER_KEEP):
+        """out = act(GroupNorm(src)) + temb + res (`Block` :448-454 + ResnetBlock adds :474-480); gn: nn.GroupNorm."""
+        assert (src.B, src.H, src.W) == (out.B, out.H, out.W) and src is not out
+        gamma, beta = gn.weight.detach().float().contiguous(), gn.bias.detach().float().contiguous()
+        stats = torch.empty(2 * src.B * gn.num_groups, dtype=torch.float32, device=self.device)
+        a = L.SrdGroupNormArgs()
+        a.src, a.src_ct, a.src_coff, a.dtype = src.ptr, src.ct, 0, self.prec.dtype
+        a.out, a.out_ct, a.out_coff = out.ptr, out.ct, 0
+        a.B, a.H, a.W, a.C, a.groups = src.B, src.H, src.W, C_, gn.num_groups
+        a.act, a.border, a.eps, a.temb_bstride = act, border, gn.eps, temb_bstride
+        a.gamma, a.beta, a.stats = gamma.data_ptr(), beta.data_ptr(), stats.data_ptr()
+        if res is not None:
+            a.res, a.res_ct, a.res_coff = res[0].ptr, res[0].ct, res[1]
+
+        def f(ctx):
+            a.temb = (ctx.temb_ptr + 4 * temb_off) if temb_off is not None else None
+            L.check(L.lib().srd_groupnorm_act(C.byref(a), _stream()), "srd_groupnorm_act")
+        self.ops.append(FnOp(f, (src, out, gamma, beta, stats, res)))
+
     def upsample2x(self, src, dst):
         def f(ctx):
             L.check(L.lib().srd_upsample_nearest2x(src.ptr, dst.ptr, self.prec.dtype, src.B, src.H, src.W,
@@ -379,9 +399,32 @@ class Builder:
 # --------------------------------------------------------------------------------------------
 # layer programs (mirror the reference's module graph; see model.py for the modules)
 # --------------------------------------------------------------------------------------------
+def eff_weight(module):
+    """The weight a conv module computes with.  Under torch.nn.utils.weight_norm (`Unet.apply_weight_norm`
+    :808-814) that is g * v / ||v|| (norm over every dim but 0): `module.weight` itself is only refreshed by
+    nn.Conv2d's own forward pre-hook, which this package never runs, so it is folded here -- once per (g, v)
+    version, the folded tensor is cached on the module."""
+    g, v = getattr(module, "weight_g", None), getattr(module, "weight_v", None)
+    if g is None or v is None:
+        return module.weight
+    sig = (g.data_ptr(), g._version, v.data_ptr(), v._version)
+    hit = module.__dict__.get("_srd_wn")
+    if hit is None or hit[0] != sig:
+        w = torch._weight_norm(v.detach().float(), g.detach().float(), 0).contiguous()
+        hit = (sig, w)
+        module.__dict__["_srd_wn"] = hit
+    return hit[1]
+
+
 def _pc(module, attr="_srd_pack", **kw):
     """PackedConv attached to an nn.Conv2d / nn.ConvTranspose2d (cached on the module)."""
     p = module.__dict__.get(attr)
+    if getattr(module, "weight_g", None) is not None:
+        w = eff_weight(module)
+        if p is None or p.weight is not w or p.bias_p is not module.bias:
+            p = PackedConv(w, module.bias, transposed=False, stride=module.stride[0])
+            module.__dict__[attr] = p
+        return p
     if p is None or p.weight is not module.weight or p.bias_p is not module.bias:
         transposed = isinstance(module, torch.nn.ConvTranspose2d)
         stride = 1 if transposed else module.stride[0]
@@ -390,36 +433,54 @@ def _pc(module, attr="_srd_pack", **kw):
     return p
 
 
-def build_resnet(bld, blk, srcs, dim_out, out, border, temb_off, temb_bstride=0, extra_res=None):
+def build_resnet(bld, blk, srcs, dim_out, out, border, temb_off, temb_bstride=0, extra_res=None, mid_res=None):
     """ResnetBlock.forward :473-480.  srcs = K sources of the block input x (a list => fused concat).
     Returns `out` (Act with dim_out channels).  extra_res: (Act, c_off, beta) added at the tail
-    (`x + cond` :830)."""
+    (`x + cond` :830); mid_res: (Act, c_off, beta) added between block1 and block2 (`h += cond` :478)."""
     a0 = srcs[0][0]
     B, H, W = a0.B, a0.H, a0.W
     cin = sum(s[2] for s in srcs)
     h1 = bld.act(B, H, W, dim_out)
     use_temb = temb_off is not None
+    if len(blk.block1.block) == 4:
+        # GroupNorm variant (`Block` with groups > 0, :448-454): bias-only conv launches, each followed by one
+        # normalise + Mish pass that also carries the adds of :476-480
+        assert extra_res is None and mid_res is None
+        t1, t2 = bld.act(B, H, W, dim_out), bld.act(B, H, W, dim_out)
+        bld.conv(_pc(blk.block1.block[1]), srcs, out=t1, act=L.ACT_NONE, border=L.BORDER_KEEP)
+        bld.groupnorm(t1, dim_out, blk.block1.block[2], h1, temb_off=temb_off,
+                      temb_bstride=temb_bstride if use_temb else 0, border=L.BORDER_REFLECT)
+        bld.conv(_pc(blk.block2.block[1]), [(h1, 0, dim_out)], out=t2, act=L.ACT_NONE, border=L.BORDER_KEEP)
+        if cin != dim_out:
+            r = bld.act(B, H, W, dim_out)
+            bld.conv(_pc(blk.res_conv), srcs, out=r, act=L.ACT_NONE, border=L.BORDER_KEEP)
+            res = (r, 0)
+        else:
+            assert len(srcs) == 1
+            res = (srcs[0][0], srcs[0][1])
+        bld.groupnorm(t2, dim_out, blk.block2.block[2], out, res=res, border=border)
+        return out
     # Few-channel input (the Unet's first block, 3 -> 64) on the tcgen05 path: block1 reads the 8-channel
     # buffer through 8-pixel windows (K = 3 x 64 instead of 9 x 64), and the 1x1 res_conv (:471,480)
     # is evaluated inside block2's epilogue (3 FMAs per output) instead of a launch of its own.
     packed = (bld.prec.name == "bf16" and len(srcs) == 1 and cin <= 4 and a0.ct == 8 and srcs[0][1] == 0 and
               cin != dim_out and dim_out % 64 == 0 and W % 8 == 0 and (temb_bstride == 0 or not use_temb) and
-              extra_res is None and a0._flat.numel() - a0.t.numel() >= 56)
+              extra_res is None and mid_res is None and a0._flat.numel() - a0.t.numel() >= 56)
     if packed:
         bld.conv(_pc(blk.block1.block[1]), srcs, out=h1, act=L.ACT_MISH, temb_off=temb_off, border=L.BORDER_REFLECT,
                  win8=True)
-        lw = blk.res_conv.weight.detach().float().reshape(dim_out, cin).contiguous()
+        lw = eff_weight(blk.res_conv).detach().float().reshape(dim_out, cin).contiguous()
         lb = blk.res_conv.bias.detach().float().contiguous()
         bld.conv(_pc(blk.block2.block[1]), [(h1, 0, dim_out)], out=out, act=L.ACT_MISH, lin=(a0, lw, cin),
                  temb_static=lb, border=border)
         return out
     # channel-changing block on the tcgen05 path: the 1x1 res_conv is a second output of block1's launch
     # (same activation tiles; SrdConvDesc.N2) when the doubled accumulator still leaves two TMEM stages
-    fused_res = (cin != dim_out and FUSE_RES_CONV and bld.prec.name == "bf16" and dim_out % 64 == 0 and dim_out <= 128 and H >= 4 and
+    fused_res = (cin != dim_out and FUSE_RES_CONV and mid_res is None and bld.prec.name == "bf16" and dim_out % 64 == 0 and dim_out <= 128 and H >= 4 and
                  (temb_bstride == 0 or not use_temb) and all(s[0].ct % 8 == 0 and s[1] % 8 == 0 for s in srcs))
     r = bld.act(B, H, W, dim_out) if cin != dim_out else None
     bld.conv(_pc(blk.block1.block[1]), srcs, out=h1, act=L.ACT_MISH, temb_off=temb_off,
-             temb_bstride=temb_bstride if use_temb else 0, border=L.BORDER_REFLECT,
+             temb_bstride=temb_bstride if use_temb else 0, border=L.BORDER_REFLECT, res1=mid_res,
              dual=(blk.res_conv, r) if fused_res else None)
     if cin != dim_out:
         if not fused_res:
@@ -472,8 +533,7 @@ class UnetProgram:
             x2 = bld.act(B, h, w, d)
             extra = (self.cond, 0, 1.0) if i == 0 else None          # `x = x + cond` :830
             build_resnet(bld, r1, [(x1, 0, d)], d, x2, RB, offs[id(r1)], temb_bstride, extra_res=extra)
-            if i == 0 and hp["res"] and hp["up_input"]:
-                raise NotImplementedError("hparams['up_input']=True is outside the hot path (SURVEY 8f-3)")
+            # (hparams['up_input']: `+ up_proj(img_lr_up)` :831-832 is already part of `cond`, see CondProgram)
             hs.append((x2, d))
             if i < nlev - 1:
                 xd = bld.act(B, h // 2, w // 2, d)
@@ -505,7 +565,7 @@ class UnetProgram:
         fc0, fc1 = unet.final_conv[0].block[1], unet.final_conv[1]
         od = unet._out_dim
         if bld.prec.name == "bf16" and od <= 4:
-            hw = fc1.weight.detach().float().reshape(od, xd_).contiguous()
+            hw = eff_weight(fc1).detach().float().reshape(od, xd_).contiguous()
             hb = fc1.bias.detach().float().contiguous()
             bld.conv(_pc(fc0), [(x, 0, xd_)], out=None, act=L.ACT_MISH, planar=self.eps, planar_c=od,
                      head=(hw, hb))
@@ -602,6 +662,21 @@ class CondProgram:
                 "cond_dim / rrdb_num_feat / rrdb_num_block mismatch" % (cin_total, sum(cins), len(sel), cins[0]))
         self.cond = bld.act(a0.B, a0.H * S, a0.W * S, unet._dims[1])
         bld.conv(_pc(unet.cond_proj), [(a, 0, c) for a, c in zip(sel, cins)], out=self.cond, border=L.BORDER_KEEP)
+        # hparams['up_input'] (:803-806, 831-832): x = x + cond + up_proj(img_lr_up) -- time-invariant as well, so
+        # it is folded into the cached cond tensor.  `lr_up` (3 channels, reflect ring) is filled by the caller.
+        self.lr_up = None
+        from . import model as M
+        if M.hparams['res'] and M.hparams['up_input']:
+            self.lr_up = bld.act(a0.B, a0.H * S, a0.W * S, 3)
+            raw, self.cond = self.cond, bld.act(a0.B, a0.H * S, a0.W * S, unet._dims[1])
+            bld.conv(_pc(unet.up_proj[1]), [(self.lr_up, 0, 3)], out=self.cond, res1=(raw, 0, 1.0),
+                     border=L.BORDER_KEEP)
+
+    def load_lr_up(self, img_lr_up):
+        """img_lr_up: fp32 NCHW [B, 3, H, W] (only when the Unet has `up_proj`)."""
+        a = self.lr_up
+        L.check(L.lib().srd_nchw_to_act(img_lr_up.data_ptr(), a.B, 3, a.H, a.W, 1.0, 0.0, a.ptr, a.ct,
+                                        self.bld.prec.dtype, L.BORDER_REFLECT, _stream()), "srd_nchw_to_act")
 
     def run(self):
         self.bld.run()
@@ -699,13 +774,16 @@ class SamplerPlan:
         self.noise_buf = None
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)   # Philox seed, read by the kernels
         self.graphs = {}
-        self.sig = (params_signature(diffusion), self.T, hp["res_rescale"], hp["clip_input"])
+        self.sig = (params_signature(diffusion), self.T, hp["res_rescale"], hp["clip_input"], bool(hp["res"]),
+                    bool(hp["up_input"]))
 
     # ---- pieces -----------------------------------------------------------------------------
     def encode(self):
         """RRDB encoder + cond_proj: once per image (cached across all T steps)."""
         self.rrdb_prog.load_input(self.img_lr)
         self.rrdb_prog.run()
+        if self.cond_prog.lr_up is not None:
+            self.cond_prog.load_lr_up(self.img_lr_up)
         self.cond_prog.run()
 
     def load_x(self):

@@ -37,6 +37,21 @@ class Runtime:
 runtime = Runtime()
 
 
+def initialize_weights(net_l, scale=0.1):
+    """:78-95 -- parameter initialisation only (host side): fan-in Kaiming normal scaled by `scale` with zero biases
+    for Conv2d / Linear, unit weight and zero bias for BatchNorm2d."""
+    for net in (net_l if isinstance(net_l, list) else [net_l]):
+        for m in net.modules():
+            if isinstance(m, (nn.Conv2d, nn.Linear)):
+                nn.init.kaiming_normal_(m.weight, a=0, mode='fan_in')
+                m.weight.data *= scale
+                if m.bias is not None:
+                    m.bias.data.zero_()
+            elif isinstance(m, nn.BatchNorm2d):
+                nn.init.constant_(m.weight, 1)
+                nn.init.constant_(m.bias.data, 0.0)
+
+
 def exists(x):
     return x is not None
 
@@ -68,7 +83,7 @@ class SinusoidalPosEmb(nn.Module):
         self.dim = dim
 
 
-def _run_single(x, build):
+def _run_single(x, build, ctx=None):
     """Stand-alone forward of a sub-module: NCHW fp32 in -> program -> NCHW fp32 out."""
     E._require_cuda(x, "input")
     x = x.contiguous().float()
@@ -77,18 +92,21 @@ def _run_single(x, build):
     out_act, out_c = build(bld, x, B, C_, H, W)
     out = torch.empty((B, out_c, out_act.H, out_act.W), dtype=torch.float32, device=x.device)
     bld.act_to_nchw(out_act, 0, out_c, out)
-    bld.run()
+    bld.run(ctx)
     return out
 
 
 class Block(nn.Module):
-    """:439-457 (groups == 0 only: the config hard-wires it, :757)."""
+    """:439-457.  groups == 0 (what the Unet hard-wires, :757): ReflectionPad2d, Conv2d, Mish -- one fused launch.
+    groups > 0: a GroupNorm between conv and Mish (:448-454) -- bias-only conv launch + srd_groupnorm_act."""
 
     def __init__(self, dim, dim_out, groups=8):
         super().__init__()
-        if groups != 0:
-            raise NotImplementedError("GroupNorm Block (gn_groups > 0) is outside the hot path (SURVEY 8f-3)")
-        self.block = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(dim, dim_out, 3), Mish())
+        if groups == 0:
+            self.block = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(dim, dim_out, 3), Mish())
+        else:
+            self.block = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(dim, dim_out, 3),
+                                       nn.GroupNorm(groups, dim_out), Mish())
 
     def forward(self, x):
         conv = self.block[1]
@@ -97,7 +115,12 @@ class Block(nn.Module):
             xin = bld.act(B, H, W, C_)
             bld.nchw_to_act(lambda: x, xin, C_, border=L.BORDER_REFLECT)
             out = bld.act(B, H, W, conv.out_channels)
-            bld.conv(E._pc(conv), [(xin, 0, C_)], out=out, act=L.ACT_MISH)
+            if len(self.block) == 4:
+                tmp = bld.act(B, H, W, conv.out_channels)
+                bld.conv(E._pc(conv), [(xin, 0, C_)], out=tmp, act=L.ACT_NONE)
+                bld.groupnorm(tmp, conv.out_channels, self.block[2], out, act=L.ACT_MISH)
+            else:
+                bld.conv(E._pc(conv), [(xin, 0, C_)], out=out, act=L.ACT_MISH)
             return out, conv.out_channels
         return _run_single(x, build)
 
@@ -115,20 +138,34 @@ class ResnetBlock(nn.Module):
         self._dim, self._dim_out = dim, dim_out
 
     def forward(self, x, time_emb=None, cond=None):
-        if cond is not None:
-            raise NotImplementedError("ResnetBlock(cond=...) is never used by the reference's Unet")
-        if time_emb is not None:
-            raise NotImplementedError(
-                "stand-alone ResnetBlock.forward takes no time_emb: on this path the time embedding is a "
-                "precomputed table consumed by Unet.forward (srd_time_table)")
+        """:473-480.  Stand-alone call: `time_emb` [B, time_emb_dim] goes through `self.mlp` (Mish + Linear, one
+        srd_linear_f32 launch) and is added per sample after block1; `cond` [B, dim_out, H, W] likewise (:478).
+        (Inside Unet.forward the same sum comes from the precomputed time table instead.)"""
+        E._require_cuda(x, "input")
+        temb = None
+        if time_emb is not None and hasattr(self, "mlp"):
+            te = time_emb.contiguous().float()
+            lin = self.mlp[1]
+            w, b = lin.weight.detach().float().contiguous(), lin.bias.detach().float().contiguous()
+            temb = torch.empty((te.shape[0], lin.out_features), dtype=torch.float32, device=x.device)
+            L.check(L.lib().srd_linear_f32(te.data_ptr(), w.data_ptr(), b.data_ptr(), te.shape[0], te.shape[1],
+                                           lin.out_features, 1, temb.data_ptr(), E._stream()), "srd_linear_f32")
+            if temb.shape[0] != x.shape[0]:
+                raise RuntimeError("time_emb must have one row per image")
 
         def build(bld, x, B, C_, H, W):
             xin = bld.act(B, H, W, C_)
             bld.nchw_to_act(lambda: x, xin, C_, border=L.BORDER_REFLECT)
+            mid = None
+            if cond is not None:
+                ca = bld.act(B, H, W, self._dim_out)
+                bld.nchw_to_act(lambda: cond.contiguous().float(), ca, self._dim_out)
+                mid = (ca, 0, 1.0)
             out = bld.act(B, H, W, self._dim_out)
-            E.build_resnet(bld, self, [(xin, 0, C_)], self._dim_out, out, L.BORDER_KEEP, None)
+            E.build_resnet(bld, self, [(xin, 0, C_)], self._dim_out, out, L.BORDER_KEEP,
+                           0 if temb is not None else None, temb_bstride=self._dim_out, mid_res=mid)
             return out, self._dim_out
-        return _run_single(x, build)
+        return _run_single(x, build, E.RunCtx(temb.data_ptr()) if temb is not None else None)
 
 
 class Upsample(nn.Module):
@@ -274,13 +311,30 @@ class Unet(nn.Module):
                 Upsample(dim_in) if not is_last else nn.Identity()]))
         self.final_conv = nn.Sequential(Block(dim, dim, groups=groups), nn.Conv2d(dim, out_dim, 1))
         if hparams['res'] and hparams['up_input']:
-            raise NotImplementedError("up_input=True is outside the hot path (SURVEY 8f-3)")
+            self.up_proj = nn.Sequential(nn.ReflectionPad2d(1), nn.Conv2d(3, dim, 3))      # :803-806
         if hparams['use_wn']:
-            raise NotImplementedError("use_wn=True is outside the hot path (SURVEY 8f-3)")
+            self.apply_weight_norm()
         if hparams['weight_init']:
-            raise NotImplementedError("weight_init=True is a training-time option outside the hot path")
+            self.apply(initialize_weights)
         self._dim, self._dims, self._out_dim, self._cond_dim = dim, dims, out_dim, cond_dim
         self._progs = {}
+
+    def apply_weight_norm(self):
+        """:808-814: weight_norm on every Conv1d / Conv2d (not the transposed convs, not the Linears) -- the state
+        dict then carries `weight_g` / `weight_v`; the engine folds them when it packs (engine.eff_weight)."""
+        def _apply_weight_norm(m):
+            if isinstance(m, (torch.nn.Conv1d, torch.nn.Conv2d)):
+                torch.nn.utils.weight_norm(m)
+        self.apply(_apply_weight_norm)
+
+    def make_generation_fast_(self):
+        """:849-856"""
+        def remove_weight_norm(m):
+            try:
+                nn.utils.remove_weight_norm(m)
+            except ValueError:      # this module didn't have weight norm
+                return
+        self.apply(remove_weight_norm)
 
     def resnet_blocks(self):
         """Fixed order used for the columns of the time table."""
@@ -301,7 +355,7 @@ class Unet(nn.Module):
         dev = x.device
         sel = cond[2::3]
         key = (B, H, W, runtime.precision, str(dev), E.params_signature(self),
-               tuple(tuple(f.shape) for f in sel))
+               tuple(tuple(f.shape) for f in sel), bool(hparams['res'] and hparams['up_input']))
         p = self._progs.get("p")
         if p is None or p[0] != key:
             bld = E.Builder(dev, runtime.precision)
@@ -318,6 +372,8 @@ class Unet(nn.Module):
             fc = f.contiguous().float()
             L.check(L.lib().srd_nchw_to_act(fc.data_ptr(), B, fc.shape[1], a.H, a.W, 1.0, 0.0, a.ptr, a.ct,
                                             bld.prec.dtype, L.BORDER_KEEP, E._stream()), "srd_nchw_to_act")
+        if cprog.lr_up is not None:
+            cprog.load_lr_up(img_lr_up.contiguous().float())
         cprog.run()
         L.check(L.lib().srd_nchw_to_act(x.data_ptr(), B, x.shape[1], H, W, 1.0, 0.0, uprog.xin.ptr, uprog.xin.ct,
                                         bld.prec.dtype, L.BORDER_REFLECT, E._stream()), "srd_nchw_to_act")
@@ -576,3 +632,86 @@ class GaussianDiffusion(nn.Module):
         if save_intermediate:
             return img, rrdb_out, images
         return img, rrdb_out
+
+
+# ------------------------------------------------------------------------------------------ checkpoints
+# the upstream LeiaLi/SRDiff checkpoint format (:1405-1496): `{work_dir}/model_ckpt_steps_{N}.ckpt`
+# holding {'global_step', 'optimizer_states', 'state_dict': {'model': <GaussianDiffusion state dict>}} (or a flat
+# state dict with 'model.' prefixes).  Host-side file handling only; the state dict lands in the same nn.Module
+# parameters the engine packs from.
+def get_all_ckpts(work_dir, steps=None):
+    """:1416-1422 -- checkpoint paths, newest (largest step) first."""
+    import glob
+    import re
+    pattern = f'{work_dir}/model_ckpt_steps_*.ckpt' if steps is None else f'{work_dir}/model_ckpt_steps_{steps}.ckpt'
+    return sorted(glob.glob(pattern), key=lambda x: -int(re.findall(r'.*steps\_(\d+)\.ckpt', x)[0]))
+
+
+def get_last_checkpoint(work_dir, steps=None):
+    """:1405-1413"""
+    checkpoint, last_ckpt_path = None, None
+    ckpt_paths = get_all_ckpts(work_dir, steps)
+    if len(ckpt_paths) > 0:
+        last_ckpt_path = ckpt_paths[0]
+        checkpoint = torch.load(last_ckpt_path, map_location='cpu')
+    return checkpoint, last_ckpt_path
+
+
+def load_ckpt(cur_model, ckpt_base_dir, model_name='model', force=True, strict=True):
+    """:1463-1496 -- load `model_name`'s weights from a checkpoint file or the newest one in a directory."""
+    import os
+    if os.path.isfile(ckpt_base_dir):
+        base_dir = os.path.dirname(ckpt_base_dir)
+        ckpt_path = ckpt_base_dir
+        checkpoint = torch.load(ckpt_base_dir, map_location='cpu')
+    else:
+        base_dir = ckpt_base_dir
+        checkpoint, ckpt_path = get_last_checkpoint(ckpt_base_dir)
+    if checkpoint is None:
+        e_msg = f"| ckpt not found in {base_dir}."
+        if force:
+            assert False, e_msg
+        print(e_msg)
+        return
+    state_dict = checkpoint["state_dict"]
+    if len([k for k in state_dict.keys() if '.' in k]) > 0:
+        state_dict = {k[len(model_name) + 1:]: v for k, v in state_dict.items() if k.startswith(f'{model_name}.')}
+    else:
+        state_dict = state_dict[model_name]
+    if not strict:
+        cur = cur_model.state_dict()
+        unmatched = [k for k, p in state_dict.items() if k in cur and cur[k].shape != p.shape]
+        for k in unmatched:
+            print("| Unmatched keys: ", k, cur[k].shape, state_dict[k].shape)
+            del state_dict[k]
+    cur_model.load_state_dict(state_dict, strict=strict)
+    print(f"| load '{model_name}' from '{ckpt_path}'.")
+
+
+def load_checkpoint(model, optimizer, work_dir):
+    """:1425-1438 -- resume: weights + optimizer state + step counter (0 when the directory has no checkpoint)."""
+    checkpoint, _ = get_last_checkpoint(work_dir)
+    training_step = 0
+    if checkpoint is not None:
+        model.load_state_dict(checkpoint['state_dict']['model'])
+        model.cuda()
+        optimizer.load_state_dict(checkpoint['optimizer_states'][0])
+        training_step = checkpoint['global_step']
+        del checkpoint
+        torch.cuda.empty_cache()
+    else:
+        model.cuda()
+    return training_step
+
+
+def save_checkpoint(model, optimizer, work_dir, global_step, num_ckpt_keep):
+    """:1441-1454 -- same file layout (legacy, non-zipfile serialisation), pruning all but the newest N."""
+    import os
+    ckpt_path = f'{work_dir}/model_ckpt_steps_{global_step}.ckpt'
+    print(f'Step@{global_step}: saving model to {ckpt_path}')
+    checkpoint = {'global_step': global_step, 'optimizer_states': [optimizer.state_dict()],
+                  'state_dict': {'model': model.state_dict()}}
+    torch.save(checkpoint, ckpt_path, _use_new_zipfile_serialization=False)
+    for old_ckpt in get_all_ckpts(work_dir)[num_ckpt_keep:]:
+        os.remove(old_ckpt)
+        print(f'Delete ckpt: {os.path.basename(old_ckpt)}')

@@ -220,6 +220,43 @@ int srd_nchw_to_u8hwc(const float* in, int32_t B, int32_t C, int32_t H, int32_t 
 int srd_tiles(const float* src, float* dst, int32_t n, int32_t C, int32_t nx, int32_t ny, int32_t th,
               int32_t tw, int32_t to_tiles, void* stream);
 
+/* ---- architecture variants and quality metrics (csrc/variant_ops.cu) ---- */
+
+/* GroupNorm variant of `Block` (srdiff/model.py:448-454), applied to the output of a bias-only conv launch:
+ *   out = act(GroupNorm(groups, C)(src)) + temb[b][c] + res      (ResnetBlock.forward :474-480)
+ * on padded NHWC activations of `dtype`; statistics are per (image, group) over (C/groups, H, W), biased variance,
+ * eps inside the square root (nn.GroupNorm).  border = SRD_BORDER_REFLECT fills the ring with the mirrored result
+ * (the next launch is a ReflectionPad2d conv), anything else writes a zero ring.  src != out. */
+typedef struct SrdGroupNormArgs {
+  const void* src; int32_t src_ct, src_coff;
+  int32_t dtype;                          /* SRD_BF16 / SRD_F32 of src, res and out */
+  void* out; int32_t out_ct, out_coff;
+  int32_t B, H, W, C, groups;
+  int32_t act, border;
+  float eps; int32_t temb_bstride;        /* temb row stride (floats) per image; 0 = one row for all */
+  const float* gamma; const float* beta;  /* [C] GroupNorm weight / bias */
+  const float* temb;                      /* optional [B][temb_bstride] or [C] */
+  const void* res; int32_t res_ct, res_coff;
+  int32_t reserved;
+  float* stats;                           /* workspace, 2 * B * groups floats (mean, rstd) */
+} SrdGroupNormArgs;
+int srd_groupnorm_act(const SrdGroupNormArgs* args, void* stream);
+/* y[B][N] = f(x[B][K]) . w[N][K]^T + bias[N], f = Mish when pre_mish: the ResnetBlock time MLP
+ * `Sequential(Mish(), Linear(time_emb_dim, dim_out))` (:464-468) for stand-alone block calls. */
+int srd_linear_f32(const float* x, const float* w, const float* bias, int32_t B, int32_t K, int32_t N,
+                   int32_t pre_mish, float* y, void* stream);
+/* torch SSIM (:146-222): per-image mean of the SSIM map of fp32 NCHW images after x*pre_scale + pre_shift
+ * (`SSIM.forward` uses 0.5 / 0.5, the functional `ssim()` 1 / 0), depthwise window window1d (x) window1d with
+ * zero padding window_size/2.  out: [B] floats; workspace: srd_ssim_workspace(...) floats. */
+int srd_ssim_workspace(int32_t B, int32_t C, int32_t H, int32_t W);
+int srd_ssim(const float* img1, const float* img2, int32_t B, int32_t C, int32_t H, int32_t W,
+             int32_t window_size, const float* window1d, float pre_scale, float pre_shift, float* workspace,
+             float* out, void* stream);
+/* `Measure.measure` (:1503-1542): np.round((x + 1) * 127.5).clip(0, 255).astype(uint8), element order kept ... */
+int srd_f32_to_u8_round(const float* x, int64_t n, uint8_t* out, void* stream);
+/* ... and the exact sum of squared differences of two uint8 arrays (PSNR = 10 log10(255^2 * n / sum)). */
+int srd_sq_err_u8(const uint8_t* a, const uint8_t* b, int64_t n, uint64_t* out_sum, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -26,8 +26,17 @@ def mish(x):
     return x * torch.tanh(F.softplus(x))
 
 
+def _weight(sd, key):
+    """Effective conv weight: plain, or under `torch.nn.utils.weight_norm` (`apply_weight_norm` :808-814, state
+    dict keys weight_g / weight_v) g * v / ||v|| with the norm over every dim but 0."""
+    if (key + ".weight") in sd:
+        return sd[key + ".weight"]
+    v, g = sd[key + ".weight_v"], sd[key + ".weight_g"]
+    return v * (g / v.flatten(1).norm(dim=1).view(-1, 1, 1, 1))
+
+
 def _conv(sd, key, x, stride=1, padding=0):
-    return F.conv2d(x, sd[key + ".weight"], sd[key + ".bias"], stride=stride, padding=padding)
+    return F.conv2d(x, _weight(sd, key), sd[key + ".bias"], stride=stride, padding=padding)
 
 
 def _rpad(x):
@@ -155,9 +164,26 @@ def time_embedding(sd, time, dim, prefix="denoise_fn."):
     return F.linear(mish(h), sd[prefix + "mlp.2.weight"], sd[prefix + "mlp.2.bias"])
 
 
-def _block(sd, p, x):
-    """`Block` (groups == 0 branch) :442-447,456-457: reflect-pad, conv3x3, Mish."""
-    return mish(_conv(sd, p + "block.1", _rpad(x)))
+def _block(sd, p, x, groups=0):
+    """`Block` :439-457: reflect-pad, conv3x3, [GroupNorm(groups) when groups > 0 :448-454], Mish."""
+    h = _conv(sd, p + "block.1", _rpad(x))
+    if groups:
+        h = F.group_norm(h, groups, sd[p + "block.2.weight"], sd[p + "block.2.bias"], eps=1e-5)
+    return mish(h)
+
+
+def resnet_block(sd, p, x, time_emb=None, cond=None, groups=0):
+    """Stand-alone `ResnetBlock.forward(x, time_emb, cond)` :473-480 (the caller's `time_emb` goes through
+    `self.mlp` = Mish + Linear :464-468)."""
+    h = _block(sd, p + "block1.", x, groups)
+    if time_emb is not None:
+        h = h + F.linear(mish(time_emb), sd[p + "mlp.1.weight"], sd[p + "mlp.1.bias"])[:, :, None, None]
+    if cond is not None:
+        h = h + cond
+    h = _block(sd, p + "block2.", h, groups)
+    if (p + "res_conv.bias") in sd:
+        return h + _conv(sd, p + "res_conv", x)
+    return h + x
 
 
 def _resnet(sd, p, x, temb):
@@ -165,17 +191,17 @@ def _resnet(sd, p, x, temb):
     h = _block(sd, p + "block1.", x)
     h = h + F.linear(mish(temb), sd[p + "mlp.1.weight"], sd[p + "mlp.1.bias"])[:, :, None, None]
     h = _block(sd, p + "block2.", h)
-    if (p + "res_conv.weight") in sd:
+    if (p + "res_conv.bias") in sd:
         return h + _conv(sd, p + "res_conv", x)
     return h + x
 
 
-def unet_forward(sd, x, time, cond_feas, hp, prefix="denoise_fn.", taps=None):
+def unet_forward(sd, x, time, cond_feas, hp, prefix="denoise_fn.", taps=None, img_lr_up=None):
     """`Unet.forward` :820-847.  `cond_feas` is the RRDB feature list; `taps`, if a dict,
     receives intermediate activations (test instrumentation only)."""
     dim = sd[prefix + "mlp.2.weight"].shape[0]
     n_levels = 0
-    while (prefix + "downs.%d.0.block1.block.1.weight" % n_levels) in sd:
+    while (prefix + "downs.%d.0.block1.block.1.bias" % n_levels) in sd:
         n_levels += 1
     temb = time_embedding(sd, time.float(), dim, prefix)
     s = hp["sr_scale"]
@@ -188,6 +214,8 @@ def unet_forward(sd, x, time, cond_feas, hp, prefix="denoise_fn.", taps=None):
         x = _resnet(sd, p + "1.", x, temb)
         if i == 0:
             x = x + cond
+            if hp["res"] and hp["up_input"]:             # :831-832
+                x = x + _conv(sd, prefix + "up_proj.1", _rpad(img_lr_up))
         hs.append(x)
         if i < n_levels - 1:                         # `Downsample` :494-503
             x = _conv(sd, p + "2.conv.1", _rpad(x), stride=2)
@@ -258,7 +286,7 @@ def sample(sd, sched, hp, img_lr, img_lr_up, noises, record=None):
         raise NotImplementedError("use_rrdb=False is outside the hot path")
     for k, i in enumerate(reversed(range(T))):
         t = torch.full((b,), i, dtype=torch.long)
-        eps = unet_forward(sd, x, t, cond, hp)
+        eps = unet_forward(sd, x, t, cond, hp, img_lr_up=img_lr_up)
         x, x0 = p_sample_update(sched, x, t, eps, noises[1 + k])
         if record is not None:
             record.setdefault("eps", []).append(eps)
@@ -353,3 +381,36 @@ def psnr(a, b, peak=2.0):
     """PSNR for images in [-1, 1] (peak-to-peak 2)."""
     mse = float(((a.double() - b.double()) ** 2).mean())
     return float("inf") if mse == 0 else 10.0 * math.log10(peak * peak / mse)
+
+
+# ----------------------------------------------------------------------------- SURVEY 8f-4: metrics
+def ssim_torch(img1, img2, window_size=11, size_average=True, map01=True):
+    """`SSIM.forward` :196-209 (map01: img * 0.5 + 0.5 first) / functional `ssim` :212-221 + `_ssim` :161-182."""
+    if map01:
+        img1, img2 = img1 * 0.5 + 0.5, img2 * 0.5 + 0.5
+    ch = img1.shape[1]
+    g = torch.Tensor([math.exp(-(x - window_size // 2) ** 2 / float(2 * 1.5 ** 2)) for x in range(window_size)])
+    g = (g / g.sum()).unsqueeze(1)
+    window = g.mm(g.t()).float().unsqueeze(0).unsqueeze(0).expand(ch, 1, window_size, window_size).contiguous()
+    pad = window_size // 2
+    mu1 = F.conv2d(img1, window, padding=pad, groups=ch)
+    mu2 = F.conv2d(img2, window, padding=pad, groups=ch)
+    mu1_sq, mu2_sq, mu1_mu2 = mu1.pow(2), mu2.pow(2), mu1 * mu2
+    s1 = F.conv2d(img1 * img1, window, padding=pad, groups=ch) - mu1_sq
+    s2 = F.conv2d(img2 * img2, window, padding=pad, groups=ch) - mu2_sq
+    s12 = F.conv2d(img1 * img2, window, padding=pad, groups=ch) - mu1_mu2
+    C1, C2 = 0.01 ** 2, 0.03 ** 2
+    m = ((2 * mu1_mu2 + C1) * (2 * s12 + C2)) / ((mu1_sq + mu2_sq + C1) * (s1 + s2 + C2))
+    return m.mean() if size_average else m.mean(1).mean(1).mean(1)
+
+
+def to_uint8_round(img):
+    """`Measure.measure` :1516-1518: np.round((img + 1) * 127.5).clip(0, 255).astype(np.uint8)."""
+    return np.round((img.numpy() + 1) * 127.5).clip(min=0, max=255).astype(np.uint8)
+
+
+def psnr_u8(a, b):
+    """`Measure.psnr` :1541-1542 = skimage.metrics.peak_signal_noise_ratio(a, b, data_range=255) (scikit-image, not
+    vendored by the reference and absent here; published definition: 10 log10(R^2 / mean((a - b)^2)) in float64)."""
+    err = np.mean((a.astype(np.float64) - b.astype(np.float64)) ** 2, dtype=np.float64)
+    return float("inf") if err == 0 else 10 * np.log10((255 ** 2) / err)

@@ -11,6 +11,6 @@ ARCH="-gencode arch=compute_100a,code=sm_100a"
 for spec in "$@"; do
   name="${spec%%=*}"; flags="${spec#*=}"
   $NVCC $flags -O3 -std=c++17 -lineinfo $ARCH -Xcompiler -fPIC --expt-relaxed-constexpr -Xptxas -v -c conv_tc.cu -o ../variants/conv_tc_$name.o 2>&1 | grep -E "error|Used|spill" | grep -A1 -B1 conv_tc | head -4 || true
-  $NVCC $ARCH -shared -o ../variants/lib_$name.so api.o conv_direct.o elementwise.o image_ops.o ../variants/conv_tc_$name.o -cudart static
+  $NVCC $ARCH -shared -o ../variants/lib_$name.so api.o conv_direct.o elementwise.o image_ops.o variant_ops.o ../variants/conv_tc_$name.o -cudart static
   echo "built variants/lib_$name.so ($flags)"
 done
