@@ -105,6 +105,7 @@ SYMBOLS = {
     "srd_nchw_to_u8hwc": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "srd_tiles": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp]),
     "srd_groupnorm_act": (C.c_int, [C.POINTER(SrdGroupNormArgs), _vp]),
+    "srd_linear_attention": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _i32, _i32, _vp]),
     "srd_linear_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "srd_ssim_workspace": (C.c_int, [_i32, _i32, _i32, _i32]),
     "srd_ssim": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _f, _f, _vp, _vp, _vp]),

@@ -91,6 +91,81 @@ __global__ void gn_apply_kernel(SrdGroupNormArgs a) {
   }
 }
 
+// ---------------------------------------------------------------------------- LinearAttention core (:514-522)
+// qkv: padded NHWC activation with 3 * heads * D channels ordered (qkv, head, d) -- the reference's
+// 'b (qkv heads c) h w'.  Per (image, head): k <- softmax over the n = H*W positions; context[d][e] = sum_n k[d][n] *
+// v[e][n]; out[e][n] = sum_d context[d][e] * q[d][n], written to channel head*D + e.  One block per (image, head), D = 32.
+template <typename T>
+__global__ void linear_attention_kernel(const T* qkv, int ct, int c_off, int H, int W, int heads, T* out, int out_ct,
+                                        int out_coff) {
+  constexpr int D = 32, TN = 32;
+  __shared__ float s_max[D], s_inv[D], s_ctx[D][D + 1], s_k[TN][D + 1], s_v[TN][D + 1];
+  const int b = blockIdx.x / heads, hd = blockIdx.x % heads;
+  const int n = H * W, Wp = W + 2;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarp = blockDim.x >> 5;
+  const size_t img = (size_t)b * (H + 2) * Wp;
+  auto pix = [&](int i) { return img + (size_t)(i / W + 1) * Wp + (i % W) + 1; };
+  const int kq = c_off + hd * D, kk = c_off + (heads + hd) * D, kv = c_off + (2 * heads + hd) * D;
+  // row statistics of k: lane = channel d, warps stride over the positions
+  float m = -INFINITY;
+  for (int i = warp; i < n; i += nwarp) m = fmaxf(m, Elem<T>::ld(qkv + pix(i) * ct + kk + lane));
+  s_k[warp][lane] = m;
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < nwarp; ++w) m = fmaxf(m, s_k[w][lane]);
+    s_max[lane] = m;
+  }
+  __syncthreads();
+  m = s_max[lane];
+  float sum = 0.f;
+  for (int i = warp; i < n; i += nwarp) sum += expf(Elem<T>::ld(qkv + pix(i) * ct + kk + lane) - m);
+  __syncthreads();
+  s_k[warp][lane] = sum;
+  __syncthreads();
+  if (warp == 0) {
+    for (int w = 1; w < nwarp; ++w) sum += s_k[w][lane];
+    s_inv[lane] = 1.f / sum;
+  }
+  __syncthreads();
+  // context: thread owns (d, e) pairs; positions staged TN at a time
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};     // blockDim.x == 256: 1024 / 256 entries per thread
+  for (int i0 = 0; i0 < n; i0 += TN) {
+    for (int j = threadIdx.x; j < TN * D; j += blockDim.x) {
+      const int p = j / D, c = j % D;
+      float kvv = 0.f, vv = 0.f;
+      if (i0 + p < n) {
+        const size_t base = pix(i0 + p) * ct;
+        kvv = expf(Elem<T>::ld(qkv + base + kk + c) - s_max[c]) * s_inv[c];
+        vv = Elem<T>::ld(qkv + base + kv + c);
+      }
+      s_k[p][c] = kvv; s_v[p][c] = vv;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int r = 0; r < 4; ++r) {
+      const int idx = threadIdx.x + r * 256, d = idx / D, e = idx % D;
+      float a = acc[r];
+      for (int p = 0; p < TN; ++p) a = fmaf(s_k[p][d], s_v[p][e], a);
+      acc[r] = a;
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int r = 0; r < 4; ++r) {
+    const int idx = threadIdx.x + r * 256;
+    s_ctx[idx / D][idx % D] = acc[r];
+  }
+  __syncthreads();
+  // out[e][i]: lane = e, warps stride over the positions
+  for (int i = warp; i < n; i += nwarp) {
+    const size_t base = pix(i);
+    const float qd = Elem<T>::ld(qkv + base * ct + kq + lane);
+    float o = 0.f;
+    for (int d = 0; d < D; ++d) o = fmaf(s_ctx[d][lane], __shfl_sync(0xffffffffu, qd, d), o);
+    Elem<T>::st(out + base * out_ct + out_coff + hd * D + lane, o);
+  }
+}
+
 // ---------------------------------------------------------------------------- time MLP
 // y[b][n] = sum_k f(x[b][k]) * w[n][k] + bias[n], f = Mish when pre_mish (ResnetBlock.mlp :464-468)
 __global__ void linear_kernel(const float* x, const float* w, const float* bias, int B, int K, int N, int pre_mish,
@@ -202,6 +277,24 @@ int srd_groupnorm_act(const SrdGroupNormArgs* args, void* stream) {
                                                         a.groups, a.eps, a.stats);
     gn_apply_kernel<float><<<vgrid(total), 256, 0, s>>>(a);
   }
+  SRD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int srd_linear_attention(const void* qkv, int32_t qkv_ct, int32_t qkv_coff, int32_t dtype, int32_t B, int32_t H,
+                         int32_t W, int32_t heads, int32_t dim_head, void* out, int32_t out_ct, int32_t out_coff,
+                         void* stream) {
+  SRD_CHECK(qkv && out && B > 0 && H > 0 && W > 0 && heads > 0, "srd_linear_attention: bad arguments");
+  SRD_CHECK(dim_head == 32, "srd_linear_attention: dim_head must be 32 (the reference's default), got %d", dim_head);
+  SRD_CHECK(qkv_coff + 3 * heads * dim_head <= qkv_ct && out_coff + heads * dim_head <= out_ct,
+            "srd_linear_attention: channel window exceeds the buffer");
+  SRD_CHECK(dtype == SRD_BF16 || dtype == SRD_F32, "srd_linear_attention: bad dtype");
+  if (dtype == SRD_BF16)
+    linear_attention_kernel<__nv_bfloat16><<<B * heads, 256, 0, (cudaStream_t)stream>>>(
+        (const __nv_bfloat16*)qkv, qkv_ct, qkv_coff, H, W, heads, (__nv_bfloat16*)out, out_ct, out_coff);
+  else
+    linear_attention_kernel<float><<<B * heads, 256, 0, (cudaStream_t)stream>>>((const float*)qkv, qkv_ct, qkv_coff, H, W,
+                                                                              heads, (float*)out, out_ct, out_coff);
   SRD_CUDA(cudaGetLastError());
   return 0;
 }

@@ -388,6 +388,13 @@ class Builder:
             L.check(L.lib().srd_groupnorm_act(C.byref(a), _stream()), "srd_groupnorm_act")
         self.ops.append(FnOp(f, (src, out, gamma, beta, stats, res)))
 
+    def linear_attention(self, qkv, heads, dim_head, out):
+        """`LinearAttention.forward` :514-522 between its 1x1 convs (k softmax over positions, k v^T, context^T q)."""
+        def f(ctx):
+            L.check(L.lib().srd_linear_attention(qkv.ptr, qkv.ct, 0, self.prec.dtype, qkv.B, qkv.H, qkv.W, heads,
+                                                 dim_head, out.ptr, out.ct, 0, _stream()), "srd_linear_attention")
+        self.ops.append(FnOp(f, (qkv, out)))
+
     def upsample2x(self, src, dst):
         def f(ctx):
             L.check(L.lib().srd_upsample_nearest2x(src.ptr, dst.ptr, self.prec.dtype, src.B, src.H, src.W,
@@ -425,10 +432,16 @@ def _pc(module, attr="_srd_pack", **kw):
             p = PackedConv(w, module.bias, transposed=False, stride=module.stride[0])
             module.__dict__[attr] = p
         return p
-    if p is None or p.weight is not module.weight or p.bias_p is not module.bias:
+    bias = module.bias
+    if bias is None:                       # bias-free conv (LinearAttention.to_qkv :511): a cached zero vector
+        bias = module.__dict__.get("_srd_zero_bias")
+        if bias is None or bias.device != module.weight.device:
+            bias = torch.zeros(module.out_channels, dtype=torch.float32, device=module.weight.device)
+            module.__dict__["_srd_zero_bias"] = bias
+    if p is None or p.weight is not module.weight or p.bias_p is not bias:
         transposed = isinstance(module, torch.nn.ConvTranspose2d)
         stride = 1 if transposed else module.stride[0]
-        p = PackedConv(module.weight, module.bias, transposed=transposed, stride=stride)
+        p = PackedConv(module.weight, bias, transposed=transposed, stride=stride)
         module.__dict__[attr] = p
     return p
 
@@ -546,7 +559,15 @@ class UnetProgram:
         m1 = bld.act(B, h, w, d)
         build_resnet(bld, unet.mid_block1, x_src, d, m1, RB, offs[id(unet.mid_block1)], temb_bstride)
         if hp["use_attn"]:
-            raise NotImplementedError("hparams['use_attn']=True is outside the hot path (SURVEY 2 #11)")
+            # mid_attn = Residual(Rezero(LinearAttention)) :788-789,836-837: x + g * to_out(attn(to_qkv(x)))
+            att = unet.mid_attn.fn.fn
+            hidden = att.to_out.in_channels
+            qkv, ao, m1a = bld.act(B, h, w, 3 * hidden), bld.act(B, h, w, hidden), bld.act(B, h, w, d)
+            bld.conv(_pc(att.to_qkv), [(m1, 0, d)], out=qkv, border=RK)
+            bld.linear_attention(qkv, att.heads, hidden // att.heads, ao)
+            bld.conv(_pc(att.to_out), [(ao, 0, hidden)], out=m1a, alpha=float(unet.mid_attn.fn.g.detach().float().item()),
+                     res1=(m1, 0, 1.0), border=RB)
+            m1 = m1a
         m2 = bld.act(B, h, w, d)
         build_resnet(bld, unet.mid_block2, [(m1, 0, d)], d, m2, RB, offs[id(unet.mid_block2)], temb_bstride)
         x, xd_ = m2, d

@@ -168,6 +168,47 @@ class ResnetBlock(nn.Module):
         return _run_single(x, build, E.RunCtx(temb.data_ptr()) if temb is not None else None)
 
 
+class Residual(nn.Module):
+    """:398-404 -- container only; Unet.forward evaluates `fn(x) + x` inside the launch list."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+
+
+class Rezero(nn.Module):
+    """:427-434 -- `fn(x) * g`, g initialised to 0."""
+
+    def __init__(self, fn):
+        super().__init__()
+        self.fn = fn
+        self.g = nn.Parameter(torch.zeros(1))
+
+
+class LinearAttention(nn.Module):
+    """:506-522.  (Upstream's forward needs einops' `rearrange`, which the reference file never imports -- SURVEY Q6;
+    the semantics built here are those of the code with that import present.)"""
+
+    def __init__(self, dim, heads=4, dim_head=32):
+        super().__init__()
+        self.heads = heads
+        hidden_dim = dim_head * heads
+        self.to_qkv = nn.Conv2d(dim, hidden_dim * 3, 1, bias=False)
+        self.to_out = nn.Conv2d(hidden_dim, dim, 1)
+
+    def forward(self, x):
+        def build(bld, x, B, C_, H, W):
+            hidden = self.to_out.in_channels
+            xin = bld.act(B, H, W, C_)
+            bld.nchw_to_act(lambda: x, xin, C_)
+            qkv, ao, out = bld.act(B, H, W, 3 * hidden), bld.act(B, H, W, hidden), bld.act(B, H, W, C_)
+            bld.conv(E._pc(self.to_qkv), [(xin, 0, C_)], out=qkv)
+            bld.linear_attention(qkv, self.heads, hidden // self.heads, ao)
+            bld.conv(E._pc(self.to_out), [(ao, 0, hidden)], out=out)
+            return out, C_
+        return _run_single(x, build)
+
+
 class Upsample(nn.Module):
     """:483-491 ConvTranspose2d(dim, dim, 4, 2, 1)"""
 
@@ -301,7 +342,7 @@ class Unet(nn.Module):
         mid_dim = dims[-1]
         self.mid_block1 = ResnetBlock(mid_dim, mid_dim, time_emb_dim=dim, groups=groups)
         if hparams['use_attn']:
-            raise NotImplementedError("use_attn=True: LinearAttention is outside the hot path (SURVEY 2 #11)")
+            self.mid_attn = Residual(Rezero(LinearAttention(mid_dim)))
         self.mid_block2 = ResnetBlock(mid_dim, mid_dim, time_emb_dim=dim, groups=groups)
         for ind, (dim_in, dim_out) in enumerate(reversed(in_out[1:])):
             is_last = ind >= (num_resolutions - 1)          # never true: three Upsamples

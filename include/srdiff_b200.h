@@ -115,7 +115,8 @@ typedef struct SrdConvPlan SrdConvPlan;
 const char* srd_last_error(void);
 int srd_version(void);
 /* ABI self-check for FFI bindings: which = 0 -> sizeof(SrdConvDesc), 1 -> sizeof(SrdPSampleArgs),
- * 2 -> offsetof(SrdConvDesc, dst2), 3 -> offsetof(SrdPSampleArgs, seed_ptr). */
+ * 2 -> offsetof(SrdConvDesc, dst2), 3 -> offsetof(SrdPSampleArgs, seed_ptr), 4 -> sizeof(SrdGroupNormArgs),
+ * 5 -> offsetof(SrdGroupNormArgs, stats). */
 int srd_abi_sizeof(int32_t which);
 /* 1 if the tcgen05/TMA path can serve this descriptor (bf16, channel/stride alignment...). */
 int srd_conv_tc_supported(const SrdConvDesc* desc);
@@ -241,6 +242,12 @@ typedef struct SrdGroupNormArgs {
   float* stats;                           /* workspace, 2 * B * groups floats (mean, rstd) */
 } SrdGroupNormArgs;
 int srd_groupnorm_act(const SrdGroupNormArgs* args, void* stream);
+/* Core of `LinearAttention.forward` (:514-522) between its two 1x1 convs: qkv holds 3*heads*dim_head channels in
+ * (qkv, head, d) order; k is soft-maxed over the H*W positions, context = k v^T per head, out = context^T q, written
+ * as heads*dim_head channels in (head, d) order.  dim_head must be 32. */
+int srd_linear_attention(const void* qkv, int32_t qkv_ct, int32_t qkv_coff, int32_t dtype, int32_t B, int32_t H,
+                         int32_t W, int32_t heads, int32_t dim_head, void* out, int32_t out_ct, int32_t out_coff,
+                         void* stream);
 /* y[B][N] = f(x[B][K]) . w[N][K]^T + bias[N], f = Mish when pre_mish: the ResnetBlock time MLP
  * `Sequential(Mish(), Linear(time_emb_dim, dim_out))` (:464-468) for stand-alone block calls. */
 int srd_linear_f32(const float* x, const float* w, const float* bias, int32_t B, int32_t K, int32_t N,

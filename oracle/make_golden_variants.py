@@ -72,6 +72,26 @@ def main():
                      "n_wn": sum(1 for m in diff.denoise_fn.modules() if isinstance(m, torch.nn.Conv2d))}
     ref.hparams.update(hp)
 
+    # ---- use_attn (:506-522, 788-789, 836-837).  The reference never imports einops' `rearrange`: the
+    # missing name is supplied here, nothing else is touched.  Rezero's gain starts at 0; it is set to 400 so
+    # that the branch moves eps by several per cent.
+    import einops
+    hpa = dict(hp, use_attn=True)
+    ref, diff = ref_loader.build_reference(hpa, timesteps=2, seed=SEED)
+    ref.rearrange = einops.rearrange
+    with torch.no_grad():
+        diff.denoise_fn.mid_attn.fn.g.fill_(400.0)
+    img_lr, img_lr_up, g = gen_inputs(2, 8, 8, hp["sr_scale"], 61)
+    x = torch.randn((2, 3, 32, 32), generator=g)
+    xa = torch.randn((2, 256, 6, 5), generator=g)
+    t = torch.tensor([0, 1], dtype=torch.long)
+    with torch.no_grad():
+        _, feas = diff.rrdb(img_lr, True)
+        out["use_attn"] = {"img_lr": img_lr, "img_lr_up": img_lr_up, "x": x, "t": t,
+                           "eps": diff.denoise_fn(x, t, feas, img_lr_up),
+                           "xa": xa, "attn": diff.denoise_fn.mid_attn.fn.fn(xa)}
+    ref.hparams.update(hp)
+
     # ---- GroupNorm Block / stand-alone ResnetBlock (:439-480) ----------------------------------------------
     g = torch.Generator().manual_seed(53)
     x = torch.randn((2, 8, 10, 12), generator=g)

@@ -196,6 +196,18 @@ def _resnet(sd, p, x, temb):
     return h + x
 
 
+def linear_attention(sd, p, x, heads=4):
+    """`LinearAttention.forward` :514-522 with einops' rearrange spelled out:
+    'b (qkv heads c) h w -> qkv b heads c (h w)' and back 'b heads c (h w) -> b (heads c) h w'."""
+    b, _, h, w = x.shape
+    qkv = F.conv2d(x, sd[p + "to_qkv.weight"])
+    q, k, v = qkv.reshape(b, 3, heads, -1, h * w).unbind(1)
+    k = k.softmax(dim=-1)
+    context = torch.einsum('bhdn,bhen->bhde', k, v)
+    out = torch.einsum('bhde,bhdn->bhen', context, q).reshape(b, -1, h, w)
+    return _conv(sd, p + "to_out", out)
+
+
 def unet_forward(sd, x, time, cond_feas, hp, prefix="denoise_fn.", taps=None, img_lr_up=None):
     """`Unet.forward` :820-847.  `cond_feas` is the RRDB feature list; `taps`, if a dict,
     receives intermediate activations (test instrumentation only)."""
@@ -222,6 +234,8 @@ def unet_forward(sd, x, time, cond_feas, hp, prefix="denoise_fn.", taps=None, im
         if taps is not None:
             taps["down%d" % i] = x
     x = _resnet(sd, prefix + "mid_block1.", x, temb)
+    if hp["use_attn"]:                               # Residual(Rezero(LinearAttention)) :788-789, 836-837
+        x = linear_attention(sd, prefix + "mid_attn.fn.fn.", x) * sd[prefix + "mid_attn.fn.g"] + x
     x = _resnet(sd, prefix + "mid_block2.", x, temb)
     if taps is not None:
         taps["mid"] = x

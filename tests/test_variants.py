@@ -100,6 +100,25 @@ def test_oracle_weight_norm_matches_fixture_and_state_dict_keys(hp):
         M.hparams.update(hp)
 
 
+def test_oracle_linear_attention_matches_fixture(hp):
+    f = golden("variants.pt")["use_attn"]
+    hpa = dict(hp, use_attn=True)
+    M, diff = build_ours(hpa, timesteps=2)
+    try:
+        with torch.no_grad():
+            diff.denoise_fn.mid_attn.fn.g.fill_(400.0)
+            sd = _sd(diff)
+            assert sd["denoise_fn.mid_attn.fn.fn.to_qkv.weight"].shape == (384, 256, 1, 1)
+            assert "denoise_fn.mid_attn.fn.fn.to_qkv.bias" not in sd
+            assert O.rel_l2(O.linear_attention(sd, "denoise_fn.mid_attn.fn.fn.", f["xa"]), f["attn"]) < 5e-6
+            _, feas = O.rrdb_forward(sd, f["img_lr"], hpa)
+            assert O.rel_l2(O.unet_forward(sd, f["x"], f["t"], feas, hpa), f["eps"]) < 5e-6
+            sd["denoise_fn.mid_attn.fn.g"] = torch.zeros(1)            # the gain matters
+            assert O.rel_l2(O.unet_forward(sd, f["x"], f["t"], feas, hpa), f["eps"]) > 2e-2
+    finally:
+        M.hparams.update(hp)
+
+
 def test_oracle_groupnorm_blocks_match_fixture(hp):
     import dgm_img_super_resolution_b200.model as M
     f = golden("variants.pt")["gn"]
@@ -218,6 +237,30 @@ def test_weight_norm_unet_matches_reference_fixture(hp, prec):
             diff.denoise_fn.final_conv[0].block[1].weight_g.mul_(0.5)
         diff.denoise_fn.make_generation_fast_()
         assert O.rel_l2(diff.denoise_fn(*args).cpu(), f["eps_fast"]) < TOL[prec]
+    finally:
+        M.runtime.precision = "bf16"
+        M.hparams.update(hp)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("prec", ["fp32", "bf16"])
+def test_linear_attention_unet_matches_reference_fixture(hp, prec):
+    hpa = dict(hp, use_attn=True)
+    M, diff = build_ours(hpa, timesteps=2, device=DEV)
+    with torch.no_grad():
+        diff.denoise_fn.mid_attn.fn.g.fill_(400.0)
+    M.runtime.precision = prec
+    f = golden("variants.pt")["use_attn"]
+    try:
+        attn = diff.denoise_fn.mid_attn.fn.fn(f["xa"].to(DEV))
+        assert O.rel_l2(attn.cpu(), f["attn"]) < TOL[prec]
+        _, feas = diff.rrdb(f["img_lr"].to(DEV), True)
+        eps = diff.denoise_fn(f["x"].to(DEV), f["t"].to(DEV), feas, f["img_lr_up"].to(DEV))
+        assert O.rel_l2(eps.cpu(), f["eps"]) < TOL[prec]
+        with torch.no_grad():                                       # Rezero gain is read when the program is built
+            diff.denoise_fn.mid_attn.fn.g.fill_(0.0)
+        eps0 = diff.denoise_fn(f["x"].to(DEV), f["t"].to(DEV), feas, f["img_lr_up"].to(DEV))
+        assert O.rel_l2(eps0.cpu(), f["eps"]) > 2e-2
     finally:
         M.runtime.precision = "bf16"
         M.hparams.update(hp)
