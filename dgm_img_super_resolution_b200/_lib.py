@@ -109,6 +109,8 @@ SYMBOLS = {
     "srd_linear_f32": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp]),
     "srd_ssim_workspace": (C.c_int, [_i32, _i32, _i32, _i32]),
     "srd_ssim": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _i32, _vp, _f, _f, _vp, _vp, _vp]),
+    "srd_resize_dim": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _i32, _i32, _vp, _vp, _i32, _vp, _vp]),
+    "srd_ssim_uniform_u8": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),
     "srd_f32_to_u8_round": (C.c_int, [_vp, _i64, _vp, _vp]),
     "srd_sq_err_u8": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
 }

@@ -249,6 +249,68 @@ __global__ void sq_err_u8_kernel(const uint8_t* a, const uint8_t* b, long long n
   if ((threadIdx.x & 31) == 0 && acc) atomicAdd(out, acc);
 }
 
+
+// ---------------------------------------------------------------------------- imresize (:1162-1306)
+// One separable pass of the MATLAB-compatible resize: out[i] = sum_p weights[i][p] * in[indices[i][p]] along `dim`
+// of an [H][W][C] image, accumulated in float64 like the reference (`imresizevec`); uint8 images are clipped to
+// [0, 255] and rounded half-to-even after EVERY pass (np.around), float64 images are returned as they are.
+template <typename T>
+__global__ void resize_dim_kernel(const T* in, int H, int W, int C, int dim, int out_len, const double* weights,
+                                  const int* indices, int P, T* out) {
+  const int Ho = dim == 0 ? out_len : H, Wo = dim == 1 ? out_len : W;
+  const long long total = (long long)Ho * Wo * C;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), x = (int)((i / C) % Wo), y = (int)(i / ((long long)C * Wo));
+    const int o = dim == 0 ? y : x;
+    double acc = 0.0;
+    for (int p = 0; p < P; ++p) {
+      const int src = indices[(size_t)o * P + p];
+      const size_t at = dim == 0 ? ((size_t)src * W + x) * C + c : ((size_t)y * W + src) * C + c;
+      acc = __dadd_rn(acc, __dmul_rn(weights[(size_t)o * P + p], (double)in[at]));   // no FMA: numpy multiplies, then sums
+    }
+    if (sizeof(T) == 1) out[i] = (T)rint(fmin(fmax(acc, 0.0), 255.0));
+    else out[i] = (T)acc;
+  }
+}
+
+// ---------------------------------------------------------------------------- skimage-style SSIM (Measure.ssim :1537-1539)
+// structural_similarity(a, b, multichannel=True, data_range=255) of scikit-image: uniform 7x7 window, sample
+// covariance (NP / (NP - 1)), float64, mean over the map cropped by (win - 1) / 2, then over channels.
+__global__ void ssim_uniform_u8_kernel(const uint8_t* a, const uint8_t* b, int H, int W, int C, int win, double* partial) {
+  __shared__ double sh[32];
+  const int pad = (win - 1) / 2, Hc = H - 2 * pad, Wc = W - 2 * pad;
+  const double NP = (double)win * win, cov_norm = NP / (NP - 1.0);
+  const double C1 = (0.01 * 255.0) * (0.01 * 255.0), C2 = (0.03 * 255.0) * (0.03 * 255.0);
+  const long long total = (long long)Hc * Wc * C;
+  double acc = 0.0;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int c = (int)(i % C), x = (int)((i / C) % Wc), y = (int)(i / ((long long)C * Wc));
+    double sx = 0, sy = 0, sxx = 0, syy = 0, sxy = 0;
+    for (int dy = 0; dy < win; ++dy)
+      for (int dx = 0; dx < win; ++dx) {
+        const size_t at = ((size_t)(y + dy) * W + x + dx) * C + c;
+        const double p = (double)a[at], q = (double)b[at];
+        sx += p; sy += q; sxx += p * p; syy += q * q; sxy += p * q;
+      }
+    const double ux = sx / NP, uy = sy / NP;
+    const double vx = cov_norm * (sxx / NP - ux * ux), vy = cov_norm * (syy / NP - uy * uy);
+    const double vxy = cov_norm * (sxy / NP - ux * uy);
+    acc += ((2 * ux * uy + C1) * (2 * vxy + C2)) / ((ux * ux + uy * uy + C1) * (vx + vy + C2));
+  }
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) partial[blockIdx.x] = acc;
+}
+
+__global__ void sum_f64_kernel(const double* partial, int n, double scale, double* out) {
+  __shared__ double sh[32];
+  double acc = 0.0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) acc += partial[i];
+  acc = block_sum(acc, sh);
+  if (threadIdx.x == 0) *out = acc * scale;
+}
+
 }  // namespace srd
 
 using namespace srd;
@@ -320,6 +382,35 @@ int srd_ssim(const float* img1, const float* img2, int32_t B, int32_t C, int32_t
   ssim_map_kernel<<<B * C * bpp, 256, 0, (cudaStream_t)stream>>>(img1, img2, H, W, window_size, window1d, pre_scale,
                                                                pre_shift, bpp, workspace);
   ssim_reduce_kernel<<<B, 256, 0, (cudaStream_t)stream>>>(workspace, C * bpp, 1.0 / ((double)C * H * W), out);
+  SRD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int srd_resize_dim(const void* in, int32_t is_u8, int32_t H, int32_t W, int32_t C, int32_t dim, int32_t out_len,
+                   const double* weights, const int32_t* indices, int32_t P, void* out, void* stream) {
+  SRD_CHECK(in && out && weights && indices, "srd_resize_dim: null pointer");
+  SRD_CHECK(H > 0 && W > 0 && C > 0 && out_len > 0 && P > 0 && (dim == 0 || dim == 1), "srd_resize_dim: bad arguments");
+  const long long total = (long long)(dim == 0 ? out_len : H) * (dim == 1 ? out_len : W) * C;
+  if (is_u8)
+    resize_dim_kernel<uint8_t><<<vgrid(total), 256, 0, (cudaStream_t)stream>>>((const uint8_t*)in, H, W, C, dim, out_len,
+                                                                              weights, indices, P, (uint8_t*)out);
+  else
+    resize_dim_kernel<double><<<vgrid(total), 256, 0, (cudaStream_t)stream>>>((const double*)in, H, W, C, dim, out_len,
+                                                                             weights, indices, P, (double*)out);
+  SRD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int srd_ssim_uniform_u8(const uint8_t* a, const uint8_t* b, int32_t H, int32_t W, int32_t C, int32_t win,
+                        double* workspace, double* out, void* stream) {
+  SRD_CHECK(a && b && workspace && out, "srd_ssim_uniform_u8: null pointer");
+  SRD_CHECK(win >= 3 && (win & 1) && H >= win && W >= win && C > 0,
+            "srd_ssim_uniform_u8: win_size (%d) must be odd and not exceed the image (%d x %d)", win, H, W);
+  const int pad = (win - 1) / 2;
+  const long long total = (long long)(H - 2 * pad) * (W - 2 * pad) * C;
+  const int nb = total < 256LL * 512 ? (int)((total + 255) / 256) : 512;      // workspace: 512 doubles
+  ssim_uniform_u8_kernel<<<nb, 256, 0, (cudaStream_t)stream>>>(a, b, H, W, C, win, workspace);
+  sum_f64_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(workspace, nb, 1.0 / (double)total, out);
   SRD_CUDA(cudaGetLastError());
   return 0;
 }

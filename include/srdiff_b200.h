@@ -264,6 +264,18 @@ int srd_f32_to_u8_round(const float* x, int64_t n, uint8_t* out, void* stream);
 /* ... and the exact sum of squared differences of two uint8 arrays (PSNR = 10 log10(255^2 * n / sum)). */
 int srd_sq_err_u8(const uint8_t* a, const uint8_t* b, int64_t n, uint64_t* out_sum, void* stream);
 
+/* One separable pass of `imresize` (:1162-1306, `imresizevec`): out[i] = sum_p weights[i][p] * in[indices[i][p]]
+ * along dim (0: rows, 1: columns) of an [H][W][C] image; weights [out_len][P] float64 and indices [out_len][P] come
+ * from the host-side `contributions` (:1196-1218).  is_u8: uint8 image, clipped and rounded half-to-even after the
+ * pass; otherwise a float64 image. */
+int srd_resize_dim(const void* in, int32_t is_u8, int32_t H, int32_t W, int32_t C, int32_t dim, int32_t out_len,
+                   const double* weights, const int32_t* indices, int32_t P, void* out, void* stream);
+/* `Measure.ssim` (:1537-1539) = skimage.metrics.structural_similarity(a, b, multichannel=True, data_range=255) on
+ * uint8 [H][W][C] images: uniform win x win window (default 7), sample covariance, float64, mean over the map
+ * cropped by (win-1)/2 and over channels.  workspace: 512 doubles; out: 1 double. */
+int srd_ssim_uniform_u8(const uint8_t* a, const uint8_t* b, int32_t H, int32_t W, int32_t C, int32_t win,
+                        double* workspace, double* out, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

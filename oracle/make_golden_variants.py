@@ -122,6 +122,19 @@ def main():
     with torch.no_grad():
         out["ssim"] = {"a": a, "b": b, "module": ref.SSIM()(a, b), "per_image": ref.SSIM(size_average=False)(a, b),
                        "functional": ref.ssim(a, b), "win7": ref.ssim(a, b, window_size=7, size_average=False)}
+    # ---- imresize (:1162-1306), uint8 and float64, shrinking (antialiased) and enlarging -----------------------
+    g = torch.Generator().manual_seed(67)
+    u8 = torch.randint(0, 256, (24, 20, 3), generator=g, dtype=torch.uint8).numpy()
+    f64 = torch.rand((12, 10), generator=g, dtype=torch.float64).numpy() * 255
+    out["imresize"] = {
+        "u8": torch.from_numpy(u8), "f64": torch.from_numpy(f64),
+        "u8_quarter": torch.from_numpy(ref.imresize(u8, 1 / 4)),
+        "u8_sizes_9x31": torch.from_numpy(ref.imresize(u8, sizes=(9, 31))),
+        "u8_x2": torch.from_numpy(ref.imresize(u8, 2)),
+        "u8_bilinear_third": torch.from_numpy(ref.imresize(u8, 1 / 3, method="bilinear")),
+        "f64_half": torch.from_numpy(ref.imresize(f64, 0.5)),
+        "f64_x3": torch.from_numpy(ref.imresize(f64, 3)),
+    }
     torch.save(out, os.path.join(OUT, "variants.pt"))
     print("variants.pt %d bytes" % os.path.getsize(os.path.join(OUT, "variants.pt")))
 

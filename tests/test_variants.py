@@ -327,3 +327,76 @@ def test_ssim_and_psnr_match_reference_fixture():
     assert Q.psnr_u8(big_a.to(DEV), big_b.to(DEV)) == pytest.approx(O.psnr_u8(big_a.numpy(), big_b.numpy()), rel=1e-12)
     with pytest.raises(NotImplementedError):
         m.lpips(a, b)
+
+
+# ------------------------------------------------------------------------------------------ imresize / Measure
+_RESIZE_CASES = [("u8", dict(scale=1 / 4), "u8_quarter"), ("u8", dict(sizes=(9, 31)), "u8_sizes_9x31"),
+                 ("u8", dict(scale=2), "u8_x2"), ("u8", dict(scale=1 / 3, method="bilinear"), "u8_bilinear_third"),
+                 ("f64", dict(scale=0.5), "f64_half"), ("f64", dict(scale=3), "f64_x3")]
+
+
+def test_oracle_imresize_matches_fixture_and_host_taps_agree():
+    from dgm_img_super_resolution_b200 import metrics as Q
+    f = golden("variants.pt")["imresize"]
+    for src, kw, key in _RESIZE_CASES:
+        got = O.imresize_np(f[src].numpy(), **kw)
+        if src == "u8":
+            assert np.array_equal(got, f[key].numpy()), key                       # integer work: bit-exact
+        else:
+            assert np.abs(got - f[key].numpy()).max() < 1e-10, key
+    # the product's host-side tap tables (metrics.contributions) against the oracle's per-sample restatement
+    for n_in, n_out, scale, kern, okern in ((24, 6, 0.25, Q._cubic, O._k_cubic), (20, 31, 31 / 20, Q._cubic, O._k_cubic),
+                                            (24, 8, 1 / 3, Q._triangle, O._k_triangle)):
+        w, idx = Q.contributions(n_in, n_out, scale, kern, 4.0)
+        taps = O._resize_taps(n_in, n_out, scale, okern)
+        assert w.shape[0] == n_out and all(np.allclose(w[o], taps[o][0], rtol=0, atol=1e-15) and
+                                           np.array_equal(idx[o], taps[o][1]) for o in range(n_out))
+
+
+def test_oracle_ssim_uniform_properties():
+    g = torch.Generator().manual_seed(71)
+    a = torch.randint(0, 256, (20, 18, 3), generator=g, dtype=torch.uint8).numpy()
+    b = np.clip(a.astype(np.int64) + torch.randint(-20, 21, (20, 18, 3), generator=g).numpy(), 0, 255).astype(np.uint8)
+    assert O.ssim_uniform_u8(a, a) == pytest.approx(1.0, abs=1e-12)
+    s = O.ssim_uniform_u8(a, b)
+    assert 0.5 < s < 1.0 and s == pytest.approx(O.ssim_uniform_u8(b, a), rel=1e-12)           # symmetric
+    assert O.ssim_uniform_u8(a[:, ::-1].copy(), b[:, ::-1].copy()) == pytest.approx(s, rel=1e-12)   # flip-invariant
+
+
+@pytest.mark.gpu
+def test_imresize_matches_reference_fixture():
+    from dgm_img_super_resolution_b200 import metrics as Q
+    f = golden("variants.pt")["imresize"]
+    for src, kw, key in _RESIZE_CASES:
+        got = Q.imresize(f[src].to(DEV), **kw).cpu()
+        assert got.shape == f[key].shape and got.dtype == f[key].dtype, key
+        if src == "u8":
+            assert torch.equal(got, f[key]), key
+        else:
+            assert float((got - f[key]).abs().max()) < 1e-10, key
+    g = torch.Generator().manual_seed(73)                                            # st_app-sized image, 2-D input
+    big = torch.randint(0, 256, (640, 480), generator=g, dtype=torch.uint8)
+    assert np.array_equal(Q.imresize(big.to(DEV), 1 / 4).cpu().numpy(), O.imresize_np(big.numpy(), 1 / 4))
+    with pytest.raises(RuntimeError):
+        Q.imresize(torch.zeros((4, 4), device=DEV), 2)                               # float32: not a reference dtype
+
+
+@pytest.mark.gpu
+def test_measure_matches_oracle():
+    from dgm_img_super_resolution_b200 import metrics as Q
+    g = torch.Generator().manual_seed(79)
+    hr = torch.rand((3, 64, 48), generator=g) * 2 - 1
+    sr = (hr + 0.1 * torch.randn((3, 64, 48), generator=g)).clamp(-1, 1)
+    lr = torch.rand((3, 16, 12), generator=g) * 2 - 1
+    res = Q.Measure().measure(sr.to(DEV), hr.to(DEV), lr.to(DEV), 4)
+    A, B_, LR = [O.to_uint8_round(v).transpose(1, 2, 0) for v in (sr, hr, lr)]
+    assert set(res) == {"psnr", "ssim", "lr_psnr"}
+    assert res["psnr"] == pytest.approx(O.psnr_u8(A, B_), rel=1e-12)
+    assert res["lr_psnr"] == pytest.approx(O.psnr_u8(O.imresize_np(A, 1 / 4), LR), rel=1e-12)
+    assert res["ssim"] == pytest.approx(O.ssim_uniform_u8(A, B_), rel=1e-9)
+    a8 = torch.from_numpy(np.ascontiguousarray(A)).to(DEV)
+    assert Q.ssim_uniform_u8(a8, a8) == pytest.approx(1.0, abs=1e-12)
+    res2 = Q.Measure(lpips_fn=lambda x, y: 0.25).measure(sr.to(DEV), hr.to(DEV), lr.to(DEV), 4)
+    assert res2["lpips"] == 0.25
+    with pytest.raises(NotImplementedError):
+        Q.Measure().lpips(a8, a8)
