@@ -159,7 +159,7 @@ int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream) {
 }
 
 int srd_tc_set_mode(int32_t a_mode, int32_t b_resident) {
-  SRD_CHECK(a_mode >= 0 && a_mode <= 63, "srd_tc_set_mode: a_mode must be in 0..63");
+  SRD_CHECK(a_mode >= 0 && a_mode <= 127, "srd_tc_set_mode: a_mode must be in 0..127");
   tc_set_mode(a_mode, b_resident ? 1 : 0);
   return 0;
 }

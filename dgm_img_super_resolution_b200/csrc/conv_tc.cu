@@ -127,6 +127,8 @@ struct TcArgs {
                            // group sets work on different items concurrently (<= n_stages of them)
   int stage_shift;         // log2(n_stages)
   unsigned long long* dbg; // optional timeline buffer [cta][DBG_ITEMS][8] of clock64 stamps (debug)
+  unsigned* sched_counter; // dynamic item scheduler (see Sched): per-plan ticket counter, 0 between launches
+  int dyn_sched;           // 1: items beyond each pair's first are handed out by tickets, not round-robin
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -350,6 +352,64 @@ __device__ __forceinline__ PairId pair_id() {
   return p;
 }
 
+// Work distribution.  Static (default): pair p runs items p, p + n_pairs, ...  Dynamic (a.dyn_sched, opt-in through
+// srd_tc_set_mode bit 6): pairs progress at different speeds, and with a static deal the last pair exits 7-12 us
+// after the first while the next launch waits -- so hand the items out by tickets instead.  The first two items of
+// a pair stay static; every further one is a ticket: the leader CTA's activation-producer thread draws
+// `atomicAdd(counter)` when it starts an item (the latency hides behind that item's loads) and publishes the item
+// after next -- or -1 -- into a small ring in the shared memory of BOTH CTAs of the pair (st.async + mbarrier
+// complete_tx, so the value is visible to whoever waits on the slot's barrier).  Every other role reads its items
+// from that ring, in order.  Each processed item draws exactly one ticket, so a launch draws n_items tickets in
+// total and the thread that gets the last one resets the counter.  The ring (32 slots) is deeper than the furthest
+// any role can lag behind the producer (A ring <= 8 items + 2 x 4 accumulator stages + the trailing -1 entries the
+// residual prefetch may look ahead into).
+// MEASURED: correct (same-seed replays bit-identical) but 2 % SLOWER end to end than the static deal (221 vs 226
+// images/s): the ring reads and the later start of the peer CTA's loads cost more than the evened-out tail wins,
+// and the 20x20 layers (1.8 item rounds) cannot be helped by any scheduler.  Kept as a switch.
+constexpr int SCHED_SLOTS = 32;
+constexpr uint32_t SCHED_BAR_OFF = 8u * (4 * MAX_STAGES + 10 + 2 * EPI_WARPS);    // inside the BAR_BYTES block
+constexpr uint32_t SCHED_RING_OFF = SCHED_BAR_OFF + 8u * SCHED_SLOTS;
+static_assert(SCHED_RING_OFF + 4 * SCHED_SLOTS <= BAR_BYTES, "scheduler ring does not fit the barrier block");
+struct Sched {
+  uint32_t bar0, ring0;      // shared::cta addresses of the slot barriers / values
+  int dyn, pair, n_pairs, n_items;
+  int* err;
+  // the il-th item of this pair, -1 past the end
+  __device__ __forceinline__ int get(int il) const {
+    if (!dyn) {
+      const int item = pair + il * n_pairs;
+      return item < n_items ? item : -1;
+    }
+    const uint32_t slot = (uint32_t)il & (SCHED_SLOTS - 1);
+    mbar_wait(bar0 + 8u * slot, ((uint32_t)il / SCHED_SLOTS) & 1u, err, 10);
+    int v;
+    asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(ring0 + 4u * slot) : "memory");
+    return v;
+  }
+  // scheduler thread only: entry il := item, in every CTA of the pair
+  template <int CG>
+  __device__ __forceinline__ void publish(int il, int item) const {
+    const uint32_t slot = (uint32_t)il & (SCHED_SLOTS - 1);
+#pragma unroll
+    for (uint32_t r = 0; r < (uint32_t)CG; ++r) {
+      uint32_t rbar, rval;
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rbar) : "r"(bar0 + 8u * slot), "r"(r));
+      asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(rval) : "r"(ring0 + 4u * slot), "r"(r));
+      asm volatile("mbarrier.arrive.expect_tx.shared::cluster.b64 _, [%0], 4;" ::"r"(rbar) : "memory");
+      asm volatile("st.async.weak.shared::cluster.mbarrier::complete_tx::bytes.b32 [%0], %1, [%2];"
+                   ::"r"(rval), "r"(item), "r"(rbar) : "memory");
+    }
+  }
+};
+template <int CG>
+__device__ __forceinline__ Sched make_sched(const TcArgs& a, uint32_t bar_base) {
+  const PairId pid = pair_id<CG>();
+  Sched sc;
+  sc.bar0 = bar_base + SCHED_BAR_OFF; sc.ring0 = bar_base + SCHED_RING_OFF;
+  sc.dyn = a.dyn_sched; sc.pair = pid.pair; sc.n_pairs = pid.n_pairs; sc.n_items = a.n_items; sc.err = a.err_flag;
+  return sc;
+}
+
 // taps served by one A box load: stride 1 -> all nky taps at row offset ky0+j;
 // stride 2 -> load 0 = even input rows (ky 0 -> off 0, ky 2 -> off 1), load 1 = odd rows (ky 1).
 __device__ __forceinline__ int n_loads(const TcArgs& a) { return a.stride == 2 ? 2 : 1; }
@@ -559,7 +619,7 @@ __device__ __forceinline__ TileGeo tile_geo(const TcArgs& a, int tt, int g, int 
 // the items with local index = h (mod 2), i.e. TMEM stage h.
 // ---------------------------------------------------------------------------------------------
 template <int ACT, int CG>
-__device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es, uint32_t tmem_base,
+__device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es, const Sched& sc, uint32_t tmem_base,
                                               uint32_t t_full0, uint32_t t_empty0, int warp, int lane) {
   const int S = a.up;
   const PairId pid = pair_id<CG>();
@@ -575,8 +635,8 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
   // groups sharing an item split the 16-column chunks round-robin
   const int c_first = share, c_step = a.n_share;
   for (int it = set;; it += n_conc) {
-    const int item = pid.pair + it * pid.n_pairs;
-    if (item >= a.n_items) break;
+    const int item = sc.get(it);
+    if (item < 0) break;
     const int stage = it & (a.n_stages - 1);
     const uint32_t round = (uint32_t)(it >> a.stage_shift);   // parity of this TMEM stage
     const uint32_t t_full = t_full0 + 8u * stage, t_empty = t_empty0 + 8u * stage;
@@ -709,7 +769,7 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // Each epilogue WARP owns 32 TMEM lanes = 4 tile rows x 8 px and stages them in its own 4 KB
 // swizzled buffer(s): no cross-warp synchronisation, one lane issues the warp's TMA traffic.
 template <int ACT, int CG>
-__device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es, const StageSmem& sg,
+__device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es, const StageSmem& sg, const Sched& sc,
                                              uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0,
                                              int warp, int lane) {
   const PairId pid = pair_id<CG>();
@@ -738,8 +798,8 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   auto prepare = [&](uint32_t kn, int itn, int qn) {
     if (qn >= n_sub) { itn += n_conc; qn = share; }
     if (qn >= n_sub) return;                                   // this group never has a sub-tile
-    const int item = pid.pair + itn * pid.n_pairs;
-    if (item >= a.n_items) return;
+    const int item = sc.get(itn);                              // may be a later item of this group: see Sched
+    if (item < 0) return;
     if (qn >= n_sub1) qn -= n_sub1;                            // second output: same tiles again
     const int mt = (qn >= nsj) ? 1 : 0, j = qn - mt * nsj;     // MT <= 2
     const int ph = fdiv(item, a.fd_ipp);
@@ -758,8 +818,8 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   uint32_t k = 0;
   if (lane == 0) prepare(0, set, share);
   for (int it = set;; it += n_conc) {
-    const int item = pid.pair + it * pid.n_pairs;
-    if (item >= a.n_items) break;
+    const int item = sc.get(it);
+    if (item < 0) break;
     const int stage = it & (a.n_stages - 1);
     const uint32_t round = (uint32_t)(it >> a.stage_shift);   // parity of this TMEM stage
     const uint32_t t_full = t_full0 + 8u * stage, t_empty = t_empty0 + 8u * stage;
@@ -1038,8 +1098,23 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, 
   const uint32_t a_stage_bytes = (uint32_t)a.a_stage_bytes;
   int* err = a.err_flag;
   Ring ra{0, 0, a.a_stages};
-  int il = 0;
-  for (int item = pid.pair; item < n_items; item += G, ++il) {
+  const Sched sc = make_sched<CG>(a, bar_base);
+  const bool scheduler = sc.dyn && leader;                       // this thread hands out the pair's items
+  // the first two items of a pair are static; the ticket drawn while item il is loaded names item il + 2, so an
+  // entry is in the ring a whole item before the peer CTA's producer needs it
+  int next_item = pid.pair, next2 = (pid.pair + G < n_items) ? pid.pair + G : -1;
+  if (scheduler) { sc.publish<CG>(0, next_item); sc.publish<CG>(1, next2); }
+  for (int il = 0;; ++il) {
+    int item;
+    unsigned ticket = 0;
+    if (scheduler) {
+      item = next_item;
+      if (item < 0) break;
+      ticket = atomicAdd(a.sched_counter, 1u);                   // consumed after this item's loads are issued
+    } else {
+      item = sc.get(il);
+      if (item < 0) break;
+    }
     const int phase = fdiv(item, a.fd_ipp);
     const int t0 = (item - phase * ipp) * (MT * CG) + pid.rank;
     int kx0 = a.kx0;
@@ -1083,6 +1158,18 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, 
         }
       }
     }
+    if (scheduler) {
+      const bool ended = next2 < 0;                                       // entry il + 1 was already the end marker
+      next_item = next2;
+      next2 = 2 * G + (int)ticket;
+      if (next2 >= n_items || ended) next2 = -1;
+      if (ticket == (unsigned)(n_items - 1)) *a.sched_counter = 0u;     // the launch's last draw: ready for the next one
+      if (!ended) {
+        sc.publish<CG>(il + 2, next2);
+        if (next2 < 0)
+          for (int k = 3; k <= 10; ++k) sc.publish<CG>(il + k, -1);       // look-ahead room of the residual prefetch
+      }
+    }
   }
 }
 
@@ -1103,9 +1190,12 @@ __device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b
       tma_load_2d<CG>(b_base + (uint32_t)kb * B_BYTES, &a.tmB, bars.B_res(), 0, kb * Npad + b_row0);
     return;
   }
-  const int n_items = a.n_items, G = pid.n_pairs, kb_per_phase = a.kb_per_phase;
+  const int kb_per_phase = a.kb_per_phase;
   Ring rb{0, 0, a.b_stages};
-  for (int item = pid.pair; item < n_items; item += G) {
+  const Sched sc = make_sched<CG>(a, bar_base);
+  for (int il = 0;; ++il) {
+    const int item = sc.get(il);
+    if (item < 0) break;
     int kb = (a.up > 1) ? fdiv(item, a.fd_ipp) * kb_per_phase : 0;
     for (int j = 0; j < kb_per_phase; ++j, ++kb) {
       mbar_wait(bars.B_empty(rb.stage), rb.phase ^ 1, err, 2);
@@ -1128,7 +1218,7 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
                                          uint32_t bar_base, int issuer = 0) {
   const Bars bars{bar_base};
   const PairId pid = pair_id<CG>();                  // only the leader CTA of a pair runs this role
-  const int n_items = a.n_items, G = pid.n_pairs, S = a.up, n_chunks = a.n_chunks;
+  const int S = a.up, n_chunks = a.n_chunks;
   const uint32_t Npad = (uint32_t)a.Npad, idesc = a.idesc;
   const uint32_t bB16 = Npad * 8u / CG, aS16 = (uint32_t)a.a_stage_bytes >> 4;   // per-CTA weight tile = Npad/CG rows
   const uint32_t a_lo_base = a_base >> 4, b_lo_base = b_base >> 4;
@@ -1146,7 +1236,10 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
   const int dual = SRD_DUAL_ISSUE ? a.dual_issue : 0;
   if (!dual && issuer != 0) return;
   int mma_il = 0;
-  for (int item = pid.pair; item < n_items; item += G) {
+  const Sched sc = make_sched<CG>(a, bar_base);
+  for (int sched_il = 0;; ++sched_il) {
+    const int item = sc.get(sched_il);
+    if (item < 0) break;
     if (dual && (mma_il & 1) != issuer) {
       ra.skip(n_chunks);
       rt.next();
@@ -1313,6 +1406,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int s = 0; s < 4; ++s) { mbar_init(T_full(s), 1); mbar_init(T_empty(s), (uint32_t)(4 * a.n_share * CG)); }
     mbar_init(B_res, 1);
     for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(R_full0 + 8u * s, 1);
+    for (int s = 0; s < SCHED_SLOTS; ++s) mbar_init(bar_base + SCHED_BAR_OFF + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int s = 0; s < a.n_src; ++s)
       asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA[s]) : "memory");
@@ -1404,6 +1498,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   } else {
     // ================================================================= epilogue (warps 2..9)
     EpiSmem es;
+    const Sched sc = make_sched<CG>(a, bar_base);
     es.bias = s_bias; es.temb = s_temb;
     es.head_w = a.head_w ? s_head : nullptr; es.head_b = s_headb; es.hpart = s_hpart;
     es.lin_w = a.lin_w ? s_head : nullptr;
@@ -1414,15 +1509,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       sg.gen = smem_raw + (sg.base - smem_u32(smem_raw));
       sg.r_full0 = R_full0 + 8u * (uint32_t)(ew * 2);
       if (a.ep.act == SRD_ACT_MISH)
-        epilogue_tma<SRD_ACT_MISH, CG>(a, es, sg, tmem_base, T_full(0), T_empty(0), warp, lane);
+        epilogue_tma<SRD_ACT_MISH, CG>(a, es, sg, sc, tmem_base, T_full(0), T_empty(0), warp, lane);
       else
-        epilogue_tma<SRD_ACT_NONE, CG>(a, es, sg, tmem_base, T_full(0), T_empty(0), warp, lane);
+        epilogue_tma<SRD_ACT_NONE, CG>(a, es, sg, sc, tmem_base, T_full(0), T_empty(0), warp, lane);
     } else if (a.ep.act == SRD_ACT_MISH)
-      epilogue_role<SRD_ACT_MISH, CG>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
+      epilogue_role<SRD_ACT_MISH, CG>(a, es, sc, tmem_base, T_full(0), T_empty(0), warp, lane);
     else if (a.ep.act == SRD_ACT_LRELU02)
-      epilogue_role<SRD_ACT_LRELU02, CG>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
+      epilogue_role<SRD_ACT_LRELU02, CG>(a, es, sc, tmem_base, T_full(0), T_empty(0), warp, lane);
     else
-      epilogue_role<SRD_ACT_NONE, CG>(a, es, tmem_base, T_full(0), T_empty(0), warp, lane);
+      epilogue_role<SRD_ACT_NONE, CG>(a, es, sc, tmem_base, T_full(0), T_empty(0), warp, lane);
   }
 
   kern_stamp(a, 3);
@@ -1466,6 +1561,7 @@ static int g_cg = 2;                     // CTAs per MMA: 2 = cta_group::2 pairs
 static int g_pdl = 1;                    // programmatic dependent launch of consecutive conv layers
 static int g_res_mt2 = 1;                // MT = 2 also with resident weights
 static int g_small_mt2 = 0;              // MT = 2 with a single TMEM stage on small, wide layers (measured slower: off)
+static int g_dyn_sched = 0;              // ticket-based item scheduling (see Sched; measured 2 % slower: off)
 static unsigned long long* g_dbg = nullptr;
 void tc_set_debug(unsigned long long* p) { g_dbg = p; }
 void tc_set_mode(int a_mode, int b_resident) {
@@ -1475,6 +1571,7 @@ void tc_set_mode(int a_mode, int b_resident) {
   g_pdl = (a_mode & 8) ? 0 : 1;          // bit 3 of a_mode: no programmatic dependent launch
   g_res_mt2 = (a_mode & 16) ? 0 : 1;     // bit 4 of a_mode: resident weights always with MT = 1
   g_small_mt2 = (a_mode & 32) ? 1 : 0;   // bit 5 of a_mode: trade the second TMEM stage for MT = 2 on small, wide layers
+  g_dyn_sched = (a_mode & 64) ? 1 : 0;   // bit 6 of a_mode: ticket-based item scheduling instead of round-robin
   g_b_resident = b_resident;
 }
 
@@ -1509,6 +1606,8 @@ int tc_supported(const SrdConvDesc& d, const char** why) {
 struct TcPlan {
   TcArgs args;
   int grid, smem;
+  unsigned* counter = nullptr;           // ticket counter of the dynamic item scheduler (device memory)
+  ~TcPlan() { if (counter) cudaFree(counter); }
 };
 
 int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
@@ -1659,6 +1758,13 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
             "(stride-1 conv, N %% 64 == 0, NHWC output, batch-uniform temb)");
   plan->smem = a.a_stages * stage_bytes + b_bytes_total + stg_total + BAR_BYTES + VEC_BYTES + 1024;
   plan->grid = (a.n_items < n_sm / cg ? a.n_items : n_sm / cg) * cg;
+  // dynamic item scheduling (see Sched) once a pair has more than one item
+  a.dyn_sched = (g_dyn_sched && a.n_items > 2 * (plan->grid / cg)) ? 1 : 0;
+  if (a.dyn_sched) {
+    if (!plan->counter) SRD_CUDA(cudaMalloc((void**)&plan->counter, sizeof(unsigned)));
+    SRD_CUDA(cudaMemset(plan->counter, 0, sizeof(unsigned)));
+    a.sched_counter = plan->counter;
+  }
 
   // ---- tensor maps
   for (int i = 0; i < d.n_src; ++i) {

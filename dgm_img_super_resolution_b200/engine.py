@@ -727,6 +727,14 @@ def time_table(unet, t_values):
     return out
 
 
+def plan_signature(diffusion):
+    """Everything a cached SamplerPlan (and its captured graph) depends on besides (B, h, w, precision, device)."""
+    from . import model as M
+    hp = M.hparams
+    return (params_signature(diffusion), diffusion.num_timesteps, hp["res_rescale"], hp["clip_input"], bool(hp["res"]),
+            bool(hp.get("up_input", False)), bool(hp.get("use_attn", False)), hp["sr_scale"])
+
+
 def params_signature(module):
     return tuple((p.data_ptr(), p._version) for p in module.parameters())
 
@@ -795,8 +803,7 @@ class SamplerPlan:
         self.noise_buf = None
         self.seed_dev = torch.zeros(1, dtype=torch.int64, device=device)   # Philox seed, read by the kernels
         self.graphs = {}
-        self.sig = (params_signature(diffusion), self.T, hp["res_rescale"], hp["clip_input"], bool(hp["res"]),
-                    bool(hp["up_input"]))
+        self.sig = plan_signature(diffusion)
 
     # ---- pieces -----------------------------------------------------------------------------
     def encode(self):

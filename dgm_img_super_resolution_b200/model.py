@@ -522,7 +522,7 @@ class GaussianDiffusion(nn.Module):
 
     # ---- plan cache -------------------------------------------------------------------------
     def _plan(self, B, h, w, device):
-        sig = (E.params_signature(self), self.num_timesteps, hparams['res_rescale'], hparams['clip_input'])
+        sig = E.plan_signature(self)
         key = (B, h, w, runtime.precision, str(device))
         p = self._plans.get(key)
         if p is None or p.sig != sig:

@@ -135,6 +135,7 @@ int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream);
  *        bit 3: no programmatic dependent launch between consecutive conv layers.
  *        bit 4: resident weights always with one M tile per CTA and item (MT = 1).
  *        bit 5: give up the second TMEM accumulator stage for MT = 2 on small, wide layers (measured slower).
+ *        bit 6: hand work items to CTA pairs through a ticket counter instead of round-robin (measured slower).
  * b_resident: keep all weight k-blocks in shared memory when they fit. */
 int srd_tc_set_mode(int32_t a_mode, int32_t b_resident);
 /* Debug: plans created afterwards record per-item clock64 stamps into buf [grid][64][8] (NULL = off). */

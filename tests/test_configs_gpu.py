@@ -59,9 +59,14 @@ def test_config4_timestep_sweep_graph_loop(hp, T):
         img, rrdb_out = diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
         assert img.shape == (2, 3, 256, 256) and torch.isfinite(img).all()
         assert diff.last_stats["graph"] and diff.last_stats["gpu_launches"] > 40 * T
+        plan = next(iter(diff._plans.values()))
+        graph = next(iter(plan.graphs.values()))
         M.runtime.seed_counter = 100                    # same seed -> bit-identical replay of the captured graph
         img2, _ = diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
         assert torch.equal(img, img2)
+        # ... and it WAS a replay: the cached plan and its graph are reused, not rebuilt per call
+        assert len(diff._plans) == 1 and next(iter(diff._plans.values())) is plan
+        assert len(plan.graphs) == 1 and next(iter(plan.graphs.values())) is graph
         if T == 25:                                     # eager loop == graph loop, bit for bit
             M.runtime.graph = False
             M.runtime.seed_counter = 100
