@@ -787,6 +787,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   const int Ho = a.ep.H_out, Wo = a.ep.W_out;
   const bool reflect = (a.ep.border == SRD_BORDER_REFLECT);
   const bool has_r1 = a.ep.res1 != nullptr;
+  const bool has_temb = a.ep.temb != nullptr;      // block2 / resampling layers: no vector after the activation
   const bool r1_packed = (a.ep.beta1 == 1.0f), r2_packed = (a.ep.beta2 == 1.0f);
   const uint32_t swz = (uint32_t)(lane & 7);     // == m & 7
   uint8_t* my_row = sg.gen + lane * 128;         // this pixel's 128 B row inside a staging buffer
@@ -905,7 +906,8 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
           } else {
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
-              const float4 b4 = sb[q], t4 = st[q];
+              const float4 b4 = sb[q];
+              const float4 t4 = has_temb ? st[q] : make_float4(0.f, 0.f, 0.f, 0.f);   // saves a shared-memory wavefront
               v[4 * q + 0] = act_axpy<ACT>(__uint_as_float(r[4 * q + 0]) + b4.x, alpha, t4.x);
               v[4 * q + 1] = act_axpy<ACT>(__uint_as_float(r[4 * q + 1]) + b4.y, alpha, t4.y);
               v[4 * q + 2] = act_axpy<ACT>(__uint_as_float(r[4 * q + 2]) + b4.z, alpha, t4.z);
