@@ -3,6 +3,7 @@ launch-list CSV (`--metrics gpu__time_duration.sum[,dram__bytes_*] --csv --log-f
     python tools/ncu_summary.py report.ncu-rep > profiles/rNN/..._summary.txt
     python tools/ncu_summary.py launches.csv   > profiles/rNN/..._summary.txt"""
 import csv
+import os
 import io
 import subprocess
 import sys
@@ -69,6 +70,40 @@ def launches(path):
     print("%-44s %8s %12.1f" % ("total", "", tot))
 
 
+def pass_traffic(path, out_json):
+    """One Unet pass = the conv launches between the last two p_sample launches of the list: serialized time and
+    DRAM bytes, per launch and summed -> out_json (read by bench.py as roofline.traffic)."""
+    import json
+    text = open(path).read()
+    rows = list(csv.DictReader(io.StringIO(text[text.index('"ID"'):])))
+    L = OrderedDict()
+    for r in rows:
+        e = L.setdefault(r["ID"], {"name": r["Kernel Name"].split("(")[0]})
+        v, unit = float(r["Metric Value"].replace(",", "")), r["Metric Unit"]
+        if r["Metric Name"] == "gpu__time_duration.sum":
+            e["us"] = v / 1000.0 if unit in ("ns", "nsecond") else (v if unit in ("us", "usecond") else v * 1000.0)
+        else:
+            scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}.get(unit, 1.0)
+            e["rd" if "read" in r["Metric Name"] else "wr"] = v * scale
+    ids = list(L)
+    ps = [i for i, k in enumerate(ids) if "p_sample" in L[k]["name"]]
+    a, b = ps[-2], ps[-1]
+    convs = [L[ids[i]] for i in range(a + 1, b)]
+    res = {"conv_launches_per_unet_pass": len(convs), "serialized_cold_us": sum(c["us"] for c in convs),
+           "dram_bytes_read": sum(c.get("rd", 0.0) for c in convs), "dram_bytes_write": sum(c.get("wr", 0.0) for c in convs),
+           "per_launch": [{"us": round(c["us"], 2), "rd_MB": round(c.get("rd", 0.0) / 1e6, 2),
+                           "wr_MB": round(c.get("wr", 0.0) / 1e6, 2)} for c in convs],
+           "source": "profiles/r01/" + os.path.basename(path) + " (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
+                     "dram__bytes_write.sum --clock-control none, python bench.py --steps 1 --warmup 1 --no-cpu)"}
+    json.dump(res, open(out_json, "w"), indent=1)
+    print("pass: %d launches, %.1f us serialized, %.2f GB read + %.2f GB written -> %s" % (
+        res["conv_launches_per_unet_pass"], res["serialized_cold_us"], res["dram_bytes_read"] / 1e9,
+        res["dram_bytes_write"] / 1e9, out_json))
+
+
 if __name__ == "__main__":
     p = sys.argv[1]
-    (report if p.endswith(".ncu-rep") else launches)(p)
+    if len(sys.argv) > 3 and sys.argv[2] == "--pass-json":
+        pass_traffic(p, sys.argv[3])
+    else:
+        (report if p.endswith(".ncu-rep") else launches)(p)

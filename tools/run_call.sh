@@ -1,10 +1,10 @@
-mkdir -p gpurun_out
-timeout 600 python -m pytest tests/test_gpu_kernels.py -m gpu -x -q > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -2 gpurun_out/pytest.log
-for v in prev default prev default; do
-if [ $v = default ]; then unset SRD_LIB_PATH; else export SRD_LIB_PATH=$PWD/dgm_img_super_resolution_b200/variants/lib_$v.so; fi
-timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu > gpurun_out/bench_$v.log 2>&1
-python -c "
-import json;d=json.loads(open('gpurun_out/bench_$v.log').read().strip().splitlines()[-1]);
-print('$v: img/s',round(d['value'],1),'pass ms',round(d['roofline']['ms_per_pass'],3),'frac',round(d['roofline']['frac'],4), d['clocks']['sm_mhz'])
-" || tail -3 gpurun_out/bench_$v.log
-done
+mkdir -p gpurun_out/final
+O=gpurun_out/final
+timeout 1500 python -m pytest tests -m gpu -q > $O/pytest_gpu_final.txt 2>&1; echo "pytest rc=$?"; tail -2 $O/pytest_gpu_final.txt
+timeout 300 python -c "import __graft_entry__ as g; g.smoke(); print('smoke ok')" 2>&1 | tail -2
+timeout 900 python bench.py --impl reference > $O/bench_reference_arm_final.json 2> $O/bench_reference_arm.err; echo "ref rc=$?"; tail -c 600 $O/bench_reference_arm_final.json
+timeout 900 python bench.py > $O/bench_final.json 2> $O/bench.err; echo "bench rc=$?"; tail -c 1500 $O/bench_final.json
+timeout 600 python tools/accuracy_report.py > $O/accuracy_report.txt 2>&1; tail -12 $O/accuracy_report.txt
+timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -k regex:"conv_tc|p_sample|nchw_to_act|upsample2x" --launch-skip 260 -c 330 --csv --log-file $O/ncu_launch_list_bench.csv python bench.py --steps 1 --warmup 1 --no-cpu > $O/ncu_bench.log 2>&1; echo "ncu rc=$?"
+python tools/ncu_summary.py $O/ncu_launch_list_bench.csv > $O/ncu_launch_list_summary.txt 2>&1; cat $O/ncu_launch_list_summary.txt
+python tools/ncu_summary.py $O/ncu_launch_list_bench.csv --pass-json $O/unet_pass_traffic.json
