@@ -92,3 +92,39 @@ def test_smallest_and_ragged_inputs(hp):
                 diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
     finally:
         M.runtime.noise = "torch"
+
+
+def test_no_write_outside_activation_buffers(hp):
+    """Every activation buffer of an RRDB + cond_proj + Unet program gets canary-filled guard bands in front of and
+    behind it; after a full pass (ragged width, non-multiple-of-16 rows, every layer type) the bands are intact.
+    (compute-sanitizer is not available on the GPU pool: this is the bounds check of our own.)"""
+    from dgm_img_super_resolution_b200 import engine as E
+    G, CANARY = 4096, -7.25
+    guards = []
+    orig_init = E.Act.__init__
+
+    def guarded_init(self, B, H, W, ct, prec, device, slack=0):
+        self.B, self.H, self.W, self.ct = B, H, W, ct
+        n = B * (H + 2) * (W + 2) * ct
+        whole = torch.full((G + n + slack + G,), CANARY, dtype=prec.torch_dtype, device=device)
+        whole[G:G + n + slack].zero_()
+        self._flat = whole[G:G + n + slack]
+        self.t = self._flat[:n].view(B, H + 2, W + 2, ct)
+        guards.append((whole, n + slack))
+
+    E.Act.__init__ = guarded_init
+    try:
+        M, diff = build_ours(hp, timesteps=3, device=DEV)
+        for prec in ("bf16", "fp32"):
+            M.runtime.precision, M.runtime.noise, M.runtime.graph = prec, "philox", False
+            for (B, h, w) in ((3, 10, 6), (2, 8, 8)):               # HR 40x24 (ragged 8-px blocks) and 32x32
+                img_lr, img_lr_up, _ = gen_inputs(B, h, w, hp["sr_scale"], 12)
+                img, _ = diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
+                assert torch.isfinite(img).all()
+        torch.cuda.synchronize()
+        assert len(guards) > 100
+        for whole, n in guards:
+            assert bool((whole[:G] == CANARY).all()) and bool((whole[G + n:] == CANARY).all())
+    finally:
+        E.Act.__init__ = orig_init
+        M.runtime.precision, M.runtime.graph = "bf16", True
