@@ -128,3 +128,45 @@ def test_no_write_outside_activation_buffers(hp):
     finally:
         E.Act.__init__ = orig_init
         M.runtime.precision, M.runtime.graph = "bf16", True
+
+
+def test_config1_full_bench_batch(hp):
+    """configs[1] at the bench's own size (64 images, 40x40 -> 160x160; T shortened to 3): the tcgen05 path against
+    the fp32 validation path on the same injected noise, and the LAST image of the batch (the tail of the stacked-row
+    tiling) against the same image sampled alone."""
+    M, diff = build_ours(hp, timesteps=3, device=DEV)
+    img_lr, img_lr_up, g = gen_inputs(64, 40, 40, hp["sr_scale"], 21)
+    noises = torch.randn((4, 64, 3, 160, 160), generator=g)
+
+    class inject:
+        def __init__(self, sl):
+            self.i, self.sl = 0, sl
+
+        def nxt(self, dev):
+            n = noises[self.i][self.sl].to(dev)
+            self.i += 1
+            return n
+
+        def __enter__(self):
+            self.old = (torch.randn, M.noise_like)
+            torch.randn = lambda *a, **k: self.nxt(k.get("device", "cpu"))
+            M.noise_like = lambda shape, device, repeat=False: self.nxt(device)
+
+        def __exit__(self, *exc):
+            torch.randn, M.noise_like = self.old
+            return False
+
+    M.runtime.noise = "torch"
+    out = {}
+    try:
+        for prec in ("bf16", "fp32"):
+            M.runtime.precision = prec
+            with inject(slice(0, 64)):
+                out[prec], _ = diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
+        assert O.psnr(out["bf16"].cpu(), out["fp32"].cpu()) >= 40.0
+        M.runtime.precision = "bf16"
+        with inject(slice(63, 64)):
+            one, _ = diff.sample(img_lr[63:].to(DEV), img_lr_up[63:].to(DEV), (1, 3, 160, 160))
+        assert torch.equal(one[0], out["bf16"][63])
+    finally:
+        M.runtime.precision = "bf16"

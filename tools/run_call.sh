@@ -1,4 +1,2 @@
 mkdir -p gpurun_out
-timeout 600 python tools/dual_stream_probe.py 64 2 2>&1 | tail -4
-timeout 600 python tools/dual_stream_probe.py 64 4 2>&1 | tail -2
-timeout 600 python tools/dual_stream_probe.py 128 2 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_configs_gpu.py -m gpu -x -q -k "full_bench" > gpurun_out/pytest.log 2>&1; echo "pytest rc=$?"; tail -15 gpurun_out/pytest.log
