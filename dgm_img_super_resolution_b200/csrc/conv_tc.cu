@@ -129,6 +129,7 @@ struct TcArgs {
   unsigned long long* dbg; // optional timeline buffer [cta][DBG_ITEMS][8] of clock64 stamps (debug)
   unsigned* sched_counter; // dynamic item scheduler (see Sched): per-plan ticket counter, 0 between launches
   int dyn_sched;           // 1: items beyond each pair's first are handed out by tickets, not round-robin
+  int reverse_items;       // static deal only: item order reversed (see SrdConvDesc.reverse_items)
 };
 
 // ------------------------------------------------------------------------------------------ PTX
@@ -372,13 +373,14 @@ constexpr uint32_t SCHED_RING_OFF = SCHED_BAR_OFF + 8u * SCHED_SLOTS;
 static_assert(SCHED_RING_OFF + 4 * SCHED_SLOTS <= BAR_BYTES, "scheduler ring does not fit the barrier block");
 struct Sched {
   uint32_t bar0, ring0;      // shared::cta addresses of the slot barriers / values
-  int dyn, pair, n_pairs, n_items;
+  int dyn, rev, pair, n_pairs, n_items;
   int* err;
   // the il-th item of this pair, -1 past the end
   __device__ __forceinline__ int get(int il) const {
     if (!dyn) {
       const int item = pair + il * n_pairs;
-      return item < n_items ? item : -1;
+      if (item >= n_items) return -1;
+      return rev ? n_items - 1 - item : item;          // SrdConvDesc.reverse_items: last tile first
     }
     const uint32_t slot = (uint32_t)il & (SCHED_SLOTS - 1);
     mbar_wait(bar0 + 8u * slot, ((uint32_t)il / SCHED_SLOTS) & 1u, err, 10);
@@ -406,7 +408,7 @@ __device__ __forceinline__ Sched make_sched(const TcArgs& a, uint32_t bar_base) 
   const PairId pid = pair_id<CG>();
   Sched sc;
   sc.bar0 = bar_base + SCHED_BAR_OFF; sc.ring0 = bar_base + SCHED_RING_OFF;
-  sc.dyn = a.dyn_sched; sc.pair = pid.pair; sc.n_pairs = pid.n_pairs; sc.n_items = a.n_items; sc.err = a.err_flag;
+  sc.dyn = a.dyn_sched; sc.rev = a.reverse_items; sc.pair = pid.pair; sc.n_pairs = pid.n_pairs; sc.n_items = a.n_items; sc.err = a.err_flag;
   return sc;
 }
 
@@ -1762,6 +1764,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   plan->grid = (a.n_items < n_sm / cg ? a.n_items : n_sm / cg) * cg;
   // dynamic item scheduling (see Sched) once a pair has more than one item
   a.dyn_sched = (g_dyn_sched && a.n_items > 2 * (plan->grid / cg)) ? 1 : 0;
+  a.reverse_items = (d.reverse_items && !a.dyn_sched) ? 1 : 0;
   if (a.dyn_sched) {
     if (!plan->counter) SRD_CUDA(cudaMalloc((void**)&plan->counter, sizeof(unsigned)));
     SRD_CUDA(cudaMemset(plan->counter, 0, sizeof(unsigned)));

@@ -15,6 +15,7 @@ from . import _lib as L
 PRECISIONS = ("bf16", "fp32", "bf16_direct")
 # developer switch for A/B measurements: res_conv as a second output of block1's launch (SrdConvDesc.N2)
 FUSE_RES_CONV = os.environ.get("SRD_NO_FUSED_RES") != "1"
+REVERSE_ORDER = os.environ.get("SRD_NO_REVERSE", "0") != "1"   # alternate the tile order of consecutive conv launches
 
 
 def _ceil(a, b):
@@ -259,6 +260,7 @@ class Builder:
         self.device = device
         self.prec = precision if isinstance(precision, Precision) else Precision(precision)
         self.ops = []
+        self._dir = {}          # id(Act) -> 1 if its last writer walked the tiles in reverse order
 
     def act(self, B, H, W, C_, ct=None, slack=0):
         ct = _ceil(C_ if ct is None else ct, 8) * 8
@@ -343,6 +345,13 @@ class Builder:
         if out2 is not None:
             d.out2, d.out2_ct, d.out2_coff = out2.ptr, out2.ct, out2_coff
         d.border = border
+        # serpentine tile order: start where the producer of the first source finished (its output tail is still
+        # in L2); REVERSE_ORDER = False keeps every layer front-to-back
+        if REVERSE_ORDER and d.kernel != L.KERNEL_DIRECT:
+            d.reverse_items = 1 - self._dir.get(id(a0), 0)        # unknown writers (converters, p_sample) go front to back
+            for o in (out, out2, dual[1] if dual is not None else None):
+                if o is not None:
+                    self._dir[id(o)] = d.reverse_items
         if planar is not None:
             d.planar, d.planar_c, d.planar_clamp01 = planar.data_ptr(), planar_c, planar_clamp01
         if head is not None:

@@ -108,6 +108,10 @@ typedef struct {
   int32_t dst2_ct, dst2_coff, reserved2;
   const float* bias2;     /* [N2] */
   void* dst2;
+  /* tc kernel: walk the output tiles from the last to the first.  A consumer that starts where its producer
+   * just finished finds the freshest part of its input still in the 126 MB L2 (layers are launched back to back
+   * and every 160x160 / 80x80 tensor of a 64-image batch is larger than L2), so consecutive layers alternate. */
+  int32_t reverse_items, reserved3;
 } SrdConvDesc;
 
 typedef struct SrdConvPlan SrdConvPlan;
