@@ -1,8 +1,6 @@
-mkdir -p gpurun_out
-for v in 0 24 16 8 7 0 24; do
-SRD_L2_HINT_MASK=$v timeout 300 python bench.py --steps 3 --warmup 2 --no-cpu > gpurun_out/bench_m$v.log 2>&1
-python -c "
-import json;d=json.loads(open('gpurun_out/bench_m$v.log').read().strip().splitlines()[-1]);
-print('mask=$v: img/s',round(d['value'],1),'pass ms',round(d['roofline']['ms_per_pass'],3),'frac',round(d['roofline']['frac'],4), d['clocks']['sm_mhz'])
-" || tail -3 gpurun_out/bench_m$v.log
+mkdir -p gpurun_out/final
+O=gpurun_out/final
+for v in 0 1; do
+SRD_NO_REVERSE=$v timeout 900 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none --cache-control none -k regex:"conv_tc|p_sample|nchw_to_act|upsample2x" --launch-skip 260 -c 330 --csv --log-file $O/ncu_launch_list_warm_norev$v.csv python bench.py --steps 1 --warmup 1 --no-cpu > $O/ncu_bench.log 2>&1; echo "ncu rc=$?"
+python tools/ncu_summary.py $O/ncu_launch_list_warm_norev$v.csv --pass-json $O/unet_pass_traffic_warm_norev$v.json
 done
