@@ -4,7 +4,6 @@ UNMODIFIED reference.
 
     python -m oracle.make_golden_variants      ->  tests/golden/variants.pt
 """
-import math
 import os
 import sys
 

@@ -1,7 +1,7 @@
 """GPU experiment: does interleaving two independent half-batches on two streams fill the per-launch tail / fill
 bubbles of the persistent conv kernels?  Compares one B-image graph against two B/2-image graphs replayed
 concurrently on two streams.   python tools/dual_stream_probe.py [B] [splits]"""
-import os, sys, json
+import os, sys
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
 import torch
