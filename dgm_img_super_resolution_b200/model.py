@@ -9,7 +9,6 @@ launches the sm_100a kernels of libsrdiff_b200.so through `engine.py`.  CPU tens
 
 Line numbers cite /root/reference/srdiff/model.py.
 """
-import math
 from functools import partial
 
 import numpy as np
