@@ -170,3 +170,36 @@ def test_config1_full_bench_batch(hp):
         assert torch.equal(one[0], out["bf16"][63])
     finally:
         M.runtime.precision = "bf16"
+
+
+@pytest.mark.parametrize("prec", ["bf16", "fp32"])
+def test_config0_full_T100_trajectory_matches_reference_fixture(hp, prec):
+    """configs[0]: the reference's own CPU-runnable case, ALL 100 steps, against the final image of the unmodified
+    reference (tests/golden/sample_T100.pt).  This is where rounding errors would accumulate: the north-star bar is
+    PSNR >= 40 dB on the final image."""
+    from conftest import golden
+    from oracle.make_golden_T100 import make_noises
+    f = golden("sample_T100.pt")
+    M, diff = build_ours(hp, device=DEV)
+    assert diff.num_timesteps == f["T"] == 100
+    img_lr, img_lr_up, _ = gen_inputs(1, 40, 40, hp["sr_scale"], f["seed_inputs"])
+    noises = make_noises(f["T"], img_lr_up.shape)
+    state = {"i": 0}
+
+    def nxt(dev):
+        n = noises[state["i"]].to(dev)
+        state["i"] += 1
+        return n
+
+    old = (torch.randn, M.noise_like)
+    torch.randn = lambda *a, **k: nxt(k.get("device", "cpu"))
+    M.noise_like = lambda shape, device, repeat=False: nxt(device)
+    M.runtime.precision, M.runtime.noise, M.runtime.graph = prec, "torch", True
+    try:
+        img, _ = diff.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
+    finally:
+        torch.randn, M.noise_like = old
+        M.runtime.precision = "bf16"
+    assert state["i"] == 101
+    p = O.psnr(img.cpu(), f["img"].float())
+    assert p >= (40.0 if prec == "bf16" else 80.0), p

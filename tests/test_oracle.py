@@ -84,3 +84,16 @@ def test_oracle_against_live_reference(hp, cpu_state):
         o_out, o_feas = O.rrdb_forward(cpu_state, img_lr, hp)
         o_eps = O.unet_forward(cpu_state, x, t, o_feas, hp)
     assert O.rel_l2(o_out, r_out) < TOL and O.rel_l2(o_eps, r_eps) < 5e-6
+
+
+def test_oracle_full_T100_trajectory_matches_reference_fixture(hp, cpu_state):
+    """configs[0] end to end: one 40x40 -> 160x160 image through all 100 steps (fixture: final image of the
+    unmodified reference, fp16; inputs and the 101 noise tensors are regenerated from the stored seeds)."""
+    from oracle.make_golden_T100 import make_noises
+    f = golden("sample_T100.pt")
+    img_lr, img_lr_up, _ = gen_inputs(1, 40, 40, hp["sr_scale"], f["seed_inputs"])
+    noises = make_noises(f["T"], img_lr_up.shape)
+    with torch.no_grad():
+        img, _ = O.sample(cpu_state, O.make_schedule(f["T"], hp), hp, img_lr, img_lr_up, noises)
+    assert float(img.norm()) == pytest.approx(f["img_norm"], rel=1e-4)
+    assert O.psnr(img, f["img"].float()) > 100.0

@@ -41,3 +41,14 @@ for prec in precs:
     print("%-11s %-14s sample() PSNR vs reference %.1f dB, rrdb_out rel-L2 %.3e" % (
         prec, "sample_T4.pt", O.psnr(img.cpu(), g["img"]), O.rel_l2(rrdb_out.cpu(), g["rrdb_out"])))
     M4.runtime.precision = "bf16"
+    # the full configs[0] trajectory: all 100 steps against the reference's final image
+    from oracle.make_golden_T100 import make_noises  # noqa: E402
+    g = golden("sample_T100.pt")
+    M100, d100 = build_ours(hp, device=DEV)
+    M100.runtime.precision, M100.runtime.graph, M100.runtime.noise = prec, True, "torch"
+    img_lr, img_lr_up, _ = gen_inputs(1, 40, 40, hp["sr_scale"], g["seed_inputs"])
+    with inject_noise(M100, make_noises(g["T"], img_lr_up.shape)):
+        img, _ = d100.sample(img_lr.to(DEV), img_lr_up.to(DEV), tuple(img_lr_up.shape))
+    print("%-11s %-14s sample() T=100 PSNR vs reference %.1f dB" % (
+        prec, "sample_T100.pt", O.psnr(img.cpu(), g["img"].float())))
+    M100.runtime.precision = "bf16"
