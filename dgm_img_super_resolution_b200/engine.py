@@ -16,6 +16,7 @@ PRECISIONS = ("bf16", "fp32", "bf16_direct")
 # developer switch for A/B measurements: res_conv as a second output of block1's launch (SrdConvDesc.N2)
 FUSE_RES_CONV = os.environ.get("SRD_NO_FUSED_RES") != "1"
 REVERSE_ORDER = os.environ.get("SRD_NO_REVERSE", "0") != "1"   # alternate the tile order of consecutive conv launches
+FOLD_COND = os.environ.get("SRD_NO_FOLD_COND", "0") != "1"     # add cond after the first Downsample (see CondProgram)
 
 
 def _ceil(a, b):
@@ -415,6 +416,11 @@ class Builder:
 # --------------------------------------------------------------------------------------------
 # layer programs (mirror the reference's module graph; see model.py for the modules)
 # --------------------------------------------------------------------------------------------
+def M_hparams():
+    from . import model as M
+    return M.hparams
+
+
 def eff_weight(module):
     """The weight a conv module computes with.  Under torch.nn.utils.weight_norm (`Unet.apply_weight_norm`
     :808-814) that is g * v / ||v|| (norm over every dim but 0): `module.weight` itself is only refreshed by
@@ -435,23 +441,32 @@ def eff_weight(module):
 def _pc(module, attr="_srd_pack", **kw):
     """PackedConv attached to an nn.Conv2d / nn.ConvTranspose2d (cached on the module)."""
     p = module.__dict__.get(attr)
-    if getattr(module, "weight_g", None) is not None:
-        w = eff_weight(module)
-        if p is None or p.weight is not w or p.bias_p is not module.bias:
-            p = PackedConv(w, module.bias, transposed=False, stride=module.stride[0])
-            module.__dict__[attr] = p
-        return p
+    w = eff_weight(module)                 # module.weight, or the folded weight under weight norm
     bias = module.bias
     if bias is None:                       # bias-free conv (LinearAttention.to_qkv :511): a cached zero vector
         bias = module.__dict__.get("_srd_zero_bias")
-        if bias is None or bias.device != module.weight.device:
-            bias = torch.zeros(module.out_channels, dtype=torch.float32, device=module.weight.device)
+        if bias is None or bias.device != w.device:
+            bias = torch.zeros(module.out_channels, dtype=torch.float32, device=w.device)
             module.__dict__["_srd_zero_bias"] = bias
-    if p is None or p.weight is not module.weight or p.bias_p is not bias:
+    if p is None or p.weight is not w or p.bias_p is not bias:
         transposed = isinstance(module, torch.nn.ConvTranspose2d)
         stride = 1 if transposed else module.stride[0]
-        p = PackedConv(module.weight, bias, transposed=transposed, stride=stride)
+        p = PackedConv(w, bias, transposed=transposed, stride=stride)
         module.__dict__[attr] = p
+    return p
+
+
+def _pc_nobias(module):
+    """PackedConv of an nn.Conv2d with a zero bias (for the linear part of a conv applied to a constant term)."""
+    w = eff_weight(module)              # (under weight norm `module.weight` is a stale non-parameter attribute)
+    z = module.__dict__.get("_srd_zero_bias2")
+    if z is None or z.device != w.device:
+        z = torch.zeros(module.out_channels, dtype=torch.float32, device=w.device)
+        module.__dict__["_srd_zero_bias2"] = z
+    p = module.__dict__.get("_srd_pack_nobias")
+    if p is None or p.weight is not w or p.bias_p is not z:
+        p = PackedConv(w, z, transposed=False, stride=module.stride[0])
+        module.__dict__["_srd_pack_nobias"] = p
     return p
 
 
@@ -524,7 +539,7 @@ class UnetProgram:
     precomputed table row addressed through RunCtx.temb_ptr.
     """
 
-    def __init__(self, unet, B, H, W, precision, device, cond_act=None, per_sample_temb=False):
+    def __init__(self, unet, B, H, W, precision, device, cond_act=None, per_sample_temb=False, dcond_act=None):
         from . import model as M
         hp = M.hparams
         bld = self.bld = Builder(device, precision)
@@ -553,13 +568,14 @@ class UnetProgram:
             x1 = bld.act(B, h, w, d)
             build_resnet(bld, r0, x_src, d, x1, RB, offs[id(r0)], temb_bstride)
             x2 = bld.act(B, h, w, d)
-            extra = (self.cond, 0, 1.0) if i == 0 else None          # `x = x + cond` :830
+            extra = (self.cond, 0, 1.0) if (i == 0 and dcond_act is None) else None          # `x = x + cond` :830
             build_resnet(bld, r1, [(x1, 0, d)], d, x2, RB, offs[id(r1)], temb_bstride, extra_res=extra)
             # (hparams['up_input']: `+ up_proj(img_lr_up)` :831-832 is already part of `cond`, see CondProgram)
             hs.append((x2, d))
             if i < nlev - 1:
                 xd = bld.act(B, h // 2, w // 2, d)
-                bld.conv(_pc(down.conv[1]), [(x2, 0, d)], out=xd, act=L.ACT_NONE, border=RB)   # :494-503
+                bld.conv(_pc(down.conv[1]), [(x2, 0, d)], out=xd, act=L.ACT_NONE, border=RB,
+                         res2=(dcond_act, 0, 1.0) if (i == 0 and dcond_act is not None) else None)   # :494-503
                 x_src = [(xd, 0, d)]
                 h, w = h // 2, w // 2
             else:
@@ -690,17 +706,29 @@ class CondProgram:
             raise RuntimeError(
                 "cond_proj expects %d input channels but the RRDB features provide %d (%d maps of %d): "
                 "cond_dim / rrdb_num_feat / rrdb_num_block mismatch" % (cin_total, sum(cins), len(sel), cins[0]))
+        # `x = x + cond` :830 sits right before the first Downsample (a ReflectionPad2d + stride-2 conv, both linear)
+        # and that sum has no other reader (the level-0 skip is never popped), so when FOLD_COND the
+        # Unet adds `Downsample_linear(cond)` -- time-invariant, a quarter of the pixels -- to the Downsample's
+        # output instead of reading the full-resolution cond tensor in every step.
+        down = unet.downs[0][2]
+        self.fold = FOLD_COND and len(unet.downs) > 1 and not isinstance(down, torch.nn.Identity)
+        ring = L.BORDER_REFLECT if self.fold else L.BORDER_KEEP
+        up_in = bool(M_hparams()['res'] and M_hparams()['up_input'])
         self.cond = bld.act(a0.B, a0.H * S, a0.W * S, unet._dims[1])
-        bld.conv(_pc(unet.cond_proj), [(a, 0, c) for a, c in zip(sel, cins)], out=self.cond, border=L.BORDER_KEEP)
+        bld.conv(_pc(unet.cond_proj), [(a, 0, c) for a, c in zip(sel, cins)], out=self.cond,
+                 border=L.BORDER_KEEP if up_in else ring)
         # hparams['up_input'] (:803-806, 831-832): x = x + cond + up_proj(img_lr_up) -- time-invariant as well, so
         # it is folded into the cached cond tensor.  `lr_up` (3 channels, reflect ring) is filled by the caller.
         self.lr_up = None
-        from . import model as M
-        if M.hparams['res'] and M.hparams['up_input']:
+        if up_in:
             self.lr_up = bld.act(a0.B, a0.H * S, a0.W * S, 3)
             raw, self.cond = self.cond, bld.act(a0.B, a0.H * S, a0.W * S, unet._dims[1])
-            bld.conv(_pc(unet.up_proj[1]), [(self.lr_up, 0, 3)], out=self.cond, res1=(raw, 0, 1.0),
-                     border=L.BORDER_KEEP)
+            bld.conv(_pc(unet.up_proj[1]), [(self.lr_up, 0, 3)], out=self.cond, res1=(raw, 0, 1.0), border=ring)
+        self.dcond = None
+        if self.fold:
+            c = self.cond
+            self.dcond = bld.act(c.B, c.H // 2, c.W // 2, unet._dims[1])
+            bld.conv(_pc_nobias(down.conv[1]), [(c, 0, unet._dims[1])], out=self.dcond, border=L.BORDER_KEEP)
 
     def load_lr_up(self, img_lr_up):
         """img_lr_up: fp32 NCHW [B, 3, H, W] (only when the Unet has `up_proj`)."""
@@ -797,7 +825,8 @@ class SamplerPlan:
         unet, rrdb = diffusion.denoise_fn, diffusion.rrdb
         self.rrdb_prog = RRDBProgram(rrdb, B, h, w, self.prec, device)
         self.cond_prog = CondProgram(unet, self.rrdb_prog.feas, self.prec, device)
-        self.unet_prog = UnetProgram(unet, B, self.H, self.W, self.prec, device, cond_act=self.cond_prog.cond)
+        self.unet_prog = UnetProgram(unet, B, self.H, self.W, self.prec, device, cond_act=self.cond_prog.cond,
+                                     dcond_act=self.cond_prog.dcond)
         C_ = unet._out_dim
         f32 = dict(dtype=torch.float32, device=device)
         self.x = torch.empty((B, C_, self.H, self.W), **f32)

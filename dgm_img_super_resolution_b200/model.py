@@ -404,7 +404,8 @@ class Unet(nn.Module):
                 raise RuntimeError("cond features have %d channels, Unet was built with cond_dim=%d"
                                    % (sel[0].shape[1], self._cond_dim))
             cprog = E.CondProgram(self, fea_acts, bld.prec, dev)
-            uprog = E.UnetProgram(self, B, H, W, bld.prec, dev, cond_act=cprog.cond, per_sample_temb=True)
+            uprog = E.UnetProgram(self, B, H, W, bld.prec, dev, cond_act=cprog.cond, per_sample_temb=True,
+                                  dcond_act=cprog.dcond)
             p = (key, (bld, fea_acts, cprog, uprog))
             self._progs["p"] = p
         bld, fea_acts, cprog, uprog = p[1]
