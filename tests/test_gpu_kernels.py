@@ -278,3 +278,33 @@ def test_philox_sampler_runs_and_is_shard_invariant(hp):
         assert torch.equal(full[2:], half)          # image k of a batch == the same image in a shard
     finally:
         M.runtime.noise, M.runtime.image_offset = "torch", 0
+
+
+@pytest.mark.parametrize("a_mode,what", [(1 | 64, "ticket-based item scheduling"), (1 | 4, "single-CTA MMAs"),
+                                         (1 | 16, "resident weights with MT = 1"), (1 | 8, "no dependent launch"),
+                                         (1 | 2, "register epilogue"), (0, "per-kx activation boxes")])
+def test_tc_mode_switches_do_not_change_results(ours, a_mode, what):
+    """The tuning / validation switches of srd_tc_set_mode change HOW the tcgen05 kernel works, never what it computes:
+    a ResnetBlock with enough tiles for several item rounds per CTA pair gives the same bits in every scheduling /
+    pairing / launch mode (64 -> 128 channels: 1x1 res_conv as a second output), and the same values up to the
+    rounding order of the residual add with the register epilogue or the per-kx activation boxes (64 -> 64: those two
+    modes do not offer the second output)."""
+    from dgm_img_super_resolution_b200 import _lib as L
+    M, _ = ours
+    M.runtime.precision = "bf16"
+    exact = a_mode not in (1 | 2, 0)
+    g = torch.Generator().manual_seed(97)
+    x = torch.randn((48, 64, 40, 40), generator=g).to(DEV)
+    outs = []
+    try:
+        for mode in (1, a_mode):
+            L.check(L.lib().srd_tc_set_mode(mode, 1), "srd_tc_set_mode")
+            blk = _mk(M, M.ResnetBlock, 64, 128 if exact else 64, time_emb_dim=0, groups=0, seed=5)   # new plans
+            outs.append(blk(x))
+    finally:
+        L.check(L.lib().srd_tc_set_mode(1, 1), "srd_tc_set_mode")
+    if exact:
+        assert torch.equal(outs[0], outs[1]), what
+    else:
+        assert O.rel_l2(outs[1].cpu(), outs[0].cpu()) < 3e-3, what
+    assert L.lib().srd_tc_set_mode(128, 1) != 0 and L.lib().srd_watchdog_flag() == 0
