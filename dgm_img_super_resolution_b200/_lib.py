@@ -92,6 +92,7 @@ SYMBOLS = {
     "srd_tc_set_mode": (C.c_int, [_i32, _i32]),
     "srd_tc_set_debug": (C.c_int, [_vp]),
     "srd_time_table": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
+    "srd_sinusoidal_emb": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),
     "srd_p_sample_step": (C.c_int, [C.POINTER(SrdPSampleArgs), _vp]),
     "srd_randn": (C.c_int, [_vp, _i32, _i32, _u64, _u32, _u32, _vp]),
     "srd_nchw_to_act": (C.c_int, [_vp, _i32, _i32, _i32, _i32, _f, _f, _vp, _i32, _i32, _i32, _vp]),
@@ -152,4 +153,6 @@ def lib():
 def check(rc, what=""):
     if rc != 0:
         msg = lib().srd_last_error()
-        raise SrdError("%s failed: %s" % (what or "libsrdiff_b200 call", msg.decode() if msg else "?"))
+        wd = lib().srd_watchdog_flag()
+        raise SrdError("%s failed: %s%s" % (what or "libsrdiff_b200 call", msg.decode() if msg else "?",
+                                            " [tcgen05 pipeline watchdog fired: wait #%d]" % wd if wd else ""))

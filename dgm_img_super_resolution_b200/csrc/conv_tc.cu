@@ -1,25 +1,27 @@
 // NHWC bf16 implicit-GEMM convolution on the 5th-gen tensor cores (sm_100a):
-// TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory -> tcgen05.mma (cta_group::1,
-// M=128, N=Cout<=256, K=16) -> fp32 accumulators in TMEM -> tcgen05.ld -> fused epilogue.
+// TMA (cp.async.bulk.tensor) -> 128B-swizzled shared memory -> tcgen05.mma.cta_group::2 (CTA pairs, M = 256 = two
+// 128-pixel tiles, N = Cout <= 256, K = 16) -> fp32 accumulators in TMEM -> tcgen05.ld -> fused epilogue -> TMA stores.
 //
-// Serves every multi-channel conv on the hot path:
-// 3x3 stride-1 (reflect or zero ring), 3x3 stride-2, ConvTranspose2d k=2S/stride S as S*S
-// sub-pixel phases, 1x1, with up to three K sources (the never-materialised torch.cat).
+// Serves every multi-channel conv on the hot path: 3x3 stride-1 (reflect or zero
+// ring), 3x3 stride-2, ConvTranspose2d k=2S/stride S as S*S sub-pixel phases, 1x1, up to three K sources (the
+// never-materialised torch.cat), an optional second 1x1 output (res_conv) and a fused 1x1 head (final_conv.1).
 //
-// Geometry.  Activations are padded NHWC [B][H+2][W+2][ct] bf16; all images are viewed as
-// ONE stack of B*(H+2) rows, so an M tile is 16 stacked rows x 8 columns = 128 output
-// positions and may straddle images (ring rows become masked garbage rows: efficiency
-// H/(H+2) instead of rounding H up to 16 per image).  Per (source, 64-channel chunk, kx) the
-// producer issues ONE TMA box {64ch, 8px, 18 rows}; the three ky taps are the same smem box
-// read at row offsets 0/1/2 (1 row = 8 px * 128 B = one 1024 B swizzle atom, so every UMMA
-// descriptor stays 1024 B aligned).  A traffic = 3 * 18/16 = 3.4x instead of 9x.  Weights
-// stream through their own ring as [Npad][64] K-major tiles.  MT (1|2) M tiles share every
-// weight tile to halve B traffic.
+// Geometry.  Activations are padded NHWC [B][H+2][W+2][ct] bf16; all images are viewed as ONE stack of B*(H+2) rows,
+// so an M tile is 16 stacked rows x 8 columns = 128 output positions and may straddle images (ring rows become
+// masked rows: efficiency H/(H+2) instead of rounding H up to 16 per image).  Stride 1: per (source, 64-channel
+// chunk) ONE halo box {64 ch, 10 px, 18 rows} per tile; the nine taps are that box addressed through UMMA descriptor
+// start offsets of (ky*10 + kx)*128 B with SBO = 1280 B.  Stride 2: one box per (kx, row parity) of a parity-split
+// 5-D map.  Weights are [k-block][Npad][64] K-major tiles, resident in shared memory when they fit, else streamed
+// through a ring; each CTA of a pair holds half of every weight tile.  MT (1|2) tile pairs share every weight tile.
 //
-// Pipeline.  warp 0: TMA producer (1 lane).  warp 1: MMA issuer (1 lane) + TMEM owner.
-// warps 2-5: epilogue (thread = output pixel = TMEM lane; channels in 16-column chunks).
-// Rings: A full/empty, B full/empty, TMEM full/empty (2 accumulator stages) so the epilogue
-// of tile i overlaps the MMAs of tile i+1.  Persistent CTAs, static round-robin tile order.
+// Roles (608 threads): warps 0-15 epilogue (4 groups x the 4 TMEM lane quarters; thread = output pixel = TMEM lane,
+// 16-column chunks; per-warp swizzled staging buffer + cp.async.bulk.tensor stores, residual prefetched into it),
+// warp 16 activation-TMA producer, warp 17 weight-TMA producer, warp 18 MMA issuer + TMEM owner (one thread each).
+// Rings: A full/empty, B full/empty, 2-4 TMEM accumulator stages full/empty.  Persistent CTAs, static item order.
+//
+// Two entry points share the role code: conv_tc_kernel (one layer per launch) and conv_chain_kernel (a list of
+// layers in ONE launch; CTAs move from layer to layer on their own, ordered by per-row-block completion counters
+// instead of kernel boundaries -- see the "layer chain" section).
 #include <cuda.h>
 #include <string.h>
 #include <new>
@@ -154,13 +156,31 @@ __device__ __forceinline__ bool mbar_try(uint32_t bar, uint32_t parity) {
       : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
   return ok != 0;
 }
-// Bounded wait: a protocol bug must not hang the GPU (a hang costs the whole box).
+// Bounded wait: a protocol bug must not hang the GPU (a hang costs the whole box).  The bound is TIME
+// (%globaltimer, 20 s), not a spin count: under a profiler, time-slicing or a PDL-overlapped predecessor a
+// legitimate wait (e.g. the weight producer parked behind the previous grid) can spin arbitrarily often.
+__device__ __forceinline__ unsigned long long global_ns() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+  return t;
+}
+constexpr unsigned long long WATCHDOG_NS = 20ull * 1000 * 1000 * 1000;
+__device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* err_flag, int code) {
+  const unsigned long long t0 = global_ns();
+  while (!mbar_try(bar, parity)) {
+    __nanosleep(64);
+    if (global_ns() - t0 > WATCHDOG_NS) {
+      if (err_flag) atomicExch(err_flag, code);
+      __trap();
+    }
+  }
+}
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* err_flag, int code) {
   uint32_t spins = 0;
   while (!mbar_try(bar, parity)) {
-    if (++spins > (1u << 25)) {                 // ~seconds: far beyond any legitimate wait
-      if (err_flag) atomicExch(err_flag, code);
-      __trap();
+    if (++spins > (1u << 16)) {                 // ~tens of ms of hardware try_wait windows: switch to the slow path
+      mbar_wait_slow(bar, parity, err_flag, code);
+      return;
     }
   }
 }
@@ -1607,6 +1627,10 @@ int tc_supported(const SrdConvDesc& d, const char** why) {
   return w == nullptr;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize is a per-DEVICE attribute: set it once per device ordinal, not once
+// per process (a second GPU in the same process would otherwise fail every launch that needs > 48 KB).
+static int tc_set_func_attrs(int dev);
+
 struct TcPlan {
   TcArgs args;
   int grid, smem;
@@ -1859,12 +1883,18 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
       SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(dst2) failed with %d", (int)r);
     }
   }
-  static bool attr_set = false;
-  if (!attr_set) {
-    SRD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    SRD_CUDA(cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
-    attr_set = true;
-  }
+  SRD_CHECK(tc_set_func_attrs(dev) == 0, "conv_tc: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+  return 0;
+}
+
+static int tc_set_func_attrs(int dev) {
+  static bool done[64] = {};
+  if (dev < 0 || dev >= 64) return 1;
+  if (done[dev]) return 0;
+  if (cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    return 1;
+  done[dev] = true;
   return 0;
 }
 

@@ -98,8 +98,9 @@ __global__ void __launch_bounds__(256, 3) p_sample_kernel(const SrdPSampleArgs a
       for (int c = 0; c < 4; ++c) {
         if (c < a.C) {
           const size_t off = ((size_t)b * a.C + c) * HW + pix;
-          px4[c] = __ldg(reinterpret_cast<const float4*>(a.x + off));
-          pe4[c] = __ldg(reinterpret_cast<const float4*>(a.eps + off));
+          // plain (coherent) loads: x_out may alias x, and ld.global.nc on memory this kernel writes is undefined
+          px4[c] = *reinterpret_cast<const float4*>(a.x + off);
+          pe4[c] = *reinterpret_cast<const float4*>(a.eps + off);
         }
       }
     }
@@ -312,6 +313,17 @@ __global__ void __launch_bounds__(256) time_table_kernel(
   }
 }
 
+// SinusoidalPosEmb.forward :412-419: out[i] = cat(sin(t[i] * f), cos(t[i] * f)), f[dim/2] host-provided
+__global__ void sinusoidal_emb_kernel(const float* t, int n, int half, const float* freqs, float* out) {
+  const int total = n * half;
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+    const int r = i / half, j = i % half;
+    const float arg = __fmul_rn(t[r], freqs[j]);
+    out[(size_t)r * 2 * half + j] = sinf(arg);
+    out[(size_t)r * 2 * half + half + j] = cosf(arg);
+  }
+}
+
 static inline int grid_for(long long total, int block = 256) {
   long long g = (total + block - 1) / block;
   const long long cap = 148LL * 16;
@@ -331,6 +343,13 @@ int srd_time_table(const float* t_values, int32_t n_t, int32_t dim, const float*
   const size_t smem = (size_t)6 * dim * sizeof(float);
   time_table_kernel<<<n_t, 256, smem, (cudaStream_t)stream>>>(t_values, dim, freqs, w0, b0, w2, b2,
                                                               w_blk, b_blk, S, out);
+  SRD_CUDA(cudaGetLastError());
+  return 0;
+}
+
+int srd_sinusoidal_emb(const float* t, int32_t n, int32_t dim, const float* freqs, float* out, void* stream) {
+  SRD_CHECK(t && freqs && out && n > 0 && dim >= 4 && (dim % 2) == 0, "srd_sinusoidal_emb: bad arguments");
+  sinusoidal_emb_kernel<<<grid_for((long long)n * (dim / 2)), 256, 0, (cudaStream_t)stream>>>(t, n, dim / 2, freqs, out);
   SRD_CUDA(cudaGetLastError());
   return 0;
 }

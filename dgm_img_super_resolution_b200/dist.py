@@ -38,16 +38,22 @@ def sample_sharded(diffusion, img_lr, img_lr_up, sample_fn=None, group=None):
     """Run `GaussianDiffusion.sample` on this rank's slice of the global batch and gather.
 
     img_lr / img_lr_up are the GLOBAL batch (same on every rank).  Returns (img, rrdb_out) for the
-    global batch on every rank.  `runtime.image_offset` is set to the slice start so in-kernel
-    Philox noise depends only on the global image index (shard-invariant results).
+    global batch on every rank.  Noise is ALWAYS the in-kernel Philox stream here (`runtime.noise` is
+    forced to "philox" for the call) keyed by the global image index (`runtime.image_offset` = slice
+    start) and by ONE seed agreed on by all ranks (rank 0's, broadcast), so the result does not depend on
+    how the batch is sharded: N ranks produce bit for bit what one GPU produces for the whole batch.
+    (torch.randn-based noise would give every rank the same per-slice draws: correlated, shard-dependent.)
     """
     from . import model as M
     world, rank = dist.get_world_size(group), dist.get_rank(group)
     total = img_lr.shape[0]
     start, count = shard_range(total, world, rank)
     lr, up = img_lr[start:start + count], img_lr_up[start:start + count]
-    old = M.runtime.image_offset
-    M.runtime.image_offset = start
+    old = (M.runtime.image_offset, M.runtime.noise, M.runtime.seed_counter, M.runtime.seed_override)
+    # one seed for the whole job: rank 0 draws it, everybody uses it
+    seed = torch.tensor([M.next_seed(img_lr.device) if rank == 0 else 0], dtype=torch.int64, device=img_lr.device)
+    dist.broadcast(seed, src=dist.get_global_rank(group, 0) if group is not None else 0, group=group)
+    M.runtime.image_offset, M.runtime.noise, M.runtime.seed_override = start, "philox", int(seed.item())
     try:
         if count > 0:
             fn = sample_fn or (lambda a, b, off: diffusion.sample(a, b, tuple(b.shape)))
@@ -56,5 +62,5 @@ def sample_sharded(diffusion, img_lr, img_lr_up, sample_fn=None, group=None):
             img = img_lr_up.new_zeros((0,) + tuple(img_lr_up.shape[1:]))
             rrdb_out = img.clone()
     finally:
-        M.runtime.image_offset = old
+        M.runtime.image_offset, M.runtime.noise, _, M.runtime.seed_override = old
     return gather_outputs(img, total, group), gather_outputs(rrdb_out, total, group)

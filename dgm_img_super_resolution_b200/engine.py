@@ -65,27 +65,41 @@ class Act:
 # --------------------------------------------------------------------------------------------
 # weight packing (one-time re-layout; see include/srdiff_b200.h for the layouts)
 # --------------------------------------------------------------------------------------------
+def _chunked(wp, nch):
+    """[rows][nch*64][...] -> [rows][nch][64][...]"""
+    return wp.reshape(wp.shape[0], nch, 64, *wp.shape[2:])
+
+
+def _pack_conv_blocks(w, src_cins, ky_order):
+    """Per source the K-blocks [nch][kw][ky*][Npad][64] (fp32) of an nn.Conv2d weight [O][I][kh][kw]: block
+    (chunk, kx, ky) holds w[:, chunk*64 + c, ky, kx] as an [Npad][64] K-major tile, zero padded.  A handful of
+    whole-tensor ops per source (pad, gather, permute) -- not one copy per (chunk, tap)."""
+    O, I, kh, kw = w.shape
+    npad = _ceil(O, 16) * 16
+    ky_idx = torch.tensor(ky_order, device=w.device)
+    out, a = [], 0
+    for cin in src_cins:
+        nch = _ceil(cin, 64)
+        wp = torch.nn.functional.pad(w[:, a:a + cin], (0, 0, 0, 0, 0, nch * 64 - cin, 0, npad - O))
+        blk = _chunked(wp, nch).index_select(3, ky_idx).permute(1, 4, 3, 0, 2)    # [nch][kw][ky*][npad][64]
+        out.append(blk)
+        a += cin
+    return out
+
+
 def _pack_conv(weight, src_cins, stride):
     """nn.Conv2d weight [O][I][kh][kw] -> (w_direct fp32 [1][K][O], w_tc bf16 [KB][Npad][64])."""
     O, I, kh, kw = weight.shape
     assert sum(src_cins) == I, (src_cins, I)
     npad = _ceil(O, 16) * 16
     w = weight.detach().float()
-    parts, blocks, a = [], [], 0
     ky_order = [0, 2, 1] if stride == 2 else list(range(kh))
+    parts, a = [], 0
     for cin in src_cins:
-        ws = w[:, a:a + cin]
-        parts.append(ws.permute(2, 3, 1, 0).reshape(kh * kw * cin, O))
-        nch = _ceil(cin, 64)
-        blk = torch.zeros((nch, kw, len(ky_order), npad, 64), dtype=torch.float32, device=w.device)
-        for ch in range(nch):
-            c0, c1 = ch * 64, min(cin, ch * 64 + 64)
-            for kx in range(kw):
-                for j, ky in enumerate(ky_order):
-                    blk[ch, kx, j, :O, :c1 - c0] = ws[:, c0:c1, ky, kx]
-        blocks.append(blk.reshape(-1, npad, 64))
+        parts.append(w[:, a:a + cin].permute(2, 3, 1, 0).reshape(kh * kw * cin, O))
         a += cin
-    w_direct = torch.cat(parts, 0).contiguous()[None].contiguous()
+    w_direct = torch.cat(parts, 0)[None].contiguous()
+    blocks = [b.reshape(-1, npad, 64) for b in _pack_conv_blocks(w, src_cins, ky_order)]
     w_tc = torch.cat(blocks, 0).to(torch.bfloat16).contiguous()
     return w_direct, w_tc
 
@@ -93,37 +107,26 @@ def _pack_conv(weight, src_cins, stride):
 def _pack_convT(weight, src_cins, S):
     """nn.ConvTranspose2d(k=2S, stride=S, pad=S/2) weight [I][O][2S][2S] -> per sub-pixel phase
     (r, s) a 2x2-tap conv: out[y*S+r] += in[y+dy] * w[ky], ky = r + S/2 - dy*S (dy in {-1,0} for
-    r < S/2, {0,1} otherwise).  SURVEY 7.4 tap tables."""
+    r < S/2, {0,1} otherwise).  SURVEY 7.4 tap tables.  All phases are gathered at once through the
+    [S][2] tap-index table."""
     I, O, k, _ = weight.shape
     assert k == 2 * S and sum(src_cins) == I
     npad = _ceil(O, 16) * 16
     w = weight.detach().float()
-    directs, tcs = [], []
-    for r in range(S):
-        ky0 = 1 if r >= S // 2 else 0
-        kys = [r + S // 2 - (ky0 + d - 1) * S for d in range(2)]
-        for s in range(S):
-            kx0 = 1 if s >= S // 2 else 0
-            kxs = [s + S // 2 - (kx0 + d - 1) * S for d in range(2)]
-            parts, blocks, a = [], [], 0
-            for cin in src_cins:
-                ws = w[a:a + cin]                                 # [cin][O][k][k]
-                for dy in range(2):
-                    for dx in range(2):
-                        parts.append(ws[:, :, kys[dy], kxs[dx]])   # [cin][O]
-                nch = _ceil(cin, 64)
-                blk = torch.zeros((nch, 2, 2, npad, 64), dtype=torch.float32, device=w.device)
-                for ch in range(nch):
-                    c0, c1 = ch * 64, min(cin, ch * 64 + 64)
-                    for dx in range(2):
-                        for dy in range(2):
-                            blk[ch, dx, dy, :O, :c1 - c0] = ws[c0:c1, :, kys[dy], kxs[dx]].t()
-                blocks.append(blk.reshape(-1, npad, 64))
-                a += cin
-            directs.append(torch.cat(parts, 0))
-            tcs.append(torch.cat(blocks, 0))
-    w_direct = torch.stack(directs).contiguous()
-    w_tc = torch.stack(tcs).to(torch.bfloat16).contiguous()
+    taps = torch.tensor([[r + S // 2 - ((1 if r >= S // 2 else 0) + d - 1) * S for d in range(2)] for r in range(S)],
+                        device=w.device)                                   # [S][2]: kernel index of tap d in phase r
+    directs, tcs, a = [], [], 0
+    for cin in src_cins:
+        ws = w[a:a + cin]                                                  # [cin][O][k][k]
+        g = ws[:, :, taps][..., taps]                                      # [cin][O][r][dy][s][dx]
+        directs.append(g.permute(2, 4, 3, 5, 0, 1).reshape(S * S, 4 * cin, O))         # K order (dy, dx, c)
+        nch = _ceil(cin, 64)
+        gp = torch.nn.functional.pad(g, (0, 0, 0, 0, 0, 0, 0, 0, 0, npad - O, 0, nch * 64 - cin))
+        gp = gp.reshape(nch, 64, npad, S, 2, S, 2)                         # [ch][c][n][r][dy][s][dx]
+        tcs.append(gp.permute(3, 5, 0, 6, 4, 2, 1).reshape(S * S, nch * 4, npad, 64))  # blocks (chunk, dx, dy)
+        a += cin
+    w_direct = torch.cat(directs, 1).contiguous()
+    w_tc = torch.cat(tcs, 1).to(torch.bfloat16).contiguous()
     return w_direct, w_tc
 
 
@@ -133,19 +136,11 @@ def _pack_conv_dual(w3, w1, src_cins):
     O, I, kh, kw = w3.shape
     assert (kh, kw) == (3, 3) and tuple(w1.shape) == (O, I, 1, 1) and sum(src_cins) == I
     npad = _ceil(O, 16) * 16
-    a3, a1 = w3.detach().float(), w1.detach().float()
-    blocks, a = [], 0
-    for cin in src_cins:
-        for ch in range(_ceil(cin, 64)):
-            c0, c1 = a + ch * 64, a + min(cin, ch * 64 + 64)
-            blk = torch.zeros((10, npad, 64), dtype=torch.float32, device=a3.device)
-            for kx in range(3):
-                for ky in range(3):
-                    blk[kx * 3 + ky, :O, :c1 - c0] = a3[:, c0:c1, ky, kx]
-            blk[9, :O, :c1 - c0] = a1[:, c0:c1, 0, 0]
-            blocks.append(blk)
-        a += cin
-    return torch.cat(blocks, 0).to(torch.bfloat16).contiguous()
+    b3 = _pack_conv_blocks(w3.detach().float(), src_cins, [0, 1, 2])
+    b1 = _pack_conv_blocks(w1.detach().float(), src_cins, [0])
+    blocks = [torch.cat([x.reshape(x.shape[0], 9, npad, 64), y.reshape(y.shape[0], 1, npad, 64)], 1)
+              for x, y in zip(b3, b1)]
+    return torch.cat([b.reshape(-1, npad, 64) for b in blocks], 0).to(torch.bfloat16).contiguous()
 
 
 def _pack_conv_win8(weight):
@@ -531,6 +526,24 @@ def build_resnet(bld, blk, srcs, dim_out, out, border, temb_off, temb_bstride=0,
     return out
 
 
+def build_rdb_input(bld, x, nf, gc):
+    """(nf + 4 gc)-channel dense-block buffer whose first nf channels hold the fp32 NCHW tensor `x` (zero ring)."""
+    B, _, H, W = x.shape
+    cat = bld.act(B, H, W, nf + 4 * gc)
+    bld.nchw_to_act(lambda: x, cat, nf)
+    return cat
+
+
+def build_rdb(bld, rdb, cat, nf, gc, out, alpha, res1, res2=None, out2=None):
+    """ResidualDenseBlock_5C.forward :685-690 on a dense-block buffer `cat` whose channels [0, nf) hold x:
+    conv1..4 append their gc output channels in place (the `torch.cat`s), conv5 writes
+    alpha * conv5(cat) + beta1 * res1 [+ beta2 * res2] into channels [0, nf) of `out` (and `out2`)."""
+    K, LR = L.BORDER_KEEP, L.ACT_LRELU02
+    for k, conv in enumerate((rdb.conv1, rdb.conv2, rdb.conv3, rdb.conv4)):
+        bld.conv(_pc(conv), [(cat, 0, nf + k * gc)], out=cat, out_coff=nf + k * gc, act=LR, border=K)
+    bld.conv(_pc(rdb.conv5), [(cat, 0, nf + 4 * gc)], out=out, out2=out2, alpha=alpha, res1=res1, res2=res2, border=K)
+
+
 class UnetProgram:
     """Unet.forward :820-847 for fixed (B, H, W) as a static launch list.
 
@@ -646,13 +659,11 @@ class RRDBProgram:
             x_rrdb = self.fea_first if i == 0 else self.feas[i - 1]
             for j, rdb in enumerate((blk.RDB1, blk.RDB2, blk.RDB3)):
                 c, n = cats[cur], cats[cur ^ 1]
-                for k, conv in enumerate((rdb.conv1, rdb.conv2, rdb.conv3, rdb.conv4)):     # :685-688
-                    bld.conv(_pc(conv), [(c, 0, nf + k * gc)], out=c, out_coff=nf + k * gc, act=LR, border=K)
                 if j < 2:       # x5*0.2 + x :690
-                    bld.conv(_pc(rdb.conv5), [(c, 0, ctot)], out=n, alpha=0.2, res1=(c, 0, 1.0), border=K)
+                    build_rdb(bld, rdb, c, nf, gc, n, alpha=0.2, res1=(c, 0, 1.0))
                 else:           # (x5*0.2 + x)*0.2 + x_rrdb :690,706
-                    bld.conv(_pc(rdb.conv5), [(c, 0, ctot)], out=n, out2=self.feas[i], alpha=0.04,
-                             res1=(c, 0, 0.2), res2=(x_rrdb, 0, 1.0), border=K)
+                    build_rdb(bld, rdb, c, nf, gc, n, alpha=0.04, res1=(c, 0, 0.2), res2=(x_rrdb, 0, 1.0),
+                              out2=self.feas[i])
                 cur ^= 1
         # trunk_conv + fea_first :734-736
         bld.conv(_pc(rrdb.trunk_conv), [(cats[cur], 0, nf)], out=self.feas[nb], res1=(self.fea_first, 0, 1.0),
@@ -887,10 +898,11 @@ class SamplerPlan:
         the shard's image offset is baked into the kernel arguments and keys the graph."""
         self.seed_dev.fill_(seed & 0x7FFFFFFFFFFFFFFF)
         key = (use_noise_buf, image_offset if not use_noise_buf else 0)
-        g = self.graphs.get(key)
+        g = self.graphs.pop(key, None)
         if g is None:
-            if len(self.graphs) >= 4:
-                self.graphs.clear()
+            from . import model as M
+            while len(self.graphs) >= max(1, M.runtime.graph_cache_size):     # LRU (dicts keep insertion order)
+                self.graphs.pop(next(iter(self.graphs)))
             noises = self.ensure_noise_buf() if use_noise_buf else None
             # warm-up outside capture (lazy module/func loading, cudaFuncSetAttribute)
             x_save = self.x.clone()
@@ -907,7 +919,7 @@ class SamplerPlan:
             with torch.cuda.graph(g):
                 self.encode()
                 self.loop(noises, seed, image_offset)
-            self.graphs[key] = g
+        self.graphs[key] = g                                                  # most recently used last
         g.replay()
 
     def n_launches(self):

@@ -9,6 +9,7 @@ launches the sm_100a kernels of libsrdiff_b200.so through `engine.py`.  CPU tens
 
 Line numbers cite /root/reference/srdiff/model.py.
 """
+import math
 from functools import partial
 
 import numpy as np
@@ -29,11 +30,61 @@ class Runtime:
     #                           "philox": generated inside the p_sample kernel (throughput mode)
     graph = True              # capture encode + T-step loop in one CUDA graph
     noise_budget_bytes = 8 << 30
+    plan_cache_size = 4       # SamplerPlans kept per GaussianDiffusion (LRU; one per (B, h, w, precision, device))
+    graph_cache_size = 8      # captured CUDA graphs kept per SamplerPlan (LRU; one per noise mode / image offset)
     seed_counter = 0
     image_offset = 0          # global index of image 0 of this shard (multi-GPU shard invariance)
+    seed_override = None      # Philox seed forced for the next sample() calls (dist.sample_sharded: one job-wide seed)
 
 
 runtime = Runtime()
+
+
+def next_seed(device):
+    """Philox seed of the next sampler call: derived from the device's torch generator seed (so torch.manual_seed
+    steers it) and a per-process call counter; `runtime.seed_override` pins it instead."""
+    if runtime.seed_override is not None:
+        return int(runtime.seed_override) & 0x7FFFFFFFFFFFFFFF
+    runtime.seed_counter += 1
+    if getattr(device, "type", "cuda") != "cuda":          # host-logic tests (gloo): no CUDA generator to read
+        base = torch.initial_seed()
+    else:
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        base = torch.cuda.default_generators[idx].initial_seed()
+    return (base * 1000003 + runtime.seed_counter) & 0x7FFFFFFFFFFFFFFF
+
+_CACHE_ATTRS = ("_srd_pack", "_srd_pack_nobias", "_srd_wn", "_srd_zero_bias", "_srd_zero_bias2", "_srd_neg",
+                "_last_table")
+
+
+class _EngineCached(nn.Module):
+    """Mixin for the modules that own engine state (plan / program caches holding ctypes handles and CUDA graphs):
+    `copy.deepcopy(model)` (EMA copies) and pickling (`torch.save(model)`) carry the parameters only -- the copy
+    re-plans on first use."""
+    _cache_fields = ()
+
+    def _strip(self, state):
+        state = dict(state)
+        for k in self._cache_fields:
+            if k in state:
+                state[k] = {}
+        for k in _CACHE_ATTRS:
+            state.pop(k, None)
+        return state
+
+    def __getstate__(self):
+        return self._strip(self.__dict__)
+
+    def __deepcopy__(self, memo):
+        import copy
+        new = self.__class__.__new__(self.__class__)
+        memo[id(self)] = new
+        for k, v in self._strip(self.__dict__).items():
+            new.__dict__[k] = copy.deepcopy(v, memo)
+        for m in new.modules():                       # packed-weight caches hung on plain nn.Conv2d containers
+            for k in _CACHE_ATTRS:
+                m.__dict__.pop(k, None)
+        return new
 
 
 def initialize_weights(net_l, scale=0.1):
@@ -70,7 +121,8 @@ class Mish(nn.Module):
         E._require_cuda(x, "Mish input")
         xc = x.contiguous().float()
         y = torch.empty_like(xc)
-        L.check(L.lib().srd_mish_f32(xc.data_ptr(), y.data_ptr(), xc.numel(), E._stream()), "srd_mish_f32")
+        with torch.cuda.device(xc.device):
+            L.check(L.lib().srd_mish_f32(xc.data_ptr(), y.data_ptr(), xc.numel(), E._stream()), "srd_mish_f32")
         return y
 
 
@@ -81,17 +133,41 @@ class SinusoidalPosEmb(nn.Module):
         super().__init__()
         self.dim = dim
 
+    def forward(self, x):
+        """x [B] (any dtype) -> [B, dim] = cat(sin(x * f), cos(x * f)); the frequencies are evaluated on the host
+        exactly as :415-416 does (fp32 exp of an arange), the sin / cos by srd_sinusoidal_emb."""
+        E._require_cuda(x, "SinusoidalPosEmb input")
+        with torch.cuda.device(x.device):
+            t = x.reshape(-1).float().contiguous()
+            half = self.dim // 2
+            freqs = torch.exp(torch.arange(half) * -(math.log(10000) / (half - 1))).float().to(x.device)
+            out = torch.empty((t.numel(), 2 * half), dtype=torch.float32, device=x.device)
+            L.check(L.lib().srd_sinusoidal_emb(t.data_ptr(), t.numel(), self.dim, freqs.data_ptr(), out.data_ptr(),
+                                               E._stream()), "srd_sinusoidal_emb")
+            return out
+
+
+def _axpby(x, y, a, b):
+    """a*x + b*y on fp32 CUDA tensors (srd_axpby)."""
+    xc, yc = x.contiguous().float(), y.contiguous().float()
+    out = torch.empty_like(xc)
+    with torch.cuda.device(xc.device):
+        L.check(L.lib().srd_axpby(xc.data_ptr(), yc.data_ptr(), float(a), float(b), xc.numel(), out.data_ptr(),
+                                  E._stream()), "srd_axpby")
+    return out
+
 
 def _run_single(x, build, ctx=None):
     """Stand-alone forward of a sub-module: NCHW fp32 in -> program -> NCHW fp32 out."""
     E._require_cuda(x, "input")
     x = x.contiguous().float()
     B, C_, H, W = x.shape
-    bld = E.Builder(x.device, runtime.precision)
-    out_act, out_c = build(bld, x, B, C_, H, W)
-    out = torch.empty((B, out_c, out_act.H, out_act.W), dtype=torch.float32, device=x.device)
-    bld.act_to_nchw(out_act, 0, out_c, out)
-    bld.run(ctx)
+    with torch.cuda.device(x.device):          # plans, streams and launches belong to the tensor's device
+        bld = E.Builder(x.device, runtime.precision)
+        out_act, out_c = build(bld, x, B, C_, H, W)
+        out = torch.empty((B, out_c, out_act.H, out_act.W), dtype=torch.float32, device=x.device)
+        bld.act_to_nchw(out_act, 0, out_c, out)
+        bld.run(ctx)
     return out
 
 
@@ -168,11 +244,16 @@ class ResnetBlock(nn.Module):
 
 
 class Residual(nn.Module):
-    """:398-404 -- container only; Unet.forward evaluates `fn(x) + x` inside the launch list."""
+    """:398-404.  Inside Unet.forward `fn(x) + x` is a residual epilogue of the launch list; the stand-alone
+    forward runs `fn` (one of this module's CUDA-backed blocks) and adds with srd_axpby."""
 
     def __init__(self, fn):
         super().__init__()
         self.fn = fn
+
+    def forward(self, x, *args, **kwargs):
+        E._require_cuda(x, "Residual input")
+        return _axpby(self.fn(x, *args, **kwargs), x, 1.0, 1.0)
 
 
 class Rezero(nn.Module):
@@ -182,6 +263,11 @@ class Rezero(nn.Module):
         super().__init__()
         self.fn = fn
         self.g = nn.Parameter(torch.zeros(1))
+
+    def forward(self, x):
+        E._require_cuda(x, "Rezero input")
+        y = self.fn(x)
+        return _axpby(y, y, float(self.g.detach().float().item()), 0.0)
 
 
 class LinearAttention(nn.Module):
@@ -264,6 +350,18 @@ class ResidualDenseBlock_5C(nn.Module):
         self.conv4 = nn.Conv2d(nf + 3 * gc, gc, 3, 1, 1, bias=bias)
         self.conv5 = nn.Conv2d(nf + 4 * gc, nf, 3, 1, 1, bias=bias)
         self.lrelu = nn.LeakyReLU(negative_slope=0.2, inplace=True)
+        self._nf, self._gc = nf, gc
+
+    def forward(self, x):
+        """:680-690 stand-alone: the four growth convs write channel slices of ONE (nf + 4 gc)-channel buffer (the
+        `cat`s), conv5's epilogue carries `x5 * 0.2 + x`.  (Inside RRDBNet the same launches come from
+        engine.RRDBProgram.)"""
+        def build(bld, x, B, C_, H, W):
+            out = bld.act(B, H, W, self._nf)
+            cat = E.build_rdb_input(bld, x, self._nf, self._gc)
+            E.build_rdb(bld, self, cat, self._nf, self._gc, out, alpha=0.2, res1=(cat, 0, 1.0))
+            return out, self._nf
+        return _run_single(x, build)
 
 
 class RRDB(nn.Module):
@@ -274,9 +372,27 @@ class RRDB(nn.Module):
         self.RDB1 = ResidualDenseBlock_5C(nf, gc)
         self.RDB2 = ResidualDenseBlock_5C(nf, gc)
         self.RDB3 = ResidualDenseBlock_5C(nf, gc)
+        self._nf, self._gc = nf, gc
+
+    def forward(self, x):
+        """:702-706 stand-alone: three dense blocks, then `out * 0.2 + x` folded into the last conv5's epilogue
+        (alpha 0.04, 0.2 * RDB3-input, 1.0 * x) exactly as engine.RRDBProgram does."""
+        def build(bld, x, B, C_, H, W):
+            nf, gc = self._nf, self._gc
+            cats = [E.build_rdb_input(bld, x, nf, gc), bld.act(B, H, W, nf + 4 * gc)]
+            keep = bld.act(B, H, W, nf)
+            bld.nchw_to_act(lambda: x, keep, nf)
+            out = bld.act(B, H, W, nf)
+            E.build_rdb(bld, self.RDB1, cats[0], nf, gc, cats[1], alpha=0.2, res1=(cats[0], 0, 1.0))
+            E.build_rdb(bld, self.RDB2, cats[1], nf, gc, cats[0], alpha=0.2, res1=(cats[1], 0, 1.0))
+            E.build_rdb(bld, self.RDB3, cats[0], nf, gc, out, alpha=0.04, res1=(cats[0], 0, 0.2), res2=(keep, 0, 1.0))
+            return out, nf
+        return _run_single(x, build)
 
 
-class RRDBNet(nn.Module):
+class RRDBNet(_EngineCached):
+    _cache_fields = ("_progs",)
+
     """:709-749"""
 
     def __init__(self, in_nc, out_nc, nf, nb, gc=32):
@@ -307,17 +423,20 @@ class RRDBNet(nn.Module):
         E._require_cuda(x, "RRDBNet input")
         x = x.contiguous().float()
         B, _, h, w = x.shape
-        prog = self._program(B, h, w, x.device)
-        prog.load_input(x)
-        prog.run()
-        out = prog.out.clone()
-        if get_fea:
-            return out, prog.feas_nchw()
-        return out
+        with torch.cuda.device(x.device):
+            prog = self._program(B, h, w, x.device)
+            prog.load_input(x)
+            prog.run()
+            out = prog.out.clone()
+            if get_fea:
+                return out, prog.feas_nchw()
+            return out
 
 
 # ------------------------------------------------------------------------------------------ Unet
-class Unet(nn.Module):
+class Unet(_EngineCached):
+    _cache_fields = ("_progs",)
+
     """:752-856"""
 
     def __init__(self, dim, out_dim=None, dim_mults=(1, 2, 4, 8), cond_dim=32):
@@ -390,6 +509,10 @@ class Unet(nn.Module):
     def forward(self, x, time, cond, img_lr_up):
         """x [B,3,H,W], time [B] (any per-sample values), cond = list of RRDB feature maps."""
         E._require_cuda(x, "Unet input")
+        with torch.cuda.device(x.device):
+            return self._forward(x, time, cond, img_lr_up)
+
+    def _forward(self, x, time, cond, img_lr_up):
         x = x.contiguous().float()
         B, _, H, W = x.shape
         dev = x.device
@@ -480,7 +603,9 @@ def cosine_beta_schedule(timesteps, s=0.008):
 
 
 # ------------------------------------------------------------------------------------------ sampler
-class GaussianDiffusion(nn.Module):
+class GaussianDiffusion(_EngineCached):
+    _cache_fields = ("_plans",)
+
     """:911-1134 (inference path)."""
 
     def __init__(self, denoise_fn, rrdb_net, timesteps=1000, loss_type='l1'):
@@ -524,12 +649,13 @@ class GaussianDiffusion(nn.Module):
     def _plan(self, B, h, w, device):
         sig = E.plan_signature(self)
         key = (B, h, w, runtime.precision, str(device))
-        p = self._plans.get(key)
+        p = self._plans.pop(key, None)
         if p is None or p.sig != sig:
-            if len(self._plans) >= 2:
-                self._plans.clear()
-            p = E.SamplerPlan(self, B, h, w, runtime.precision, device)
-            self._plans[key] = p
+            while len(self._plans) >= max(1, runtime.plan_cache_size):      # LRU: dicts keep insertion order
+                self._plans.pop(next(iter(self._plans)))
+            with torch.cuda.device(device):
+                p = E.SamplerPlan(self, B, h, w, runtime.precision, device)
+        self._plans[key] = p                                                # most recently used last
         return p
 
     def _elementwise(self, x, img_lr_up, clip_input, inverse):
@@ -540,9 +666,10 @@ class GaussianDiffusion(nn.Module):
             return x
         xc, uc = x.contiguous().float(), img_lr_up.contiguous().float()
         out = torch.empty_like(xc)
-        L.check(L.lib().srd_res2img(xc.data_ptr(), uc.data_ptr(), out.data_ptr(), xc.numel(),
-                                    float(hparams['res_rescale']), 1 if clip_input else 0, inverse, E._stream()),
-                "srd_res2img")
+        with torch.cuda.device(xc.device):
+            L.check(L.lib().srd_res2img(xc.data_ptr(), uc.data_ptr(), out.data_ptr(), xc.numel(),
+                                        float(hparams['res_rescale']), 1 if clip_input else 0, inverse, E._stream()),
+                    "srd_res2img")
         return out
 
     def res2img(self, img_, img_lr_up, clip_input=None):
@@ -553,22 +680,108 @@ class GaussianDiffusion(nn.Module):
         """:1127-1134"""
         return self._elementwise(x, img_lr_up, clip_input, 1)
 
+    def _check_t(self, t, what, allow_negative=False):
+        """The reference's `extract` gathers raise on an out-of-range timestep; the kernels index the coefficient
+        tables directly, so the public entry points validate on the host (one tiny device->host read)."""
+        tt = t.reshape(-1)
+        if tt.numel() == 0:
+            return
+        lo, hi = int(tt.min()), int(tt.max())
+        if hi >= self.num_timesteps or (lo < 0 and not allow_negative):
+            raise IndexError("%s: timestep out of range [0, %d): min %d, max %d" % (what, self.num_timesteps, lo, hi))
+
+    def _scale_pair(self, x, y, tab_a, tab_b, t, what):
+        """tab_a[t] * x + tab_b[t] * y per sample (fp32 mul, mul, add -- the reference's op order) via srd_q_sample."""
+        E._require_cuda(x, what)
+        self._check_t(t, what)
+        xc, yc = x.contiguous().float(), y.contiguous().float()
+        t32 = t.to(device=xc.device, dtype=torch.int32).contiguous()
+        out = torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            L.check(L.lib().srd_q_sample(xc.data_ptr(), yc.data_ptr(), tab_a.data_ptr(), tab_b.data_ptr(),
+                                         t32.data_ptr(), xc.shape[0], xc[0].numel(), out.data_ptr(), E._stream()),
+                    "srd_q_sample")
+        return out
+
+    def _neg(self, name):
+        """-buffer, cached (a*x - b*n == a*x + (-b)*n bit for bit: negation is exact)."""
+        buf = getattr(self, name)
+        key = (buf.data_ptr(), buf._version)
+        hit = self.__dict__.setdefault("_srd_neg", {}).get(name)
+        if hit is None or hit[0] != key:
+            hit = (key, (-buf.detach()).contiguous())
+            self.__dict__["_srd_neg"][name] = hit
+        return hit[1]
+
+    def q_mean_variance(self, x_start, t):
+        """:962-966"""
+        zeros = torch.zeros_like(self.sqrt_alphas_cumprod)
+        mean = self._scale_pair(x_start, x_start, self.sqrt_alphas_cumprod, zeros, t, "q_mean_variance input")
+        variance = extract(1. - self.alphas_cumprod, t, x_start.shape)
+        log_variance = extract(self.log_one_minus_alphas_cumprod, t, x_start.shape)
+        return mean, variance, log_variance
+
+    def predict_start_from_noise(self, x_t, t, noise):
+        """:968-972"""
+        return self._scale_pair(x_t, noise, self.sqrt_recip_alphas_cumprod, self._neg("sqrt_recipm1_alphas_cumprod"),
+                                t, "predict_start_from_noise input")
+
+    def q_posterior(self, x_start, x_t, t):
+        """:974-981"""
+        posterior_mean = self._scale_pair(x_start, x_t, self.posterior_mean_coef1, self.posterior_mean_coef2, t,
+                                          "q_posterior input")
+        posterior_variance = extract(self.posterior_variance, t, x_t.shape)
+        posterior_log_variance_clipped = extract(self.posterior_log_variance_clipped, t, x_t.shape)
+        return posterior_mean, posterior_variance, posterior_log_variance_clipped
+
+    def p_mean_variance(self, x, t, noise_pred, clip_denoised: bool):
+        """:983-990 -- the posterior mean and the (clamped) x_0 prediction come out of the fused p_sample kernel run
+        with an all-zero noise tensor (mean + sigma * 0 == mean)."""
+        E._require_cuda(x, "p_mean_variance input")
+        self._check_t(t, "p_mean_variance")
+        xc = x.contiguous().float()
+        t32 = t.to(device=xc.device, dtype=torch.int32).contiguous()
+        mean, x0 = torch.empty_like(xc), torch.empty_like(xc)
+        with torch.cuda.device(xc.device):
+            E.p_sample_step(xc, noise_pred.contiguous().float(), torch.zeros_like(xc), E.coef_table(self), t32, mean,
+                            clip_denoised, x0_out=x0)
+        return (mean, extract(self.posterior_variance, t, xc.shape),
+                extract(self.posterior_log_variance_clipped, t, xc.shape), x0)
+
+    def forward(self, img_hr, img_lr, img_lr_up, t=None, *args, **kwargs):
+        """:992-1019 is the TRAINING objective (q_sample -> denoiser -> p_losses with autograd); this package is the
+        inference hot path only (training is out of scope), so calling the module raises instead of
+        falling into nn.Module's default."""
+        raise NotImplementedError(
+            "dgm_img_super_resolution_b200.GaussianDiffusion is inference-only: use sample() / p_sample() / "
+            "interpolate(); the training forward / p_losses of srdiff/model.py:992-1039 are out of scope")
+
+    def p_losses(self, x_start, t, cond, img_lr_up, noise=None):
+        """:1021-1039 -- training loss, out of scope (see forward)."""
+        raise NotImplementedError("p_losses (training objective) is out of scope of the inference-only build")
+
     def q_sample(self, x_start, t, noise=None):
         """:1041-1048 forward diffusion of x_start to step t (per-sample t; t < 0 returns x_start)."""
         E._require_cuda(x_start, "q_sample input")
+        self._check_t(t, "q_sample", allow_negative=True)
         x = x_start.contiguous().float()
         noise = default(noise, lambda: torch.randn_like(x)).contiguous().float()
         t32 = t.to(device=x.device, dtype=torch.int32).contiguous()
         out = torch.empty_like(x)
-        L.check(L.lib().srd_q_sample(x.data_ptr(), noise.data_ptr(), self.sqrt_alphas_cumprod.data_ptr(),
-                                     self.sqrt_one_minus_alphas_cumprod.data_ptr(), t32.data_ptr(), x.shape[0],
-                                     x[0].numel(), out.data_ptr(), E._stream()), "srd_q_sample")
+        with torch.cuda.device(x.device):
+            L.check(L.lib().srd_q_sample(x.data_ptr(), noise.data_ptr(), self.sqrt_alphas_cumprod.data_ptr(),
+                                         self.sqrt_one_minus_alphas_cumprod.data_ptr(), t32.data_ptr(), x.shape[0],
+                                         x[0].numel(), out.data_ptr(), E._stream()), "srd_q_sample")
         return out
 
     @torch.no_grad()
     def interpolate(self, x1, x2, img_lr, img_lr_up, t=None, lam=0.5):
         """:1093-1116: diffuse x1 and x2 to step t, blend, and denoise from step t-1 down to 0."""
         E._require_cuda(x1, "interpolate input")
+        with torch.cuda.device(x1.device):
+            return self._interpolate(x1, x2, img_lr, img_lr_up, t, lam)
+
+    def _interpolate(self, x1, x2, img_lr, img_lr_up, t, lam):
         if not hparams['use_rrdb']:
             raise NotImplementedError("hparams['use_rrdb']=False is outside the hot path")
         assert x1.shape == x2.shape
@@ -584,9 +797,7 @@ class GaussianDiffusion(nn.Module):
                                   plan.x.data_ptr(), E._stream()), "srd_axpby")
         plan.img_lr.copy_(img_lr)
         plan.img_lr_up.copy_(img_lr_up)
-        runtime.seed_counter += 1
-        seed = (torch.cuda.default_generators[device.index or 0].initial_seed() * 1000003 + runtime.seed_counter) \
-            & 0x7FFFFFFFFFFFFFFF
+        seed = next_seed(device)
         plan.seed_dev.fill_(seed)
         plan.encode()
         plan.load_x()
@@ -600,6 +811,7 @@ class GaussianDiffusion(nn.Module):
     def p_sample(self, x, t, cond, img_lr_up, noise_pred=None, clip_denoised=True, repeat_noise=False):
         """:1050-1060 stand-alone (arbitrary per-sample t).  Returns (x_prev, x0_pred)."""
         E._require_cuda(x, "p_sample input")
+        self._check_t(t, "p_sample")
         x = x.contiguous().float()
         if noise_pred is None:
             noise_pred = self.denoise_fn(x, t, cond=cond, img_lr_up=img_lr_up)
@@ -607,15 +819,20 @@ class GaussianDiffusion(nn.Module):
         coef = E.coef_table(self)
         t32 = t.to(device=x.device, dtype=torch.int32).contiguous()
         x_out, x0 = torch.empty_like(x), torch.empty_like(x)
-        E.p_sample_step(x, noise_pred.contiguous().float(), noise, coef, t32, x_out, clip_denoised, x0_out=x0)
+        with torch.cuda.device(x.device):
+            E.p_sample_step(x, noise_pred.contiguous().float(), noise, coef, t32, x_out, clip_denoised, x0_out=x0)
         return x_out, x0
 
     @torch.no_grad()
     def sample(self, img_lr, img_lr_up, shape, save_intermediate=False):
         """:1062-1091.  Returns (img, rrdb_out[, images])."""
-        device = self.betas.device
         E._require_cuda(self.betas, "GaussianDiffusion")
         E._require_cuda(img_lr, "img_lr")
+        with torch.cuda.device(self.betas.device):      # the module's device, not whatever happens to be current
+            return self._sample(img_lr, img_lr_up, shape, save_intermediate)
+
+    def _sample(self, img_lr, img_lr_up, shape, save_intermediate):
+        device = self.betas.device
         if not hparams['use_rrdb']:
             raise NotImplementedError("hparams['use_rrdb']=False is outside the hot path")
         b = shape[0]
@@ -628,9 +845,7 @@ class GaussianDiffusion(nn.Module):
             raise RuntimeError("img_lr_up must be sr_scale x img_lr")
         T = self.num_timesteps
         use_torch_noise = runtime.noise == "torch" and plan.noise_bytes() <= runtime.noise_budget_bytes
-        runtime.seed_counter += 1
-        seed = (torch.cuda.default_generators[device.index or 0].initial_seed() * 1000003 + runtime.seed_counter) \
-            & 0x7FFFFFFFFFFFFFFF
+        seed = next_seed(device)
         # ---- x_T :1066-1070 (drawn before the RRDB forward, like the reference)
         res = bool(hparams['res'])
         if not res:         # start from the diffused bicubic image :1066-1068; res2img is the identity then
@@ -676,10 +891,11 @@ class GaussianDiffusion(nn.Module):
 
 
 # ------------------------------------------------------------------------------------------ checkpoints
-# the upstream LeiaLi/SRDiff checkpoint format (:1405-1496): `{work_dir}/model_ckpt_steps_{N}.ckpt`
-# holding {'global_step', 'optimizer_states', 'state_dict': {'model': <GaussianDiffusion state dict>}} (or a flat
-# state dict with 'model.' prefixes).  Host-side file handling only; the state dict lands in the same nn.Module
-# parameters the engine packs from.
+# reading the upstream LeiaLi/SRDiff checkpoint format (:1405-1422, 1463-1496):
+# `{work_dir}/model_ckpt_steps_{N}.ckpt` holding {'global_step', 'optimizer_states', 'state_dict': {'model': <state
+# dict>}} (or a flat state dict with 'model.' prefixes).  Host-side file handling only; the state dict lands in the
+# same nn.Module parameters the engine packs from.  The trainer's save / resume halves (:1425-1454: optimizer state,
+# step counter) belong to the training loop, which is out of scope, and are not provided.
 def get_all_ckpts(work_dir, steps=None):
     """:1416-1422 -- checkpoint paths, newest (largest step) first."""
     import glob
@@ -727,32 +943,3 @@ def load_ckpt(cur_model, ckpt_base_dir, model_name='model', force=True, strict=T
             del state_dict[k]
     cur_model.load_state_dict(state_dict, strict=strict)
     print(f"| load '{model_name}' from '{ckpt_path}'.")
-
-
-def load_checkpoint(model, optimizer, work_dir):
-    """:1425-1438 -- resume: weights + optimizer state + step counter (0 when the directory has no checkpoint)."""
-    checkpoint, _ = get_last_checkpoint(work_dir)
-    training_step = 0
-    if checkpoint is not None:
-        model.load_state_dict(checkpoint['state_dict']['model'])
-        model.cuda()
-        optimizer.load_state_dict(checkpoint['optimizer_states'][0])
-        training_step = checkpoint['global_step']
-        del checkpoint
-        torch.cuda.empty_cache()
-    else:
-        model.cuda()
-    return training_step
-
-
-def save_checkpoint(model, optimizer, work_dir, global_step, num_ckpt_keep):
-    """:1441-1454 -- same file layout (legacy, non-zipfile serialisation), pruning all but the newest N."""
-    import os
-    ckpt_path = f'{work_dir}/model_ckpt_steps_{global_step}.ckpt'
-    print(f'Step@{global_step}: saving model to {ckpt_path}')
-    checkpoint = {'global_step': global_step, 'optimizer_states': [optimizer.state_dict()],
-                  'state_dict': {'model': model.state_dict()}}
-    torch.save(checkpoint, ckpt_path, _use_new_zipfile_serialization=False)
-    for old_ckpt in get_all_ckpts(work_dir)[num_ckpt_keep:]:
-        os.remove(old_ckpt)
-        print(f'Delete ckpt: {os.path.basename(old_ckpt)}')

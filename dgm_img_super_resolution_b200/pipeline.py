@@ -15,6 +15,20 @@ def _f32(x, what):
     return x.contiguous().float()
 
 
+def _on_device(fn):
+    """Run `fn` with its first tensor argument's device current (streams and launches follow the tensor)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapped(x, *a, **k):
+        if isinstance(x, torch.Tensor) and x.is_cuda:
+            with torch.cuda.device(x.device):
+                return fn(x, *a, **k)
+        return fn(x, *a, **k)
+    return wrapped
+
+
+@_on_device
 def bicubic_upsample(x, scale_factor):
     """F.interpolate(x, scale_factor, mode='bicubic', align_corners=True) (`upsample_tensor`, st_app1.py:1593)."""
     x = _f32(x, "bicubic_upsample input")
@@ -26,6 +40,7 @@ def bicubic_upsample(x, scale_factor):
     return out
 
 
+@_on_device
 def normalize_u8(img_u8, mean=None, std=None):
     """uint8 [B, H, W, C] -> float [B, C, H, W]: ToTensor + Normalize(mean, std); without mean/std u/127.5 - 1."""
     E._require_cuda(img_u8, "normalize_u8 input")
@@ -44,6 +59,7 @@ def normalize_u8(img_u8, mean=None, std=None):
     return out
 
 
+@_on_device
 def to_uint8(img):
     """float [B, C, H, W] in [-1, 1] -> uint8 [B, H, W, C]: clamp, (x+1)/2, clip(x*255, 0, 255), truncate."""
     img = _f32(img, "to_uint8 input")
@@ -53,6 +69,7 @@ def to_uint8(img):
     return out
 
 
+@_on_device
 def split_tiles(img, th, tw):
     """[n, C, nx*th, ny*tw] -> ([n*nx*ny, C, th, tw], (nx, ny)); tile (x, y) of image i is entry i*nx*ny + x*ny + y."""
     img = _f32(img, "split_tiles input")
@@ -65,6 +82,7 @@ def split_tiles(img, th, tw):
     return out, (nx, ny)
 
 
+@_on_device
 def merge_tiles(tiles, nx, ny):
     """Inverse of split_tiles; the grid concatenation of ImgMerger.compute (:133-145)."""
     tiles = _f32(tiles, "merge_tiles input")
@@ -98,9 +116,13 @@ class ImgMerger:
     def compute(self):
         img_inputs = []
         for i in range(len(self.loc2imgs['0,0'])):
+            first = np.asarray(self.loc2imgs['0,0'][i])
             tiles = torch.stack([torch.as_tensor(np.asarray(self.loc2imgs['%d,%d' % (x, y)][i]), dtype=torch.float32)
                                  for x in range(self.max_x) for y in range(self.max_y)]).to(self.device)
-            img_inputs.append(merge_tiles(tiles, self.max_x, self.max_y)[0].cpu().numpy())
+            merged = merge_tiles(tiles, self.max_x, self.max_y)[0].cpu().numpy()
+            # np.concatenate keeps the tiles' dtype (uint8 [0, 255] arrays in the reference's use); the fp32 round
+            # trip through the merge kernel is exact for every integer / float value a uint8 or fp32 tile holds
+            img_inputs.append(merged.astype(first.dtype) if first.dtype != np.float64 else merged.astype(np.float64))
         self.clear()
         return self.eval_fn(*img_inputs)
 

@@ -156,6 +156,10 @@ int srd_time_table(const float* t_values, int32_t n_t, int32_t dim, const float*
                    const float* w_blk, const float* b_blk, int32_t S,
                    float* out, void* stream);
 
+/* SinusoidalPosEmb.forward :412-419 stand-alone: out[n][dim] = cat(sin(t[i] * freqs), cos(t[i] * freqs)),
+ * freqs[dim/2] host-provided as for srd_time_table. */
+int srd_sinusoidal_emb(const float* t, int32_t n, int32_t dim, const float* freqs, float* out, void* stream);
+
 /* p_sample update :1054-1060 (+ predict_start_from_noise :968-972, clamp :986-987, q_posterior
  * :974-981) as ONE vectorised elementwise kernel over [B][chw] fp32 tensors.
  *   coef: [T][5] fp32 rows {sqrt_recip_ac, sqrt_recipm1_ac, post_mean_coef1, post_mean_coef2,

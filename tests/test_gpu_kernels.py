@@ -308,3 +308,40 @@ def test_tc_mode_switches_do_not_change_results(ours, a_mode, what):
     else:
         assert O.rel_l2(outs[1].cpu(), outs[0].cpu()) < 3e-3, what
     assert L.lib().srd_tc_set_mode(128, 1) != 0 and L.lib().srd_watchdog_flag() == 0
+
+
+def test_sample_sharded_is_shard_invariant_with_real_diffusion(hp):
+    """dist.sample_sharded with a REAL GaussianDiffusion: (a) through an in-process world-size-1 group it equals a
+    plain Philox `sample()` with the job seed; (b) the two halves of the batch, sampled separately the way two ranks
+    would (slice start as image offset, same job seed), concatenate to exactly the single-GPU result."""
+    import os
+    import torch.distributed as dist
+    from dgm_img_super_resolution_b200 import dist as D
+    M, diff = build_ours(hp, timesteps=3, device=DEV)
+    img_lr, img_lr_up, _ = gen_inputs(5, 8, 8, hp["sr_scale"], 33)
+    lr, up = img_lr.to(DEV), img_lr_up.to(DEV)
+    created = False
+    if not dist.is_initialized():
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        os.environ.setdefault("MASTER_PORT", "29571")
+        dist.init_process_group("gloo", rank=0, world_size=1)
+        created = True
+    try:
+        M.runtime.noise = "torch"                      # sample_sharded must override this
+        M.runtime.seed_override = 424242
+        whole, whole_rrdb = D.sample_sharded(diff, lr, up)
+        assert M.runtime.noise == "torch" and M.runtime.seed_override == 424242      # restored
+        M.runtime.noise = "philox"
+        ref, _ = diff.sample(lr, up, tuple(up.shape))
+        assert torch.equal(whole, ref)
+        parts = []
+        for rank in range(2):
+            start, count = D.shard_range(5, 2, rank)
+            M.runtime.image_offset = start
+            img, _ = diff.sample(lr[start:start + count], up[start:start + count], (count, 3, 32, 32))
+            parts.append(img)
+        assert torch.equal(torch.cat(parts, 0), whole)
+    finally:
+        M.runtime.noise, M.runtime.seed_override, M.runtime.image_offset = "torch", None, 0
+        if created:
+            dist.destroy_process_group()
