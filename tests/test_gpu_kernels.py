@@ -6,7 +6,7 @@ import pytest
 import torch
 import torch.nn.functional as F
 
-from conftest import build_ours, golden
+from conftest import build_ours, gen_inputs, golden
 from oracle import srdiff_oracle as O
 
 pytestmark = pytest.mark.gpu
@@ -188,7 +188,7 @@ def test_rrdb_net_matches_reference_fixture(ours, precision, prec, name):
     g = golden(name)
     out, feas = diff.rrdb(g["img_lr"].to(DEV), True)
     assert len(feas) == 9
-    tol = 2e-5 if prec == "fp32" else 2e-2        # 126 chained convs: bf16 storage error accumulates
+    tol = 2e-5 if prec == "fp32" else 1e-2        # 126 chained convs: bf16 storage error accumulates (measured 5e-3)
     assert O.rel_l2(torch.stack(feas).cpu(), g["feas"]) < tol
     assert O.rel_l2(out.cpu(), g["rrdb_out"]) < tol
     only = diff.rrdb(g["img_lr"].to(DEV))
@@ -232,7 +232,7 @@ def test_sampler_T4_matches_reference_fixture(hp, prec, graph):
         with inject_noise(M, g["noises"]):
             img, rrdb_out = diff.sample(g["img_lr"].to(DEV), g["img_lr_up"].to(DEV), tuple(g["img_lr_up"].shape))
         assert O.psnr(img.cpu(), g["img"]) >= (80.0 if prec == "fp32" else 40.0)
-        assert O.rel_l2(rrdb_out.cpu(), g["rrdb_out"]) < (2e-5 if prec == "fp32" else 2e-2)
+        assert O.rel_l2(rrdb_out.cpu(), g["rrdb_out"]) < (2e-5 if prec == "fp32" else 1e-2)
         if not graph:
             with inject_noise(M, g["noises"]):
                 img2, _, inter = diff.sample(g["img_lr"].to(DEV), g["img_lr_up"].to(DEV),
