@@ -62,6 +62,11 @@ class SrdPSampleArgs(C.Structure):
     ]
 
 
+class SrdChainLink(C.Structure):
+    _fields_ = [("src_layer", C.c_int32 * SRD_MAX_SRC), ("src_which", C.c_int32 * SRD_MAX_SRC),
+                ("res1_layer", C.c_int32), ("res1_which", C.c_int32), ("temb_off", C.c_int32)]
+
+
 class SrdGroupNormArgs(C.Structure):
     _fields_ = [
         ("src", C.c_void_p), ("src_ct", C.c_int32), ("src_coff", C.c_int32),
@@ -89,6 +94,10 @@ SYMBOLS = {
     "srd_conv_plan_kernel": (C.c_int, [_vp]),
     "srd_conv_run": (C.c_int, [_vp, _vp, _vp]),
     "srd_watchdog_flag": (C.c_int, []),
+    "srd_chain_create": (C.c_int, [C.POINTER(_vp), C.POINTER(SrdChainLink), _i32, _i32, C.POINTER(_vp)]),
+    "srd_chain_run": (C.c_int, [_vp, _vp, _vp]),
+    "srd_chain_destroy": (C.c_int, [_vp]),
+    "srd_chain_segments": (C.c_int, [_vp]),
     "srd_tc_set_mode": (C.c_int, [_i32, _i32]),
     "srd_tc_set_debug": (C.c_int, [_vp]),
     "srd_time_table": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),

@@ -3,6 +3,7 @@
 #include <stddef.h>
 #include <cuda.h>
 #include <new>
+#include <vector>
 #include "epilogue.cuh"
 
 namespace srd {
@@ -25,6 +26,17 @@ void tc_plan_delete(TcPlan*);
 int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag);
 int launch_conv_tc(const TcPlan& plan, const float* temb, cudaStream_t stream);
 void tc_set_mode(int a_mode, int b_resident);
+struct TcChain;
+struct TcChainLink {
+  int src_layer[SRD_MAX_SRC], src_which[SRD_MAX_SRC];
+  int res1_layer, res1_which;
+  int temb_off;
+};
+TcChain* tc_chain_new();
+void tc_chain_delete(TcChain*);
+int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, TcChain* chain, int single_segments);
+int tc_chain_segments(const TcChain* c);
+int launch_chain(const TcChain& c, const float* temb_row, cudaStream_t stream);
 void tc_set_debug(unsigned long long* p);
 
 static int* g_err_flag_dev = nullptr;   // device-visible pointer to a host-mapped int
@@ -167,6 +179,39 @@ int srd_tc_set_mode(int32_t a_mode, int32_t b_resident) {
 int srd_tc_set_debug(void* buf) {
   tc_set_debug((unsigned long long*)buf);
   return 0;
+}
+
+int srd_chain_create(SrdConvPlan* const* plans, const SrdChainLink* links, int32_t n, int32_t flags, SrdChain** out) {
+  SRD_CHECK(plans && links && out && n > 0, "srd_chain_create: bad arguments");
+  static_assert(sizeof(SrdChainLink) == sizeof(srd::TcChainLink), "SrdChainLink layout");
+  std::vector<const srd::TcPlan*> tcs((size_t)n);
+  for (int i = 0; i < n; ++i) {
+    SRD_CHECK(plans[i] && plans[i]->kernel == SRD_KERNEL_TC && plans[i]->tc,
+              "srd_chain_create: layer %d is not a tcgen05 plan (only those can be chained)", i);
+    tcs[(size_t)i] = plans[i]->tc;
+  }
+  srd::TcChain* c = tc_chain_new();
+  SRD_CHECK(c != nullptr, "srd_chain_create: out of memory");
+  if (tc_chain_build(tcs.data(), reinterpret_cast<const srd::TcChainLink*>(links), n, c, flags & 1)) {
+    tc_chain_delete(c);
+    return 1;
+  }
+  *out = reinterpret_cast<SrdChain*>(c);
+  return 0;
+}
+
+int srd_chain_run(const SrdChain* chain, const float* temb_row, void* stream) {
+  SRD_CHECK(chain != nullptr, "srd_chain_run: NULL chain");
+  return launch_chain(*reinterpret_cast<const srd::TcChain*>(chain), temb_row, (cudaStream_t)stream);
+}
+
+int srd_chain_destroy(SrdChain* chain) {
+  if (chain) tc_chain_delete(reinterpret_cast<srd::TcChain*>(chain));
+  return 0;
+}
+
+int srd_chain_segments(const SrdChain* chain) {
+  return chain ? tc_chain_segments(reinterpret_cast<const srd::TcChain*>(chain)) : -1;
 }
 
 /* Non-zero after a tcgen05 pipeline watchdog fired (code = which wait timed out). */

@@ -25,6 +25,7 @@
 #include <cuda.h>
 #include <string.h>
 #include <new>
+#include <vector>
 #include "epilogue.cuh"
 
 namespace srd {
@@ -134,12 +135,60 @@ struct TcArgs {
   int reverse_items;       // static deal only: item order reversed (see SrdConvDesc.reverse_items)
 };
 
+// ------------------------------------------------------------------------------------------ layer chain
+// conv_chain_kernel runs a LIST of conv layers in one launch.  Every CTA pair walks the list on its own; what orders
+// a consumer layer after its producer is not a kernel boundary but a per-row-block completion counter in global
+// memory: every epilogue warp bumps `cnt[row block of its tile]` once the TMA stores of a sub-tile have completed,
+// and whoever is about to read rows of that tensor (the activation-TMA producer for the K sources, the epilogue warps
+// for the residual prefetch) first waits until the row blocks covering those rows -- plus the rows their mirrored
+// ring copies come from -- have reached the tensor's full count.  Row block r of a tensor = the producer's M tiles
+// [r * n_colblk, (r + 1) * n_colblk) of every sub-pixel phase.
+struct ChainDep {
+  const unsigned* cnt;     // [n_rowblk] completion counters of the producing layer's output; nullptr = written before the launch
+  unsigned expect;         // value of a complete row block
+  int n_rowblk, n_rows;    // row blocks / padded stacked rows (B * (H + 2)) of the tensor
+  int hp, H;               // padded / unpadded rows per image
+  int up_shift;            // producer's M row = output row >> up_shift (1 for the 2x transposed conv)
+  int period, voff, vstart;   // producer's stacked-row geometry (TcArgs)
+  FastDiv fd_hp;
+};
+struct ChainLayer {
+  TcArgs a;
+  ChainDep dep_src[SRD_MAX_SRC];
+  ChainDep dep_res1;
+  unsigned* out_cnt;       // counters this layer's epilogue bumps for `out` (nullptr: nobody in the chain reads it)
+  unsigned* out2_cnt;      // ... for the second output (SrdConvDesc.N2)
+  int temb_off;            // >= 0: time-embedding vector = temb_row + temb_off (per-launch row of the time table)
+  int seg_first;           // 1: first layer of a segment (see conv_chain_kernel)
+  int pad_[12];
+};
+// Role state handed from layer to layer inside a segment.
+struct Ring {
+  int stage, phase, n;
+  __device__ __forceinline__ void next() { if (++stage == n) { stage = 0; phase ^= 1; } }
+  __device__ __forceinline__ void skip(int k) {          // k slots consumed by another thread
+    stage += k;
+    while (stage >= n) { stage -= n; phase ^= 1; }
+  }
+};
+struct ChainRt {
+  const ChainLayer* L;     // current layer
+  int j, n_seg;            // its index inside the segment / layers in the segment
+  uint32_t it_base;        // items this pair has processed in the segment's earlier layers (TMEM stage / parity continuity)
+  Ring ra, rb, rt;
+  uint32_t k;              // epilogue staging-buffer counter
+  const float* temb_row;
+};
+
 // ------------------------------------------------------------------------------------------ PTX
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
   return (uint32_t)__cvta_generic_to_shared(p);
 }
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_inval(uint32_t bar) {
+  asm volatile("mbarrier.inval.shared::cta.b64 [%0];" ::"r"(bar) : "memory");
 }
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
   asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -164,7 +213,10 @@ __device__ __forceinline__ unsigned long long global_ns() {
   asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
   return t;
 }
-constexpr unsigned long long WATCHDOG_NS = 20ull * 1000 * 1000 * 1000;
+#ifndef SRD_WATCHDOG_MS
+#define SRD_WATCHDOG_MS 20000
+#endif
+constexpr unsigned long long WATCHDOG_NS = (unsigned long long)SRD_WATCHDOG_MS * 1000 * 1000;
 __device__ __noinline__ void mbar_wait_slow(uint32_t bar, uint32_t parity, int* err_flag, int code) {
   const unsigned long long t0 = global_ns();
   while (!mbar_try(bar, parity)) {
@@ -184,6 +236,55 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity, int* er
     }
   }
 }
+// ---- layer-chain dependencies (see ChainDep) --------------------------------------------------------------------
+// Producer row block that writes padded stacked row R of a tensor (ring rows map to the adjacent interior row).
+__device__ __forceinline__ int dep_rowblk(const ChainDep& d, int R) {
+  R = R < 0 ? 0 : (R >= d.n_rows ? d.n_rows - 1 : R);
+  const int b = (int)(((uint64_t)(uint32_t)R * d.fd_hp.mul) >> d.fd_hp.shr);
+  int oy = R - b * d.hp - 1;
+  oy = oy < 0 ? 0 : (oy >= d.H ? d.H - 1 : oy);
+  const int r = (b * d.period + (oy >> d.up_shift) + d.voff - d.vstart) >> 4;
+  return r >= d.n_rowblk ? d.n_rowblk - 1 : r;
+}
+__device__ __noinline__ void dep_poll(const unsigned* p, unsigned expect, int* err_flag) {
+  unsigned v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  if (v >= expect) return;
+  const unsigned long long t0 = global_ns();
+  for (;;) {
+    __nanosleep(40);
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    if (v >= expect) return;
+    if (global_ns() - t0 > WATCHDOG_NS) {
+      if (err_flag) atomicExch(err_flag, 11);
+      __trap();
+    }
+  }
+}
+// Wait until padded stacked rows [Ra, Rb) of the tensor -- and the rows two above / below, where mirrored ring rows
+// come from -- are complete.  [vlo, vhi] caches the row blocks this thread has already seen complete.
+__device__ __forceinline__ bool dep_cached(const ChainDep& d, int Ra, int Rb, int vlo, int vhi) {
+  return dep_rowblk(d, Ra - 2) >= vlo && dep_rowblk(d, Rb + 1) <= vhi;
+}
+__device__ __forceinline__ void dep_wait(const ChainDep& d, int Ra, int Rb, int& vlo, int& vhi, int* err_flag) {
+  const int lo = dep_rowblk(d, Ra - 2), hi = dep_rowblk(d, Rb + 1);
+  if (lo >= vlo && hi <= vhi) return;
+  for (int r = lo; r <= hi; ++r)
+    if (r < vlo || r > vhi) dep_poll(d.cnt + r, d.expect, err_flag);
+  if (vhi >= vlo && lo <= vhi + 1 && hi >= vlo - 1) { vlo = lo < vlo ? lo : vlo; vhi = hi > vhi ? hi : vhi; }
+  else { vlo = lo; vhi = hi; }
+  // acquire: the counters were read relaxed; order them before the (async-proxy) loads that follow
+  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+// One epilogue warp has finished a sub-tile: its bulk stores are COMPLETE (not merely read), the per-thread ring
+// stores of the other lanes are ordered before this by the preceding __syncwarp.  Lane 0 only.
+__device__ __forceinline__ void dep_publish(unsigned* cnt) {
+  asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  asm volatile("fence.proxy.async;" ::: "memory");
+  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(1u) : "memory");
+}
+
 // In a CTA pair (CG == 2) the shared::cluster address of a CTA-local object carries the CTA rank in
 // bit 24; clearing it names the same offset in the LEADER (even) CTA.  The pair's operand loads
 // (.cta_group::2) complete on the leader's mbarrier, where the single MMA-issuing thread waits.
@@ -350,15 +451,6 @@ __device__ __forceinline__ void kern_stamp(const TcArgs& a, int ev, bool global_
   (void)a; (void)ev; (void)global_ns;
 #endif
 }
-
-struct Ring {
-  int stage, phase, n;
-  __device__ __forceinline__ void next() { if (++stage == n) { stage = 0; phase ^= 1; } }
-  __device__ __forceinline__ void skip(int k) {          // k slots consumed by another thread
-    stage += k;
-    while (stage >= n) { stage -= n; phase ^= 1; }
-  }
-};
 
 // Where this CTA sits: work items are dealt to CTA pairs (CG == 2) or single CTAs (CG == 1); item i of
 // a phase covers tiles [i*MT*CG, (i+1)*MT*CG), of which CTA `rank` owns tiles i*MT*CG + mt*CG + rank.
@@ -640,9 +732,13 @@ __device__ __forceinline__ TileGeo tile_geo(const TcArgs& a, int tt, int g, int 
 // The two epilogue warpgroups (halves) ping-pong on the two TMEM accumulator stages: half h owns
 // the items with local index = h (mod 2), i.e. TMEM stage h.
 // ---------------------------------------------------------------------------------------------
-template <int ACT, int CG>
+template <int ACT, int CG, bool CHAIN = false>
 __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es, const Sched& sc, uint32_t tmem_base,
-                                              uint32_t t_full0, uint32_t t_empty0, int warp, int lane) {
+                                              uint32_t t_full0, uint32_t t_empty0, int warp, int lane,
+                                              ChainRt* cx = nullptr) {
+  const uint32_t it_base = CHAIN ? cx->it_base : 0u;
+  unsigned* const out_cnt = CHAIN ? cx->L->out_cnt : nullptr;
+  int r_vlo = 0, r_vhi = -1;
   const int S = a.up;
   const PairId pid = pair_id<CG>();
   const int quarter = warp & 3;                 // TMEM lanes [32*quarter, +32) belong to this warp
@@ -659,8 +755,8 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
   for (int it = set;; it += n_conc) {
     const int item = sc.get(it);
     if (item < 0) break;
-    const int stage = it & (a.n_stages - 1);
-    const uint32_t round = (uint32_t)(it >> a.stage_shift);   // parity of this TMEM stage
+    const int stage = (int)((it_base + (uint32_t)it) & (uint32_t)(a.n_stages - 1));
+    const uint32_t round = (it_base + (uint32_t)it) >> a.stage_shift;   // parity of this TMEM stage
     const uint32_t t_full = t_full0 + 8u * stage, t_empty = t_empty0 + 8u * stage;
     const int phase = fdiv(item, a.fd_ipp);
     const int t0 = (item - phase * a.items_per_phase) * (a.MT * CG) + pid.rank;
@@ -670,11 +766,16 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
     bool released = false;
     for (int mt = 0; mt < a.MT; ++mt) {
       const TileGeo tg = tile_geo(a, t0 + mt * CG, g, px);
+
       const bool valid = tg.valid;
       const int b = tg.b, oy = tg.y * S + pr, ox = tg.x * S + ps;
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((stage * a.MT + mt) * a.Npad);
       float head[4] = {0.f, 0.f, 0.f, 0.f};
       const bool last_tile = (mt == a.MT - 1);
+      if (CHAIN && a.ep.res1 && cx->L->dep_res1.cnt) {       // residual written inside the chain (epi_geo == 0 only)
+        if (lane == 0) dep_wait(cx->L->dep_res1, tg.V0 + quarter * 4, tg.V0 + quarter * 4 + 4, r_vlo, r_vhi, a.err_flag);
+        __syncwarp();
+      }
       if (a.fast) {
         TilePix tp;
         tp.valid = valid; tp.b = b; tp.oy = oy; tp.ox = ox;
@@ -742,6 +843,11 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
               a.ep.planar[((size_t)(b * a.ep.planar_c + jh) * Ho + oy) * Wo + ox] = head[jh] + es.head_b[jh];
         }
       }
+      if (CHAIN && out_cnt && t0 + mt * CG < a.tiles_per_phase) {   // this warp's part of the tile is in global memory
+        __syncwarp();
+        if (lane == 0)
+          asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(out_cnt + ((tg.V0 - a.vstart) >> 4)), "r"(1u) : "memory");
+      }
     }
     if (!released) {
       tc_fence_before();
@@ -790,10 +896,21 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 
 // Each epilogue WARP owns 32 TMEM lanes = 4 tile rows x 8 px and stages them in its own 4 KB
 // swizzled buffer(s): no cross-warp synchronisation, one lane issues the warp's TMA traffic.
-template <int ACT, int CG>
+template <int ACT, int CG, bool CHAIN = false>
 __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es, const StageSmem& sg, const Sched& sc,
                                              uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0,
-                                             int warp, int lane) {
+                                             int warp, int lane, ChainRt* cx = nullptr) {
+  const uint32_t it_base = CHAIN ? cx->it_base : 0u;
+  unsigned* const out_cnt = CHAIN ? cx->L->out_cnt : nullptr;
+  unsigned* const out2_cnt = CHAIN ? cx->L->out2_cnt : nullptr;
+  int r_vlo = 0, r_vhi = -1;                      // residual producer's row blocks already seen complete (lane 0)
+  // Layer chain: the counter of the sub-tile this warp stored last, not yet bumped (lane 0).  Waiting for the bulk
+  // stores to COMPLETE right after issuing them would stall the warp for a DRAM / L2 round trip per sub-tile, so
+  // the bump is deferred to the next point where the warp either would idle anyway (its next accumulator is not
+  // ready, a dependency has to be polled) or is about to issue the next store (the old one has long completed).
+  // It is always flushed before a wait that another CTA's progress could depend on.
+  unsigned* pend = nullptr;
+  auto flush = [&]() { if (CHAIN && pend) { dep_publish(pend); pend = nullptr; } };
   const PairId pid = pair_id<CG>();
   const int S = a.up;
   const int quarter = warp & 3, group = (warp - WARP_EPI0) >> 2;
@@ -809,7 +926,8 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   const int Ho = a.ep.H_out, Wo = a.ep.W_out;
   const bool reflect = (a.ep.border == SRD_BORDER_REFLECT);
   const bool has_r1 = a.ep.res1 != nullptr;
-  const bool has_temb = a.ep.temb != nullptr;      // block2 / resampling layers: no vector after the activation
+  // block2 / resampling layers: no vector after the activation
+  const bool has_temb = a.ep.temb != nullptr || (CHAIN && cx->L->temb_off >= 0);
   const bool r1_packed = (a.ep.beta1 == 1.0f), r2_packed = (a.ep.beta2 == 1.0f);
   const uint32_t swz = (uint32_t)(lane & 7);     // == m & 7
   uint8_t* my_row = sg.gen + lane * 128;         // this pixel's 128 B row inside a staging buffer
@@ -831,20 +949,25 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     const uint32_t buf = kn & nbuf_mask;
     const uint32_t bar = sg.r_full0 + 8u * buf;
     if (has_r1) {
+      const int Vr = rowblk * TILE_H + a.vstart + g0;
+      if (CHAIN && cx->L->dep_res1.cnt && !dep_cached(cx->L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi)) {
+        flush();
+        dep_wait(cx->L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi, a.err_flag);
+      }
       mbar_expect_tx(bar, 4096u);
-      tma_load_3d(sg.base + buf * 4096u, &a.tmR, bar, j * 64, colblk * TILE_W + 1, rowblk * TILE_H + a.vstart + g0);
+      tma_load_3d(sg.base + buf * 4096u, &a.tmR, bar, j * 64, colblk * TILE_W + 1, Vr);
     } else {
       mbar_arrive(bar);
     }
   };
 
-  uint32_t k = 0;
-  if (lane == 0) prepare(0, set, share);
+  uint32_t k = CHAIN ? cx->k : 0u;
+  if (lane == 0) prepare(k, set, share);
   for (int it = set;; it += n_conc) {
     const int item = sc.get(it);
     if (item < 0) break;
-    const int stage = it & (a.n_stages - 1);
-    const uint32_t round = (uint32_t)(it >> a.stage_shift);   // parity of this TMEM stage
+    const int stage = (int)((it_base + (uint32_t)it) & (uint32_t)(a.n_stages - 1));
+    const uint32_t round = (it_base + (uint32_t)it) >> a.stage_shift;   // parity of this TMEM stage
     const uint32_t t_full = t_full0 + 8u * stage, t_empty = t_empty0 + 8u * stage;
     const int phase = fdiv(item, a.fd_ipp);
     const int t0 = (item - phase * a.items_per_phase) * (a.MT * CG) + pid.rank;
@@ -852,7 +975,14 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     if (S > 1) { pr = fdiv(phase, a.fd_up); ps = phase - pr * S; }
     const bool stamp = (quarter == 0 && lane == 0);
     if (stamp) epi_stamp(a, it, 0);
-    mbar_wait(t_full, round & 1u, a.err_flag, 6);
+    if (CHAIN) {
+      if (!mbar_try(t_full, round & 1u)) {           // would idle: publish the last sub-tile meanwhile
+        if (lane == 0) flush();
+        mbar_wait(t_full, round & 1u, a.err_flag, 6);
+      }
+    } else {
+      mbar_wait(t_full, round & 1u, a.err_flag, 6);
+    }
     tc_fence_after();
     if (stamp) epi_stamp(a, it, 1);
     if (quarter == 0 && lane == 0) dbg_stamp(a, it, 5);
@@ -1008,6 +1138,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
         __syncwarp();
         if (stamp && last_sub) epi_stamp(a, it, 4);
         if (lane == 0) {
+          flush();                                                 // (the previous sub-tile's stores have long completed)
           const uint32_t src = sg.base + buf * 4096u;
           const int V0 = tg.V0 + g0, xc = tg.x0 + 1;               // this warp's 4 rows
           if (which) {                                             // second output: zero ring, one 4-row box
@@ -1071,6 +1202,10 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
           // the buffer of sub-tile k+1 was last read by the store of sub-tile k+1-nbuf
           if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+          if (CHAIN) {       // layer chain: the readers of this tensor learn about these rows at the next flush()
+            unsigned* const cnt = which ? out2_cnt : out_cnt;
+            if (cnt && (t0 + mt * CG) < a.tiles_per_phase) pend = cnt + ((tg.V0 - a.vstart) >> 4);
+          }
           if (stamp && last_sub) epi_stamp(a, it, 6);
           prepare(k + 1, it, qq + a.n_share);
           if (stamp && last_sub) epi_stamp(a, it, 7);
@@ -1087,7 +1222,11 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   }
   // Before the CTA exits the staging buffers must have been READ by the TMA unit; the global writes themselves
   // complete with the grid (and before a dependent grid's griddepcontrol.wait returns).
-  if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  if (lane == 0) {
+    flush();
+    asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+  }
+  if (CHAIN) cx->k = k;
 }
 
 
@@ -1105,14 +1244,16 @@ struct Bars {
   __device__ __forceinline__ uint32_t tmem_slot() const { return base + 8u * (4 * MAX_STAGES + 8); }
   __device__ __forceinline__ uint32_t B_res() const { return base + 8u * (4 * MAX_STAGES + 9); }
   __device__ __forceinline__ uint32_t R_full0() const { return base + 8u * (4 * MAX_STAGES + 10); }
+  // layer chain only (static item order, so the scheduler ring's slots are free): "all MMAs of the layer done"
+  __device__ __forceinline__ uint32_t M_done() const { return base + SCHED_BAR_OFF; }
 };
 
 // Activation producer (one thread).  Per (source, 64-channel chunk): ONE halo box per M tile
 // (stride 1) or one box per (kx, row parity) (stride 2), in the order the MMA role consumes them.
 // Weights have their own producer thread (below): a single in-order thread would park the next
 // activation box behind the weight ring's back-pressure and expose its full HBM latency.
-template <int CG>
-__device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, uint32_t bar_base) {
+template <int CG, bool CHAIN = false>
+__device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, uint32_t bar_base, ChainRt* cx = nullptr) {
   const Bars bars{bar_base};
   const PairId pid = pair_id<CG>();
   const bool leader = (pid.rank == 0);
@@ -1122,6 +1263,10 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, 
   const uint32_t a_stage_bytes = (uint32_t)a.a_stage_bytes;
   int* err = a.err_flag;
   Ring ra{0, 0, a.a_stages};
+  if (CHAIN) ra = cx->ra;
+  int d_vlo[SRD_MAX_SRC], d_vhi[SRD_MAX_SRC];                    // layer chain: source row blocks already seen complete
+#pragma unroll
+  for (int s = 0; s < SRD_MAX_SRC; ++s) { d_vlo[s] = 0; d_vhi[s] = -1; }
   const Sched sc = make_sched<CG>(a, bar_base);
   const bool scheduler = sc.dyn && leader;                       // this thread hands out the pair's items
   // the first two items of a pair are static; the ticket drawn while item il is loaded names item il + 2, so an
@@ -1150,6 +1295,18 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, 
       const int rowblk = fdiv(tt, a.fd_colblk);
       V0[mt] = rowblk * TILE_H + vstart;
       X0[mt] = (tt - rowblk * n_colblk) * TILE_W;
+    }
+    if (CHAIN) {
+      // the rows this item's boxes cover must have been written by the layers that produce them
+#pragma unroll
+      for (int s = 0; s < SRD_MAX_SRC; ++s) {
+        if (s < n_src && cx->L->dep_src[s].cnt) {
+          for (int mt = 0; mt < MT; ++mt) {
+            if (stride == 1) dep_wait(cx->L->dep_src[s], V0[mt] - 1, V0[mt] + TILE_H + 1, d_vlo[s], d_vhi[s], err);
+            else dep_wait(cx->L->dep_src[s], 2 * V0[mt], 2 * V0[mt] + 2 * BOX_ROWS, d_vlo[s], d_vhi[s], err);
+          }
+        }
+      }
     }
     for (int s = 0; s < n_src; ++s) {
       const CUtensorMap* tm = &a.tmA[s];
@@ -1195,13 +1352,15 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, 
       }
     }
   }
+  if (CHAIN) cx->ra = ra;
 }
 
 // Weight producer (one thread): either all k-blocks once (resident) or, per item, kb_per_phase
 // k-blocks of the item's phase streamed through the weight ring.  Each CTA of a pair holds
 // Npad / CG rows of every k-block; the leader's barriers count the bytes of BOTH CTAs.
-template <int CG>
-__device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b_base, uint32_t bar_base) {
+template <int CG, bool CHAIN = false>
+__device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b_base, uint32_t bar_base,
+                                                     ChainRt* cx = nullptr) {
   const Bars bars{bar_base};
   const PairId pid = pair_id<CG>();
   const bool leader = (pid.rank == 0);
@@ -1209,6 +1368,8 @@ __device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b
   const uint32_t B_BYTES = (uint32_t)b_rows * 128u;
   int* err = a.err_flag;
   if (a.b_resident) {
+    // layer chain: the previous layer of the segment has the resident region until its last MMA has completed
+    if (CHAIN && cx->j > 0) mbar_wait(bars.M_done(), (uint32_t)(cx->j - 1) & 1u, err, 12);
     if (leader) mbar_expect_tx(bars.B_res(), (uint32_t)a.kb_total * B_BYTES * CG);
     for (int kb = 0; kb < a.kb_total; ++kb)
       tma_load_2d<CG>(b_base + (uint32_t)kb * B_BYTES, &a.tmB, bars.B_res(), 0, kb * Npad + b_row0);
@@ -1216,6 +1377,7 @@ __device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b
   }
   const int kb_per_phase = a.kb_per_phase;
   Ring rb{0, 0, a.b_stages};
+  if (CHAIN) rb = cx->rb;
   const Sched sc = make_sched<CG>(a, bar_base);
   for (int il = 0;; ++il) {
     const int item = sc.get(il);
@@ -1228,6 +1390,7 @@ __device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b
       rb.next();
     }
   }
+  if (CHAIN) cx->rb = rb;
 }
 
 // MMA issuer (one thread).  One tap = MT x 4 MMAs (K = 64) against one weight k-block.  The issuing
@@ -1237,9 +1400,9 @@ __device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b
 // the low word (high words are constants), and for the 3x3 / 2x2 / 1x1 halo cases (TAPS = 9/4/1)
 // the tap loops are unrolled so tap offsets are immediates.  TAPS = 0: generic runtime loops
 // (stride 2, validation modes).
-template <int TAPS, int MT, bool BRES, int CG, bool DUAL = false>
+template <int TAPS, int MT, bool BRES, int CG, bool DUAL = false, bool CHAIN = false>
 __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, uint32_t a_base, uint32_t b_base,
-                                         uint32_t bar_base, int issuer = 0) {
+                                         uint32_t bar_base, int issuer = 0, ChainRt* cx = nullptr) {
   const Bars bars{bar_base};
   const PairId pid = pair_id<CG>();                  // only the leader CTA of a pair runs this role
   const int S = a.up, n_chunks = a.n_chunks;
@@ -1249,8 +1412,9 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
   const uint32_t kbpp16 = (uint32_t)a.kb_per_phase * bB16;
   int* err = a.err_flag;
   Ring ra{0, 0, a.a_stages}, rb{0, 0, a.b_stages}, rt{0, 0, a.n_stages};
+  if (CHAIN) { ra = cx->ra; rb = cx->rb; rt = cx->rt; }
   if (BRES) {
-    mbar_wait(bars.B_res(), 0, err, 7);
+    mbar_wait(bars.B_res(), CHAIN ? ((uint32_t)cx->j & 1u) : 0u, err, 7);   // chain: one phase per resident layer
     tc_fence_after();
   }
   // SRD_DUAL_ISSUE: two issuing threads (different schedulers) take alternate items, skipping each other's
@@ -1390,6 +1554,14 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
     dbg_stamp(a, mma_il, 3);
     ++mma_il;
     rt.next();
+  }
+  if (CHAIN) {
+    // "every MMA of this layer has completed": the next layer's weight producer may overwrite resident weights, and
+    // at the end of a segment this thread itself waits for it, so that no tcgen05.commit arrival is still in flight
+    // when the barriers are re-initialised for the next segment
+    tc_commit<CG>(bars.M_done());
+    if (cx->j + 1 == cx->n_seg) mbar_wait(bars.M_done(), (uint32_t)cx->j & 1u, err, 13);
+    cx->ra = ra; cx->rb = rb; cx->rt = rt;
   }
 }
 
@@ -1558,6 +1730,212 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   }
   kern_stamp(a, 5);
   kern_stamp(a, 7, true);
+}
+
+// ------------------------------------------------------------------------------------------ layer chain kernel
+// Shared-memory layout of the chain kernel: a fixed head (barriers, a DOUBLE-buffered bias / time-embedding vector
+// pair so the epilogue warps can stage layer l+1's vectors while they run layer l, the fused-head / linear-residual
+// weights) followed by the per-segment A | B | staging regions of the ordinary plan.
+constexpr int CHAIN_BT_OFF = BAR_BYTES;                        // 2 x (bias[256], temb[256]) floats
+constexpr int CHAIN_BT_BYTES = 2 * 256 * 4;
+constexpr int CHAIN_HEAD_OFF = CHAIN_BT_OFF + 2 * CHAIN_BT_BYTES;   // [4][256] + [4] floats
+constexpr int CHAIN_FIXED_BYTES = 10240;
+static_assert(CHAIN_HEAD_OFF + (4 * 256 + 4) * 4 <= CHAIN_FIXED_BYTES, "chain head does not fit");
+static_assert(CHAIN_FIXED_BYTES <= BAR_BYTES + VEC_BYTES, "chain head larger than the single-layer kernel's tail");
+
+// bias / temb (+ the second output's bias, zero temb) of one layer -> bt[0..511]; head / linear-residual weights ->
+// s_head (only one layer of a segment may use those: see same_segment)
+__device__ __forceinline__ void chain_stage_vecs(const ChainLayer& L, const float* temb_row, float* bt, float* s_head,
+                                                 int tid, int nthr) {
+  const TcArgs& a = L.a;
+  float* s_bias = bt;
+  float* s_temb = bt + 256;
+  const float* temb = L.temb_off >= 0 ? temb_row + L.temb_off : a.ep.temb;
+  const int Npad = a.Npad, N = a.ep.N;
+  for (int i = tid; i < Npad; i += nthr) {
+    s_bias[i] = (i < N) ? __ldg(a.ep.bias + i) : 0.f;
+    s_temb[i] = (temb && a.ep.temb_bstride == 0 && i < N) ? __ldg(temb + i) : 0.f;
+  }
+  if (a.dual) {
+    for (int i = tid; i < Npad; i += nthr) {
+      s_bias[Npad + i] = (i < N) ? __ldg(a.bias2 + i) : 0.f;
+      s_temb[Npad + i] = 0.f;
+    }
+  }
+  if (a.head_w) {
+    for (int i = tid; i < 4 * Npad; i += nthr) {
+      const int jh = i / Npad, c = i % Npad;
+      s_head[i] = (jh < a.ep.planar_c && c < N) ? __ldg(a.head_w + (size_t)jh * N + c) : 0.f;
+    }
+    if (tid < 4) s_head[1024 + tid] = (tid < a.ep.planar_c) ? __ldg(a.head_b + tid) : 0.f;
+  }
+  if (a.lin_w) {
+    for (int i = tid; i < 4 * Npad; i += nthr) {
+      const int c = i / Npad, n = i % Npad;
+      s_head[i] = (c < a.lin_c && n < N) ? __ldg(a.lin_w + (size_t)n * a.lin_c + c) : 0.f;
+    }
+  }
+}
+
+template <int CG>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const ChainLayer* __restrict__ layers, int n_layers,
+                                                                   const float* __restrict__ temb_row) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const gen0 = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_base = smem_base;
+  const Bars bars{bar_base};
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen0 + 8 * (4 * MAX_STAGES + 8));
+  float* const bt0 = reinterpret_cast<float*>(gen0 + CHAIN_BT_OFF);
+  float* const s_head = reinterpret_cast<float*>(gen0 + CHAIN_HEAD_OFF);
+  const uint32_t a_base = smem_base + CHAIN_FIXED_BYTES;
+
+  if (warp == WARP_MMA) {       // the 512 TMEM columns are allocated once for the whole chain
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars.tmem_slot()), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars.tmem_slot()), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  const PairId pid = pair_id<CG>();
+  ChainRt cx;
+  cx.temb_row = temb_row;
+  uint32_t tmem_base = 0;
+  bool first = true;
+  int l0 = 0;
+  while (l0 < n_layers) {
+    // ---- a SEGMENT = consecutive layers with the same shared-memory / TMEM / barrier plan: inside it every role runs
+    // from layer to layer without ever meeting the others; between segments the CTA pair drains and re-plans.
+    int l1 = l0 + 1;
+    while (l1 < n_layers && !layers[l1].seg_first) ++l1;
+    const TcArgs& a0 = layers[l0].a;
+    const uint32_t b_base = a_base + (uint32_t)a0.a_stages * a0.MT * a0.a_stage_bytes;
+    const uint32_t stg_base = b_base + (uint32_t)a0.b_region_bytes;
+    if (warp == WARP_TMA && lane == 0) {
+      // the same set of barriers is (re)built for every segment; a live mbarrier object must be invalidated before
+      // mbarrier.init may be applied to its location again
+      if (!first) {
+        for (int s = 0; s < MAX_STAGES; ++s) {
+          mbar_inval(bars.A_full(s)); mbar_inval(bars.A_empty(s)); mbar_inval(bars.B_full(s)); mbar_inval(bars.B_empty(s));
+        }
+        for (int s = 0; s < 4; ++s) { mbar_inval(bars.T_full(s)); mbar_inval(bars.T_empty(s)); }
+        mbar_inval(bars.B_res());
+        mbar_inval(bars.M_done());
+        for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_inval(bars.R_full0() + 8u * s);
+      }
+      for (int s = 0; s < MAX_STAGES; ++s) {
+        mbar_init(bars.A_full(s), 1); mbar_init(bars.A_empty(s), 1); mbar_init(bars.B_full(s), 1); mbar_init(bars.B_empty(s), 1);
+      }
+      for (int s = 0; s < 4; ++s) { mbar_init(bars.T_full(s), 1); mbar_init(bars.T_empty(s), (uint32_t)(4 * a0.n_share * CG)); }
+      mbar_init(bars.B_res(), 1);
+      mbar_init(bars.M_done(), 1);
+      for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(bars.R_full0() + 8u * s, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    chain_stage_vecs(layers[l0], temb_row, bt0, s_head, (int)threadIdx.x, TC_THREADS);
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();
+    tc_fence_after();
+    if (first) {
+      tmem_base = *tmem_slot_ptr;
+      // everything so far touched only launch constants; activations follow (see conv_tc_kernel)
+      asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+      if (warp != WARP_TMB) asm volatile("griddepcontrol.wait;" ::: "memory");
+      first = false;
+    }
+    cx.it_base = 0; cx.k = 0; cx.n_seg = l1 - l0;
+    cx.ra = Ring{0, 0, a0.a_stages}; cx.rb = Ring{0, 0, a0.b_stages}; cx.rt = Ring{0, 0, a0.n_stages};
+
+    if (warp == WARP_TMA) {
+      if (elect_one_sync()) {
+        for (int l = l0; l < l1; ++l) {
+          const TcArgs& a = layers[l].a;
+          cx.L = &layers[l]; cx.j = l - l0;
+          for (int s = 0; s < a.n_src; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA[s]) : "memory");
+          producer_role<CG, true>(a, a_base, bar_base, &cx);
+        }
+      }
+    } else if (warp == WARP_TMB) {
+      if (elect_one_sync()) {
+        for (int l = l0; l < l1; ++l) {
+          const TcArgs& a = layers[l].a;
+          cx.L = &layers[l]; cx.j = l - l0;
+          asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmB) : "memory");
+          weight_producer_role<CG, true>(a, b_base, bar_base, &cx);
+        }
+      }
+    } else if (warp == WARP_MMA) {
+      if ((CG == 1 || pid.rank == 0) && elect_one_sync()) {
+        for (int l = l0; l < l1; ++l) {
+          const TcArgs& a = layers[l].a;
+          cx.L = &layers[l]; cx.j = l - l0;
+          const int taps = a.a_mode ? a.nkx * a.nky : 0;
+#define SRD_MMA_CASE(T, D)                                                                                             \
+  do {                                                                                                                 \
+    if (a.b_resident && a.MT == 2) mma_role<T, 2, true, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);  \
+    else if (a.b_resident) mma_role<T, 1, true, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);          \
+    else if (a.MT == 2) mma_role<T, 2, false, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);            \
+    else mma_role<T, 1, false, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);                           \
+  } while (0)
+          if (a.dual) SRD_MMA_CASE(9, true);
+          else if (taps == 9 && a.nkx == 3) SRD_MMA_CASE(9, false);
+          else if (taps == 4 && a.nkx == 2) SRD_MMA_CASE(4, false);
+          else if (taps == 1) SRD_MMA_CASE(1, false);
+          else SRD_MMA_CASE(0, false);
+#undef SRD_MMA_CASE
+        }
+      }
+    } else if (warp >= WARP_EPI0 && warp < WARP_EPI0 + EPI_WARPS) {
+      const int etid = (int)threadIdx.x - WARP_EPI0 * 32;
+      const int ew = warp - WARP_EPI0;
+      for (int l = l0; l < l1; ++l) {
+        const TcArgs& a = layers[l].a;
+        const int j = l - l0;
+        cx.L = &layers[l]; cx.j = j;
+        // every epilogue warp has left layer l-1: its vector buffer may be refilled, and layer l's (staged while
+        // layer l-1 ran) is visible to all
+        asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+        if (l + 1 < l1) chain_stage_vecs(layers[l + 1], temb_row, bt0 + ((j + 1) & 1) * 512, s_head, etid, EPI_WARPS * 32);
+        EpiSmem es;
+        const Sched sc = make_sched<CG>(a, bar_base);
+        es.bias = bt0 + (j & 1) * 512; es.temb = es.bias + 256;
+        es.head_w = a.head_w ? s_head : nullptr; es.head_b = s_head + 1024; es.hpart = nullptr;
+        es.lin_w = a.lin_w ? s_head : nullptr;
+        if (a.epi_tma) {
+          StageSmem sg;
+          sg.base = stg_base + (uint32_t)(ew * a.epi_nbuf) * 4096u;
+          sg.gen = smem_raw + (sg.base - smem_u32(smem_raw));
+          sg.r_full0 = bars.R_full0() + 8u * (uint32_t)(ew * 2);
+          if (a.ep.act == SRD_ACT_MISH)
+            epilogue_tma<SRD_ACT_MISH, CG, true>(a, es, sg, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx);
+          else
+            epilogue_tma<SRD_ACT_NONE, CG, true>(a, es, sg, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx);
+        } else if (a.ep.act == SRD_ACT_MISH)
+          epilogue_role<SRD_ACT_MISH, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx);
+        else if (a.ep.act == SRD_ACT_LRELU02)
+          epilogue_role<SRD_ACT_LRELU02, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx);
+        else
+          epilogue_role<SRD_ACT_NONE, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx);
+        cx.it_base += (pid.pair < a.n_items) ? (uint32_t)((a.n_items - 1 - pid.pair) / pid.n_pairs + 1) : 0u;
+      }
+    }
+    // segment end: all roles of the pair are done (stores issued and read; completion was awaited when publishing)
+    tc_fence_before();
+    __syncthreads();
+    if (CG == 2) cluster_sync_all();
+    l0 = l1;
+  }
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    if (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
 }
 
 // ------------------------------------------------------------------------------------------ host
@@ -1892,7 +2270,9 @@ static int tc_set_func_attrs(int dev) {
   if (dev < 0 || dev >= 64) return 1;
   if (done[dev]) return 0;
   if (cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-      cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(conv_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(conv_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return 1;
   done[dev] = true;
   return 0;
@@ -1925,6 +2305,152 @@ int launch_conv_tc(const TcPlan& plan, const float* temb, cudaStream_t stream) {
   cfg.numAttrs = (unsigned)n_at;
   if (a.cg == 1) SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, a));
   else SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, a));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------ layer chain: host
+struct TcChain {
+  ChainLayer* d_layers = nullptr;
+  unsigned* d_counters = nullptr;
+  size_t counter_bytes = 0;
+  int n_layers = 0, n_segments = 0, grid = 0, smem = 0, cg = 2;
+  ~TcChain() {
+    if (d_layers) cudaFree(d_layers);
+    if (d_counters) cudaFree(d_counters);
+  }
+};
+
+// Two consecutive layers may share a segment when every role can carry its ring / barrier state across: identical
+// shared-memory partition, TMEM stage layout and epilogue organisation.  A layer that keeps head / linear-residual
+// weights in the shared vector block is a segment of its own (that block is single-buffered).
+static bool same_segment(const TcArgs& x, const TcArgs& y) {
+  return x.cg == y.cg && x.a_mode == y.a_mode && x.a_stage_bytes == y.a_stage_bytes && x.MT == y.MT &&
+         x.a_stages == y.a_stages && x.b_resident == y.b_resident && x.Npad == y.Npad && x.b_stages == y.b_stages &&
+         x.b_region_bytes == y.b_region_bytes && x.n_stages == y.n_stages && x.n_share == y.n_share && x.dual == y.dual &&
+         x.epi_tma == y.epi_tma && x.epi_nbuf == y.epi_nbuf && !x.head_w && !y.head_w && !x.lin_w && !y.lin_w;
+}
+
+// links[i]: for every K source / the res1 tensor of layer i, the chain layer that produces it (-1: written before the
+// launch) and which of its outputs (0: out, 1: second output); temb_off >= 0: offset of the layer's time-embedding
+// vector in the per-launch row.
+struct TcChainLink {
+  int src_layer[SRD_MAX_SRC], src_which[SRD_MAX_SRC];
+  int res1_layer, res1_which;
+  int temb_off;
+};
+
+int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, TcChain* chain, int g_single_segments) {
+  SRD_CHECK(n >= 1 && n <= 4096, "conv_chain: bad layer count %d", n);
+  std::vector<ChainLayer> L((size_t)n);
+  memset(L.data(), 0, sizeof(ChainLayer) * (size_t)n);
+  // counters: one array per (layer, output) that has a reader inside the chain
+  std::vector<long long> cnt_off((size_t)n * 2, -1);
+  std::vector<int> n_rowblk((size_t)n);
+  long long total = 0;
+  auto need = [&](int p, int which) {
+    if (cnt_off[(size_t)p * 2 + which] < 0) { cnt_off[(size_t)p * 2 + which] = total; total += n_rowblk[p]; }
+  };
+  int smem = 0, cg = plans[0]->args.cg;
+  for (int i = 0; i < n; ++i) {
+    const TcArgs& a = plans[i]->args;
+    SRD_CHECK(a.cg == cg, "conv_chain: layers disagree on the CTA-pair mode");
+    SRD_CHECK(!a.dyn_sched && !a.dbg, "conv_chain: layer %d uses the dynamic scheduler / debug stamps", i);
+    SRD_CHECK(a.up == 1 || a.up == 2, "conv_chain: layer %d has up = %d (only 1 and 2 can be chained)", i, a.up);
+    n_rowblk[i] = (a.n_vrows - a.vstart + TILE_H - 1) / TILE_H;
+    const int layer_smem = plans[i]->smem - (BAR_BYTES + VEC_BYTES) + CHAIN_FIXED_BYTES;
+    if (layer_smem > smem) smem = layer_smem;
+  }
+  SRD_CHECK(smem <= 227 * 1024, "conv_chain: shared-memory plan too large (%d)", smem);
+  for (int i = 0; i < n; ++i) {
+    const TcChainLink& k = links[i];
+    for (int s = 0; s < plans[i]->args.n_src; ++s)
+      if (k.src_layer[s] >= 0) {
+        SRD_CHECK(k.src_layer[s] < i && (k.src_which[s] == 0 || k.src_which[s] == 1), "conv_chain: bad source link of layer %d", i);
+        need(k.src_layer[s], k.src_which[s]);
+      }
+    if (k.res1_layer >= 0) {
+      SRD_CHECK(k.res1_layer < i && (k.res1_which == 0 || k.res1_which == 1), "conv_chain: bad res1 link of layer %d", i);
+      need(k.res1_layer, k.res1_which);
+    }
+  }
+  if (total == 0) total = 1;
+  SRD_CUDA(cudaMalloc((void**)&chain->d_counters, (size_t)total * sizeof(unsigned)));
+  chain->counter_bytes = (size_t)total * sizeof(unsigned);
+  auto make_dep = [&](int p, int which, ChainDep* d) {
+    const TcArgs& pa = plans[p]->args;
+    const int Ho = pa.ep.H_out;
+    d->cnt = chain->d_counters + cnt_off[(size_t)p * 2 + which];
+    const int n_phase = pa.up * pa.up;
+    d->expect = pa.epi_tma ? (unsigned)(pa.n_colblk * (pa.Npad / 64) * 4 * n_phase)
+                           : (unsigned)(pa.n_colblk * 4 * pa.n_share * n_phase);
+    d->n_rowblk = n_rowblk[p];
+    d->hp = Ho + 2; d->H = Ho;
+    d->n_rows = (pa.n_vrows / pa.period) * (Ho + 2);
+    d->up_shift = pa.up == 2 ? 1 : 0;
+    d->period = pa.period; d->voff = pa.voff; d->vstart = pa.vstart;
+    d->fd_hp = make_fastdiv((uint32_t)(Ho + 2));
+  };
+  int n_seg = 0;
+  for (int i = 0; i < n; ++i) {
+    const TcArgs& a = plans[i]->args;
+    const TcChainLink& k = links[i];
+    L[i].a = a;
+    L[i].temb_off = k.temb_off;
+    SRD_CHECK(k.temb_off < 0 || (a.fast && a.ep.temb_bstride == 0), "conv_chain: layer %d cannot take a per-launch temb row", i);
+    for (int s = 0; s < a.n_src; ++s)
+      if (k.src_layer[s] >= 0) make_dep(k.src_layer[s], k.src_which[s], &L[i].dep_src[s]);
+    if (k.res1_layer >= 0) {
+      SRD_CHECK(a.epi_tma || a.epi_geo == 0, "conv_chain: layer %d reads an in-chain residual in a strided register epilogue", i);
+      make_dep(k.res1_layer, k.res1_which, &L[i].dep_res1);
+    }
+    if (cnt_off[(size_t)i * 2] >= 0) L[i].out_cnt = chain->d_counters + cnt_off[(size_t)i * 2];
+    if (cnt_off[(size_t)i * 2 + 1] >= 0) {
+      SRD_CHECK(a.dual, "conv_chain: layer %d has no second output", i);
+      L[i].out2_cnt = chain->d_counters + cnt_off[(size_t)i * 2 + 1];
+    }
+    L[i].seg_first = (i == 0 || g_single_segments || !same_segment(plans[i - 1]->args, a)) ? 1 : 0;
+    n_seg += L[i].seg_first;
+  }
+  SRD_CUDA(cudaMalloc((void**)&chain->d_layers, sizeof(ChainLayer) * (size_t)n));
+  SRD_CUDA(cudaMemcpy(chain->d_layers, L.data(), sizeof(ChainLayer) * (size_t)n, cudaMemcpyHostToDevice));
+  int dev = 0, n_sm = 148;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
+  chain->n_layers = n; chain->n_segments = n_seg; chain->smem = smem; chain->cg = cg;
+  chain->grid = (n_sm / cg) * cg;
+  SRD_CHECK(tc_set_func_attrs(dev) == 0, "conv_chain: cudaFuncSetAttribute(MaxDynamicSharedMemorySize) failed");
+  return 0;
+}
+
+TcChain* tc_chain_new() { return new (std::nothrow) TcChain; }
+void tc_chain_delete(TcChain* c) { delete c; }
+int tc_chain_segments(const TcChain* c) { return c->n_segments; }
+
+int launch_chain(const TcChain& c, const float* temb_row, cudaStream_t stream) {
+  SRD_CUDA(cudaMemsetAsync(c.d_counters, 0, c.counter_bytes, stream));
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)c.grid);
+  cfg.blockDim = dim3(TC_THREADS);
+  cfg.dynamicSmemBytes = (size_t)c.smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute at[2];
+  int n_at = 0;
+  if (g_pdl) {
+    at[n_at].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[n_at].val.programmaticStreamSerializationAllowed = 1;
+    ++n_at;
+  }
+  if (c.cg == 2) {
+    at[n_at].id = cudaLaunchAttributeClusterDimension;
+    at[n_at].val.clusterDim.x = 2; at[n_at].val.clusterDim.y = 1; at[n_at].val.clusterDim.z = 1;
+    ++n_at;
+  }
+  cfg.attrs = at;
+  cfg.numAttrs = (unsigned)n_at;
+  const ChainLayer* layers = c.d_layers;
+  int n = c.n_layers;
+  if (c.cg == 1) SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel<1>, layers, n, temb_row));
+  else SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel<2>, layers, n, temb_row));
   return 0;
 }
 

@@ -17,6 +17,10 @@ PRECISIONS = ("bf16", "fp32", "bf16_direct")
 FUSE_RES_CONV = os.environ.get("SRD_NO_FUSED_RES") != "1"
 REVERSE_ORDER = os.environ.get("SRD_NO_REVERSE", "0") != "1"   # alternate the tile order of consecutive conv launches
 FOLD_COND = os.environ.get("SRD_NO_FOLD_COND", "0") != "1"     # add cond after the first Downsample (see CondProgram)
+# Unet.forward as ONE persistent launch (srd_chain_*): SRD_CHAIN=0 falls back to one launch per layer,
+# SRD_CHAIN_SINGLE=1 keeps the single launch but drains the CTA pair after every layer (debug)
+USE_CHAIN = os.environ.get("SRD_CHAIN", "1") != "0"
+CHAIN_SINGLE_SEGMENTS = os.environ.get("SRD_CHAIN_SINGLE", "0") == "1"
 
 
 def _ceil(a, b):
@@ -212,8 +216,9 @@ class PackedConv:
 # ops
 # --------------------------------------------------------------------------------------------
 class ConvOp:
-    def __init__(self, desc, keep, temb_off=None):
+    def __init__(self, desc, keep, temb_off=None, io=None):
         self.desc, self.keep, self.temb_off = desc, keep, temb_off
+        self.io = io or {}      # Act objects read / written (srcs, res1, res2, lin, out, out2, dst2): chain dependencies
         h = C.c_void_p()
         L.check(L.lib().srd_conv_plan_create(C.byref(desc), C.byref(h)), "srd_conv_plan_create")
         self.handle = h
@@ -229,6 +234,69 @@ class ConvOp:
         try:
             if self.handle:
                 L.lib().srd_conv_plan_destroy(self.handle)
+                self.handle = None
+        except Exception:
+            pass
+
+
+class ChainOp:
+    """A run of tcgen05 conv launches executed as ONE persistent kernel (include/srdiff_b200.h: srd_chain_*).
+    Dependencies between the layers are derived from the activation buffers they read and write."""
+
+    def __init__(self, ops):
+        self.ops = ops
+        n = len(ops)
+        writer = {}                                    # id(Act) -> (layer, which output)
+        links = (L.SrdChainLink * n)()
+        for i, op in enumerate(ops):
+            io, k = op.io, links[i]
+            for s_ in range(L.SRD_MAX_SRC):
+                k.src_layer[s_], k.src_which[s_] = -1, 0
+            for s_, a in enumerate(io["srcs"]):
+                k.src_layer[s_], k.src_which[s_] = writer.get(id(a), (-1, 0))
+            k.res1_layer, k.res1_which = writer.get(id(io["res1"]), (-1, 0)) if io["res1"] is not None else (-1, 0)
+            k.temb_off = op.temb_off if op.temb_off is not None else -1
+            for key, which in (("out", 0), ("dst2", 1)):
+                if io[key] is not None:
+                    writer[id(io[key])] = (i, which)
+        self.links = links
+        handles = (C.c_void_p * n)(*[op.handle for op in ops])
+        h = C.c_void_p()
+        L.check(L.lib().srd_chain_create(handles, links, n, 1 if CHAIN_SINGLE_SEGMENTS else 0, C.byref(h)),
+                "srd_chain_create")
+        self.handle = h
+        self.n_segments = L.lib().srd_chain_segments(h)
+
+    @staticmethod
+    def chainable(ops):
+        """Every op a tcgen05 conv with a batch-uniform time embedding; every buffer written once, never read before
+        it is written, nothing in place; res2 / lin sources and second NHWC copies come from outside the chain."""
+        written, read = set(), set()
+        for op in ops:
+            if not isinstance(op, ConvOp) or op.kernel != L.KERNEL_TC or op.desc.temb_bstride != 0:
+                return False
+            io = op.io
+            if io.get("out2") is not None or op.desc.up not in (1, 2):
+                return False
+            ins = [id(a) for a in io["srcs"]] + [id(io[k]) for k in ("res1", "res2", "lin") if io[k] is not None]
+            for k in ("res2", "lin"):
+                if io[k] is not None and id(io[k]) in written:
+                    return False
+            outs = [id(io[k]) for k in ("out", "dst2") if io[k] is not None]
+            if any(o in written or o in read or o in ins for o in outs):
+                return False
+            read.update(ins)
+            written.update(outs)
+        return len(ops) >= 2
+
+    def run(self, ctx):
+        L.check(L.lib().srd_chain_run(self.handle, C.c_void_p(ctx.temb_ptr) if ctx.temb_ptr else None, _stream()),
+                "srd_chain_run")
+
+    def __del__(self):
+        try:
+            if self.handle:
+                L.lib().srd_chain_destroy(self.handle)
                 self.handle = None
         except Exception:
             pass
@@ -256,6 +324,8 @@ class Builder:
         self.device = device
         self.prec = precision if isinstance(precision, Precision) else Precision(precision)
         self.ops = []
+        self.chain = None       # ChainOp over all of `ops` (make_chain)
+        self.chain_error = None
         self._dir = {}          # id(Act) -> 1 if its last writer walked the tiles in reverse order
 
     def act(self, B, H, W, C_, ct=None, slack=0):
@@ -264,12 +334,25 @@ class Builder:
 
     def run(self, ctx=None):
         ctx = ctx or RunCtx()
+        if self.chain is not None:
+            self.chain.run(ctx)
+            return
         for op in self.ops:
             op.run(ctx)
 
+    def make_chain(self):
+        """Fuse the whole launch list into one persistent launch when every op qualifies (ChainOp.chainable)."""
+        if USE_CHAIN and self.prec.name == "bf16" and ChainOp.chainable(self.ops):
+            try:
+                self.chain = ChainOp(self.ops)
+            except L.SrdError as e:          # a layer the chain planner does not take: one launch per layer instead
+                self.chain, self.chain_error = None, str(e)
+        return self.chain
+
     def count_kernels(self):
+        """(launches per run, tcgen05 conv layers among the ops)"""
         n_tc = sum(1 for o in self.ops if isinstance(o, ConvOp) and o.kernel == L.KERNEL_TC)
-        return len(self.ops), n_tc
+        return (1 if self.chain is not None else len(self.ops)), n_tc
 
     # ---- generic conv ----------------------------------------------------------------------
     def conv(self, pw, srcs, out=None, out_coff=0, out2=None, out2_coff=0, act=L.ACT_NONE, alpha=1.0,
@@ -353,7 +436,10 @@ class Builder:
         if head is not None:
             d.head_w, d.head_b = head[0].data_ptr(), head[1].data_ptr()
             keep.append(head)
-        op = ConvOp(d, keep, temb_off)
+        io = {"srcs": [s_[0] for s_ in srcs], "res1": res1[0] if res1 is not None else None,
+              "res2": res2[0] if res2 is not None else None, "lin": lin[0] if lin is not None else None,
+              "out": out, "out2": out2, "dst2": dual[1] if dual is not None else None}
+        op = ConvOp(d, keep, temb_off, io)
         self.ops.append(op)
         return op
 
@@ -632,6 +718,8 @@ class UnetProgram:
             f = bld.act(B, h, w, xd_)
             bld.conv(_pc(fc0), [(x, 0, xd_)], out=f, act=L.ACT_MISH, border=RK)
             bld.conv(_pc(fc1), [(f, 0, xd_)], planar=self.eps, planar_c=od)
+        if not per_sample_temb:
+            bld.make_chain()
 
     def run(self, temb_ptr):
         self.bld.run(RunCtx(temb_ptr))

@@ -131,6 +131,27 @@ int srd_conv_plan_destroy(SrdConvPlan* plan);
 int srd_conv_plan_kernel(const SrdConvPlan* plan);
 /* Launch.  `temb` overrides desc.temb when non-NULL (per-step row of the time table). */
 int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream);
+/* ---- Layer chain: a LIST of tcgen05 conv plans executed by ONE persistent launch (the whole Unet.forward :820-847
+ * of one denoiser call).  CTA pairs move from layer to layer on their own; a consumer layer is ordered after its
+ * producer by per-row-block completion counters in global memory instead of kernel boundaries, so the per-launch
+ * fill / drain of ~40 separate launches disappears.  links[i] names, for every K source and for res1 of layer i, the
+ * chain layer that writes that tensor (-1: written before the launch) and which of its outputs (0: out, 1: the second
+ * output dst2); res2, lin_src, temb and the weights must not be produced inside the chain.  temb_off >= 0: the
+ * layer's time-embedding vector is temb_row + temb_off of the per-launch row handed to srd_chain_run (replaces the
+ * per-launch `temb` of srd_conv_run).  flags bit 0: every layer its own segment (debug).  The buffers must all be
+ * distinct (no in-place layers). */
+typedef struct SrdChain SrdChain;
+typedef struct {
+  int32_t src_layer[SRD_MAX_SRC], src_which[SRD_MAX_SRC];
+  int32_t res1_layer, res1_which;
+  int32_t temb_off;
+} SrdChainLink;
+int srd_chain_create(SrdConvPlan* const* plans, const SrdChainLink* links, int32_t n, int32_t flags, SrdChain** out);
+int srd_chain_run(const SrdChain* chain, const float* temb_row, void* stream);
+int srd_chain_destroy(SrdChain* chain);
+/* number of segments (runs of layers the roles cross without a CTA-level drain) the planner found */
+int srd_chain_segments(const SrdChain* chain);
+
 /* Tuning / validation switches for plans created afterwards (defaults: a_mode = 1, b_resident = 1).
  * a_mode bit 0: 1 = one halo TMA box per K chunk, taps addressed by 128 B-granular UMMA descriptor
  *               offsets (default); 0 = one box per (chunk, kx) with 1024 B-aligned descriptors.
