@@ -36,6 +36,7 @@ TcChain* tc_chain_new();
 void tc_chain_delete(TcChain*);
 int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, TcChain* chain, int single_segments);
 int tc_chain_segments(const TcChain* c);
+int tc_chain_max_layers();
 int launch_chain(const TcChain& c, const float* temb_row, cudaStream_t stream);
 void tc_set_debug(unsigned long long* p);
 
@@ -209,6 +210,8 @@ int srd_chain_destroy(SrdChain* chain) {
   if (chain) tc_chain_delete(reinterpret_cast<srd::TcChain*>(chain));
   return 0;
 }
+
+int srd_chain_max_layers(void) { return tc_chain_max_layers(); }
 
 int srd_chain_segments(const SrdChain* chain) {
   return chain ? tc_chain_segments(reinterpret_cast<const srd::TcChain*>(chain)) : -1;

@@ -82,13 +82,18 @@ __device__ __forceinline__ int fdiv(int n, const FastDiv& f) {
   return (int)(((uint64_t)(uint32_t)n * f.mul) >> f.shr);
 }
 
-struct TcArgs {
+// The TMA tensor maps of one layer.  Kept apart from the scalar arguments: the single-layer kernel receives both as
+// __grid_constant__ parameters, the chain kernel receives the scalar arguments of ALL its layers in parameter space
+// (constant-bank operands, like the single-layer kernel's) and finds the maps in global memory.
+struct TcMaps {
   CUtensorMap tmA[SRD_MAX_SRC];
   CUtensorMap tmB;
   CUtensorMap tmO;         // output, box {64 ch, 8 px, 4 rows} = one epilogue warp's rows (TMA-staged epilogue)
   CUtensorMap tmOrow;      // output, box {64 ch, 8 px, 1 row}
   CUtensorMap tmR;         // residual res1, box {64 ch, 8 px, 4 rows}
   CUtensorMap tmO2;        // second output (dual), box {64 ch, 8 px, 4 rows}
+};
+struct TcArgs {
   int n_src;
   int nchunk[SRD_MAX_SRC];
   int H_m, W_m;            // output positions per image (per phase)
@@ -160,7 +165,6 @@ struct ChainLayer {
   unsigned* out2_cnt;      // ... for the second output (SrdConvDesc.N2)
   int temb_off;            // >= 0: time-embedding vector = temb_row + temb_off (per-launch row of the time table)
   int seg_first;           // 1: first layer of a segment (see conv_chain_kernel)
-  int pad_[12];
 };
 // Role state handed from layer to layer inside a segment.
 struct Ring {
@@ -172,8 +176,7 @@ struct Ring {
   }
 };
 struct ChainRt {
-  const ChainLayer* L;     // current layer
-  int j, n_seg;            // its index inside the segment / layers in the segment
+  int j, n_seg;            // the current layer's index inside its segment / layers in the segment
   uint32_t it_base;        // items this pair has processed in the segment's earlier layers (TMEM stage / parity continuity)
   Ring ra, rb, rt;
   uint32_t k;              // epilogue staging-buffer counter
@@ -735,9 +738,9 @@ __device__ __forceinline__ TileGeo tile_geo(const TcArgs& a, int tt, int g, int 
 template <int ACT, int CG, bool CHAIN = false>
 __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es, const Sched& sc, uint32_t tmem_base,
                                               uint32_t t_full0, uint32_t t_empty0, int warp, int lane,
-                                              ChainRt* cx = nullptr) {
+                                              ChainRt* cx = nullptr, const ChainLayer* L = nullptr) {
   const uint32_t it_base = CHAIN ? cx->it_base : 0u;
-  unsigned* const out_cnt = CHAIN ? cx->L->out_cnt : nullptr;
+  unsigned* const out_cnt = CHAIN ? L->out_cnt : nullptr;
   int r_vlo = 0, r_vhi = -1;
   const int S = a.up;
   const PairId pid = pair_id<CG>();
@@ -772,8 +775,8 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
       const uint32_t tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)((stage * a.MT + mt) * a.Npad);
       float head[4] = {0.f, 0.f, 0.f, 0.f};
       const bool last_tile = (mt == a.MT - 1);
-      if (CHAIN && a.ep.res1 && cx->L->dep_res1.cnt) {       // residual written inside the chain (epi_geo == 0 only)
-        if (lane == 0) dep_wait(cx->L->dep_res1, tg.V0 + quarter * 4, tg.V0 + quarter * 4 + 4, r_vlo, r_vhi, a.err_flag);
+      if (CHAIN && a.ep.res1 && L->dep_res1.cnt) {       // residual written inside the chain (epi_geo == 0 only)
+        if (lane == 0) dep_wait(L->dep_res1, tg.V0 + quarter * 4, tg.V0 + quarter * 4 + 4, r_vlo, r_vhi, a.err_flag);
         __syncwarp();
       }
       if (a.fast) {
@@ -897,12 +900,12 @@ __device__ __forceinline__ void tc_ld32(uint32_t taddr, uint32_t (&r)[32]) {
 // Each epilogue WARP owns 32 TMEM lanes = 4 tile rows x 8 px and stages them in its own 4 KB
 // swizzled buffer(s): no cross-warp synchronisation, one lane issues the warp's TMA traffic.
 template <int ACT, int CG, bool CHAIN = false>
-__device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es, const StageSmem& sg, const Sched& sc,
-                                             uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0,
-                                             int warp, int lane, ChainRt* cx = nullptr) {
+__device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, const EpiSmem& es, const StageSmem& sg,
+                                             const Sched& sc, uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0,
+                                             int warp, int lane, ChainRt* cx = nullptr, const ChainLayer* L = nullptr) {
   const uint32_t it_base = CHAIN ? cx->it_base : 0u;
-  unsigned* const out_cnt = CHAIN ? cx->L->out_cnt : nullptr;
-  unsigned* const out2_cnt = CHAIN ? cx->L->out2_cnt : nullptr;
+  unsigned* const out_cnt = CHAIN ? L->out_cnt : nullptr;
+  unsigned* const out2_cnt = CHAIN ? L->out2_cnt : nullptr;
   int r_vlo = 0, r_vhi = -1;                      // residual producer's row blocks already seen complete (lane 0)
   // Layer chain: the counter of the sub-tile this warp stored last, not yet bumped (lane 0).  Waiting for the bulk
   // stores to COMPLETE right after issuing them would stall the warp for a DRAM / L2 round trip per sub-tile, so
@@ -927,7 +930,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
   const bool reflect = (a.ep.border == SRD_BORDER_REFLECT);
   const bool has_r1 = a.ep.res1 != nullptr;
   // block2 / resampling layers: no vector after the activation
-  const bool has_temb = a.ep.temb != nullptr || (CHAIN && cx->L->temb_off >= 0);
+  const bool has_temb = a.ep.temb != nullptr || (CHAIN && L->temb_off >= 0);
   const bool r1_packed = (a.ep.beta1 == 1.0f), r2_packed = (a.ep.beta2 == 1.0f);
   const uint32_t swz = (uint32_t)(lane & 7);     // == m & 7
   uint8_t* my_row = sg.gen + lane * 128;         // this pixel's 128 B row inside a staging buffer
@@ -950,12 +953,12 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
     const uint32_t bar = sg.r_full0 + 8u * buf;
     if (has_r1) {
       const int Vr = rowblk * TILE_H + a.vstart + g0;
-      if (CHAIN && cx->L->dep_res1.cnt && !dep_cached(cx->L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi)) {
+      if (CHAIN && L->dep_res1.cnt && !dep_cached(L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi)) {
         flush();
-        dep_wait(cx->L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi, a.err_flag);
+        dep_wait(L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi, a.err_flag);
       }
       mbar_expect_tx(bar, 4096u);
-      tma_load_3d(sg.base + buf * 4096u, &a.tmR, bar, j * 64, colblk * TILE_W + 1, Vr);
+      tma_load_3d(sg.base + buf * 4096u, &m_.tmR, bar, j * 64, colblk * TILE_W + 1, Vr);
     } else {
       mbar_arrive(bar);
     }
@@ -1142,7 +1145,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
           const uint32_t src = sg.base + buf * 4096u;
           const int V0 = tg.V0 + g0, xc = tg.x0 + 1;               // this warp's 4 rows
           if (which) {                                             // second output: zero ring, one 4-row box
-            tma_store_3d(&a.tmO2, src, j * 64, xc, V0);
+            tma_store_3d(&m_.tmO2, src, j * 64, xc, V0);
           } else if (a.epi_geo == 0) {
             bool whole = !reflect;
             int yp0 = 0;
@@ -1152,7 +1155,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
               whole = (yp0 >= 3) && (yp0 + 3 <= Ho - 2) && (V0 + 4 <= a.n_vrows);
             }
             if (whole) {
-              tma_store_3d(&a.tmO, src, j * 64, xc, V0);
+              tma_store_3d(&m_.tmO, src, j * 64, xc, V0);
             } else {
               int yp = yp0;
               for (int gg = 0; gg < 4; ++gg, ++yp) {
@@ -1161,9 +1164,9 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
                 if (V >= a.n_vrows) break;
                 if (yp < 1 || yp > Ho) continue;                     // ring row: written by its mirror source
                 const uint32_t rs = src + (uint32_t)gg * 1024u;
-                tma_store_3d(&a.tmOrow, rs, j * 64, xc, V);
-                if (yp == 2) tma_store_3d(&a.tmOrow, rs, j * 64, xc, V - 2);          // oy == 1 -> ring row 0
-                if (yp == Ho - 1) tma_store_3d(&a.tmOrow, rs, j * 64, xc, V + 2);     // oy == H-2 -> ring row H+1
+                tma_store_3d(&m_.tmOrow, rs, j * 64, xc, V);
+                if (yp == 2) tma_store_3d(&m_.tmOrow, rs, j * 64, xc, V - 2);          // oy == 1 -> ring row 0
+                if (yp == Ho - 1) tma_store_3d(&m_.tmOrow, rs, j * 64, xc, V + 2);     // oy == H-2 -> ring row H+1
               }
             }
           } else {
@@ -1175,8 +1178,8 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
             const int bb0 = fdiv(V0, a.fd_period), y0 = V0 - bb0 * a.period - a.voff;
             const int oy0 = y0 * S + pr, oy3 = (y0 + 3) * S + pr;
             if (y0 >= 0 && y0 + 3 < a.H_m && V0 + 3 < a.n_vrows && (!reflect || (oy0 > 1 && oy3 < Ho - 2))) {
-              if (S == 1) tma_store_3d(&a.tmO, src, j * 64, xc, bb0 * (Ho + 2) + oy0 + 1);
-              else tma_store_5d(&a.tmO, src, j * 64, Cc & 1, Cc >> 1, (oy0 + 1) & 1, bb0 * hp2 + ((oy0 + 1) >> 1));
+              if (S == 1) tma_store_3d(&m_.tmO, src, j * 64, xc, bb0 * (Ho + 2) + oy0 + 1);
+              else tma_store_5d(&m_.tmO, src, j * 64, Cc & 1, Cc >> 1, (oy0 + 1) & 1, bb0 * hp2 + ((oy0 + 1) >> 1));
             } else
             for (int gg = 0; gg < 4; ++gg) {
               const int V = V0 + gg;
@@ -1187,8 +1190,8 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const EpiSmem& es,
               const int oy = y * S + pr;
               const uint32_t rs = src + (uint32_t)gg * 1024u;
               auto put = [&](int Rl) {                               // Rl: padded row inside image bb
-                if (S == 1) tma_store_3d(&a.tmOrow, rs, j * 64, xc, bb * (Ho + 2) + Rl);
-                else tma_store_5d(&a.tmOrow, rs, j * 64, Cc & 1, Cc >> 1, Rl & 1, bb * hp2 + (Rl >> 1));
+                if (S == 1) tma_store_3d(&m_.tmOrow, rs, j * 64, xc, bb * (Ho + 2) + Rl);
+                else tma_store_5d(&m_.tmOrow, rs, j * 64, Cc & 1, Cc >> 1, Rl & 1, bb * hp2 + (Rl >> 1));
               };
               put(oy + 1);
               if (reflect) {
@@ -1253,7 +1256,8 @@ struct Bars {
 // Weights have their own producer thread (below): a single in-order thread would park the next
 // activation box behind the weight ring's back-pressure and expose its full HBM latency.
 template <int CG, bool CHAIN = false>
-__device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, uint32_t bar_base, ChainRt* cx = nullptr) {
+__device__ __forceinline__ void producer_role(const TcArgs& a, const TcMaps& m_, uint32_t a_base, uint32_t bar_base,
+                                              ChainRt* cx = nullptr, const ChainLayer* L = nullptr) {
   const Bars bars{bar_base};
   const PairId pid = pair_id<CG>();
   const bool leader = (pid.rank == 0);
@@ -1300,16 +1304,16 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, 
       // the rows this item's boxes cover must have been written by the layers that produce them
 #pragma unroll
       for (int s = 0; s < SRD_MAX_SRC; ++s) {
-        if (s < n_src && cx->L->dep_src[s].cnt) {
+        if (s < n_src && L->dep_src[s].cnt) {
           for (int mt = 0; mt < MT; ++mt) {
-            if (stride == 1) dep_wait(cx->L->dep_src[s], V0[mt] - 1, V0[mt] + TILE_H + 1, d_vlo[s], d_vhi[s], err);
-            else dep_wait(cx->L->dep_src[s], 2 * V0[mt], 2 * V0[mt] + 2 * BOX_ROWS, d_vlo[s], d_vhi[s], err);
+            if (stride == 1) dep_wait(L->dep_src[s], V0[mt] - 1, V0[mt] + TILE_H + 1, d_vlo[s], d_vhi[s], err);
+            else dep_wait(L->dep_src[s], 2 * V0[mt], 2 * V0[mt] + 2 * BOX_ROWS, d_vlo[s], d_vhi[s], err);
           }
         }
       }
     }
     for (int s = 0; s < n_src; ++s) {
-      const CUtensorMap* tm = &a.tmA[s];
+      const CUtensorMap* tm = &m_.tmA[s];
       const int nch = a.nchunk[s];
       for (int ch = 0; ch < nch; ++ch) {
         if (a_mode) {
@@ -1359,7 +1363,7 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, uint32_t a_base, 
 // k-blocks of the item's phase streamed through the weight ring.  Each CTA of a pair holds
 // Npad / CG rows of every k-block; the leader's barriers count the bytes of BOTH CTAs.
 template <int CG, bool CHAIN = false>
-__device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b_base, uint32_t bar_base,
+__device__ __forceinline__ void weight_producer_role(const TcArgs& a, const TcMaps& m_, uint32_t b_base, uint32_t bar_base,
                                                      ChainRt* cx = nullptr) {
   const Bars bars{bar_base};
   const PairId pid = pair_id<CG>();
@@ -1372,7 +1376,7 @@ __device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b
     if (CHAIN && cx->j > 0) mbar_wait(bars.M_done(), (uint32_t)(cx->j - 1) & 1u, err, 12);
     if (leader) mbar_expect_tx(bars.B_res(), (uint32_t)a.kb_total * B_BYTES * CG);
     for (int kb = 0; kb < a.kb_total; ++kb)
-      tma_load_2d<CG>(b_base + (uint32_t)kb * B_BYTES, &a.tmB, bars.B_res(), 0, kb * Npad + b_row0);
+      tma_load_2d<CG>(b_base + (uint32_t)kb * B_BYTES, &m_.tmB, bars.B_res(), 0, kb * Npad + b_row0);
     return;
   }
   const int kb_per_phase = a.kb_per_phase;
@@ -1386,7 +1390,7 @@ __device__ __forceinline__ void weight_producer_role(const TcArgs& a, uint32_t b
     for (int j = 0; j < kb_per_phase; ++j, ++kb) {
       mbar_wait(bars.B_empty(rb.stage), rb.phase ^ 1, err, 2);
       if (leader) mbar_expect_tx(bars.B_full(rb.stage), B_BYTES * CG);
-      tma_load_2d<CG>(b_base + (uint32_t)rb.stage * B_BYTES, &a.tmB, bars.B_full(rb.stage), 0, kb * Npad + b_row0);
+      tma_load_2d<CG>(b_base + (uint32_t)rb.stage * B_BYTES, &m_.tmB, bars.B_full(rb.stage), 0, kb * Npad + b_row0);
       rb.next();
     }
   }
@@ -1565,8 +1569,14 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
   }
 }
 
+struct TcLaunch {
+  TcMaps m;
+  TcArgs a;
+};
 template <int CG>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcArgs a) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_constant__ TcLaunch lp) {
+  const TcArgs& a = lp.a;
+  const TcMaps& m_ = lp.m;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   kern_stamp(a, 0);
   kern_stamp(a, 6, true);
@@ -1605,13 +1615,13 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     for (int s = 0; s < SCHED_SLOTS; ++s) mbar_init(bar_base + SCHED_BAR_OFF + 8u * s, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     for (int s = 0; s < a.n_src; ++s)
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA[s]) : "memory");
-    asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmB) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&m_.tmA[s]) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&m_.tmB) : "memory");
     if (a.epi_tma) {
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmO) : "memory");
-      asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmOrow) : "memory");
-      if (a.ep.res1) asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmR) : "memory");
-      if (a.dual) asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmO2) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&m_.tmO) : "memory");
+      asm volatile("prefetch.tensormap [%0];" ::"l"(&m_.tmOrow) : "memory");
+      if (a.ep.res1) asm volatile("prefetch.tensormap [%0];" ::"l"(&m_.tmR) : "memory");
+      if (a.dual) asm volatile("prefetch.tensormap [%0];" ::"l"(&m_.tmO2) : "memory");
     }
   }
   if (warp == WARP_MMA) {
@@ -1664,9 +1674,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   kern_stamp(a, 2);
 
   if (warp == WARP_TMA) {
-    if (elect_one_sync()) producer_role<CG>(a, a_base, bar_base);
+    if (elect_one_sync()) producer_role<CG>(a, m_, a_base, bar_base);
   } else if (warp == WARP_TMB) {
-    if (elect_one_sync()) weight_producer_role<CG>(a, b_base, bar_base);
+    if (elect_one_sync()) weight_producer_role<CG>(a, m_, b_base, bar_base);
   } else if (warp == WARP_MMA || (SRD_DUAL_ISSUE && warp == WARP_MMA2)) {
     const int issuer = warp - WARP_MMA;
     if ((CG == 1 || cluster_ctarank() == 0) && elect_one_sync()) {
@@ -1705,9 +1715,9 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       sg.gen = smem_raw + (sg.base - smem_u32(smem_raw));
       sg.r_full0 = R_full0 + 8u * (uint32_t)(ew * 2);
       if (a.ep.act == SRD_ACT_MISH)
-        epilogue_tma<SRD_ACT_MISH, CG>(a, es, sg, sc, tmem_base, T_full(0), T_empty(0), warp, lane);
+        epilogue_tma<SRD_ACT_MISH, CG>(a, m_, es, sg, sc, tmem_base, T_full(0), T_empty(0), warp, lane);
       else
-        epilogue_tma<SRD_ACT_NONE, CG>(a, es, sg, sc, tmem_base, T_full(0), T_empty(0), warp, lane);
+        epilogue_tma<SRD_ACT_NONE, CG>(a, m_, es, sg, sc, tmem_base, T_full(0), T_empty(0), warp, lane);
     } else if (a.ep.act == SRD_ACT_MISH)
       epilogue_role<SRD_ACT_MISH, CG>(a, es, sc, tmem_base, T_full(0), T_empty(0), warp, lane);
     else if (a.ep.act == SRD_ACT_LRELU02)
@@ -1738,13 +1748,34 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
 // weights) followed by the per-segment A | B | staging regions of the ordinary plan.
 constexpr int CHAIN_BT_OFF = BAR_BYTES;                        // 2 x (bias[256], temb[256]) floats
 constexpr int CHAIN_BT_BYTES = 2 * 256 * 4;
-constexpr int CHAIN_HEAD_OFF = CHAIN_BT_OFF + 2 * CHAIN_BT_BYTES;   // [4][256] + [4] floats
-constexpr int CHAIN_FIXED_BYTES = 10240;
-static_assert(CHAIN_HEAD_OFF + (4 * 256 + 4) * 4 <= CHAIN_FIXED_BYTES, "chain head does not fit");
-static_assert(CHAIN_FIXED_BYTES <= BAR_BYTES + VEC_BYTES, "chain head larger than the single-layer kernel's tail");
+constexpr int CHAIN_HEAD_OFF = CHAIN_BT_OFF + 2 * CHAIN_BT_BYTES;   // [4][128] + [4] floats (head / lin layers: Npad <= 128)
+constexpr int CHAIN_HEAD_FLOATS = 4 * 128;
+// Shared-memory copies of the CURRENT layer's arguments, one per role (the three single-thread roles and the
+// epilogue warps, which double-buffer theirs like the vectors): the layer list lives in parameter space, where a
+// run-time layer index means register-indexed LDC loads -- cheap once per layer for a copy, far too slow for the role
+// loops, which in the single-layer kernel read their arguments as constant-bank operands.
+constexpr int CHAIN_ARG_SLOT = ((int)sizeof(ChainLayer) + 15) / 16 * 16;
+constexpr int CHAIN_ARG_OFF = (CHAIN_HEAD_OFF + (CHAIN_HEAD_FLOATS + 4) * 4 + 15) / 16 * 16;
+constexpr int CHAIN_ARG_TMA = 0, CHAIN_ARG_TMB = 1, CHAIN_ARG_MMA = 2, CHAIN_ARG_EPI = 3;   // EPI: two slots
+constexpr int CHAIN_FIXED_BYTES = 11264;
+static_assert(CHAIN_ARG_OFF + 5 * CHAIN_ARG_SLOT <= CHAIN_FIXED_BYTES, "chain head does not fit");
+static_assert(CHAIN_FIXED_BYTES <= BAR_BYTES + VEC_BYTES && CHAIN_FIXED_BYTES % 1024 == 0,
+              "chain head larger than the single-layer kernel's tail");
 
 // bias / temb (+ the second output's bias, zero temb) of one layer -> bt[0..511]; head / linear-residual weights ->
 // s_head (only one layer of a segment may use those: see same_segment)
+// All layers' scalar arguments travel as ONE kernel parameter (CUDA 12.1+: up to 32,764 bytes), i.e. in the constant
+// bank, exactly where the single-layer kernel finds its TcArgs: the role loops read them as instruction operands /
+// uniform loads instead of global-memory loads that every asm memory clobber would force to be repeated.
+constexpr int CHAIN_MAX_LAYERS = (32764 - 32) / (int)sizeof(ChainLayer);
+struct ChainParams {
+  const TcMaps* maps;      // [n_layers] in global memory
+  const float* temb_row;
+  int n_layers, pad_;
+  ChainLayer layers[CHAIN_MAX_LAYERS];
+};
+static_assert(sizeof(ChainParams) <= 32764, "chain parameters exceed the kernel parameter space");
+
 __device__ __forceinline__ void chain_stage_vecs(const ChainLayer& L, const float* temb_row, float* bt, float* s_head,
                                                  int tid, int nthr) {
   const TcArgs& a = L.a;
@@ -1767,7 +1798,7 @@ __device__ __forceinline__ void chain_stage_vecs(const ChainLayer& L, const floa
       const int jh = i / Npad, c = i % Npad;
       s_head[i] = (jh < a.ep.planar_c && c < N) ? __ldg(a.head_w + (size_t)jh * N + c) : 0.f;
     }
-    if (tid < 4) s_head[1024 + tid] = (tid < a.ep.planar_c) ? __ldg(a.head_b + tid) : 0.f;
+    if (tid < 4) s_head[CHAIN_HEAD_FLOATS + tid] = (tid < a.ep.planar_c) ? __ldg(a.head_b + tid) : 0.f;
   }
   if (a.lin_w) {
     for (int i = tid; i < 4 * Npad; i += nthr) {
@@ -1777,9 +1808,22 @@ __device__ __forceinline__ void chain_stage_vecs(const ChainLayer& L, const floa
   }
 }
 
+#ifndef SRD_CHAIN_ARGS_SMEM
+#define SRD_CHAIN_ARGS_SMEM 0      // 1: roles read their layer's arguments from shared-memory copies (measured slower)
+#endif
+// word-wise copy of one layer's arguments from parameter space into a role's shared-memory slot
+__device__ __forceinline__ void chain_copy_args(const ChainLayer& src, ChainLayer* dst, int tid, int nthr) {
+  const uint32_t* s = reinterpret_cast<const uint32_t*>(&src);
+  uint32_t* d = reinterpret_cast<uint32_t*>(dst);
+  for (int i = tid; i < (int)(sizeof(ChainLayer) / 4); i += nthr) d[i] = s[i];
+}
+
 template <int CG>
-__global__ void __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const ChainLayer* __restrict__ layers, int n_layers,
-                                                                   const float* __restrict__ temb_row) {
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const __grid_constant__ ChainParams P) {
+  const ChainLayer* const layers = P.layers;
+  const TcMaps* const maps = P.maps;
+  const int n_layers = P.n_layers;
+  const float* const temb_row = P.temb_row;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const gen0 = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -1789,6 +1833,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const ChainLa
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen0 + 8 * (4 * MAX_STAGES + 8));
   float* const bt0 = reinterpret_cast<float*>(gen0 + CHAIN_BT_OFF);
   float* const s_head = reinterpret_cast<float*>(gen0 + CHAIN_HEAD_OFF);
+  auto arg_slot = [&](int i) { return reinterpret_cast<ChainLayer*>(gen0 + CHAIN_ARG_OFF + i * CHAIN_ARG_SLOT); };
   const uint32_t a_base = smem_base + CHAIN_FIXED_BYTES;
 
   if (warp == WARP_MMA) {       // the 512 TMEM columns are allocated once for the whole chain
@@ -1836,6 +1881,8 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const ChainLa
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     chain_stage_vecs(layers[l0], temb_row, bt0, s_head, (int)threadIdx.x, TC_THREADS);
+    if (SRD_CHAIN_ARGS_SMEM && warp >= WARP_EPI0 && warp < WARP_EPI0 + EPI_WARPS)
+      chain_copy_args(layers[l0], arg_slot(CHAIN_ARG_EPI), (int)threadIdx.x - WARP_EPI0 * 32, EPI_WARPS * 32);
     tc_fence_before();
     __syncthreads();
     if (CG == 2) cluster_sync_all();
@@ -1851,28 +1898,54 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const ChainLa
     cx.ra = Ring{0, 0, a0.a_stages}; cx.rb = Ring{0, 0, a0.b_stages}; cx.rt = Ring{0, 0, a0.n_stages};
 
     if (warp == WARP_TMA) {
-      if (elect_one_sync()) {
-        for (int l = l0; l < l1; ++l) {
-          const TcArgs& a = layers[l].a;
-          cx.L = &layers[l]; cx.j = l - l0;
-          for (int s = 0; s < a.n_src; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmA[s]) : "memory");
-          producer_role<CG, true>(a, a_base, bar_base, &cx);
+      for (int l = l0; l < l1; ++l) {
+#if SRD_CHAIN_ARGS_SMEM
+        ChainLayer* const mine = arg_slot(CHAIN_ARG_TMA);
+        __syncwarp();
+        chain_copy_args(layers[l], mine, lane, 32);
+        __syncwarp();
+#else
+        const ChainLayer* const mine = &layers[l];
+#endif
+        if (elect_one_sync()) {
+          const TcArgs& a = mine->a;
+          const TcMaps& m_ = maps[l];
+          cx.j = l - l0;
+          for (int s = 0; s < a.n_src; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&m_.tmA[s]) : "memory");
+          producer_role<CG, true>(a, m_, a_base, bar_base, &cx, mine);
         }
       }
     } else if (warp == WARP_TMB) {
-      if (elect_one_sync()) {
-        for (int l = l0; l < l1; ++l) {
-          const TcArgs& a = layers[l].a;
-          cx.L = &layers[l]; cx.j = l - l0;
-          asm volatile("prefetch.tensormap [%0];" ::"l"(&a.tmB) : "memory");
-          weight_producer_role<CG, true>(a, b_base, bar_base, &cx);
+      for (int l = l0; l < l1; ++l) {
+#if SRD_CHAIN_ARGS_SMEM
+        ChainLayer* const mine = arg_slot(CHAIN_ARG_TMB);
+        __syncwarp();
+        chain_copy_args(layers[l], mine, lane, 32);
+        __syncwarp();
+#else
+        const ChainLayer* const mine = &layers[l];
+#endif
+        if (elect_one_sync()) {
+          const TcArgs& a = mine->a;
+          const TcMaps& m_ = maps[l];
+          cx.j = l - l0;
+          asm volatile("prefetch.tensormap [%0];" ::"l"(&m_.tmB) : "memory");
+          weight_producer_role<CG, true>(a, m_, b_base, bar_base, &cx);
         }
       }
     } else if (warp == WARP_MMA) {
-      if ((CG == 1 || pid.rank == 0) && elect_one_sync()) {
-        for (int l = l0; l < l1; ++l) {
-          const TcArgs& a = layers[l].a;
-          cx.L = &layers[l]; cx.j = l - l0;
+      for (int l = l0; l < l1; ++l) {
+#if SRD_CHAIN_ARGS_SMEM
+        ChainLayer* const mine = arg_slot(CHAIN_ARG_MMA);
+        __syncwarp();
+        chain_copy_args(layers[l], mine, lane, 32);
+        __syncwarp();
+#else
+        const ChainLayer* const mine = &layers[l];
+#endif
+        if ((CG == 1 || pid.rank == 0) && elect_one_sync()) {
+          const TcArgs& a = mine->a;
+          cx.j = l - l0;
           const int taps = a.a_mode ? a.nkx * a.nky : 0;
 #define SRD_MMA_CASE(T, D)                                                                                             \
   do {                                                                                                                 \
@@ -1893,17 +1966,26 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const ChainLa
       const int etid = (int)threadIdx.x - WARP_EPI0 * 32;
       const int ew = warp - WARP_EPI0;
       for (int l = l0; l < l1; ++l) {
-        const TcArgs& a = layers[l].a;
         const int j = l - l0;
-        cx.L = &layers[l]; cx.j = j;
-        // every epilogue warp has left layer l-1: its vector buffer may be refilled, and layer l's (staged while
-        // layer l-1 ran) is visible to all
+#if SRD_CHAIN_ARGS_SMEM
+        const ChainLayer* const Lc = arg_slot(CHAIN_ARG_EPI + (j & 1));
+#else
+        const ChainLayer* const Lc = &layers[l];
+#endif
+        const TcArgs& a = Lc->a;
+        const TcMaps& m_ = maps[l];
+        cx.j = j;
+        // every epilogue warp has left layer l-1: its vector / argument buffers may be refilled, and layer l's
+        // (staged while layer l-1 ran) are visible to all
         asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
-        if (l + 1 < l1) chain_stage_vecs(layers[l + 1], temb_row, bt0 + ((j + 1) & 1) * 512, s_head, etid, EPI_WARPS * 32);
+        if (l + 1 < l1) {
+          chain_stage_vecs(layers[l + 1], temb_row, bt0 + ((j + 1) & 1) * 512, s_head, etid, EPI_WARPS * 32);
+          if (SRD_CHAIN_ARGS_SMEM) chain_copy_args(layers[l + 1], arg_slot(CHAIN_ARG_EPI + ((j + 1) & 1)), etid, EPI_WARPS * 32);
+        }
         EpiSmem es;
         const Sched sc = make_sched<CG>(a, bar_base);
         es.bias = bt0 + (j & 1) * 512; es.temb = es.bias + 256;
-        es.head_w = a.head_w ? s_head : nullptr; es.head_b = s_head + 1024; es.hpart = nullptr;
+        es.head_w = a.head_w ? s_head : nullptr; es.head_b = s_head + CHAIN_HEAD_FLOATS; es.hpart = nullptr;
         es.lin_w = a.lin_w ? s_head : nullptr;
         if (a.epi_tma) {
           StageSmem sg;
@@ -1911,15 +1993,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const ChainLa
           sg.gen = smem_raw + (sg.base - smem_u32(smem_raw));
           sg.r_full0 = bars.R_full0() + 8u * (uint32_t)(ew * 2);
           if (a.ep.act == SRD_ACT_MISH)
-            epilogue_tma<SRD_ACT_MISH, CG, true>(a, es, sg, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx);
+            epilogue_tma<SRD_ACT_MISH, CG, true>(a, m_, es, sg, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, Lc);
           else
-            epilogue_tma<SRD_ACT_NONE, CG, true>(a, es, sg, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx);
+            epilogue_tma<SRD_ACT_NONE, CG, true>(a, m_, es, sg, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, Lc);
         } else if (a.ep.act == SRD_ACT_MISH)
-          epilogue_role<SRD_ACT_MISH, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx);
+          epilogue_role<SRD_ACT_MISH, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, Lc);
         else if (a.ep.act == SRD_ACT_LRELU02)
-          epilogue_role<SRD_ACT_LRELU02, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx);
+          epilogue_role<SRD_ACT_LRELU02, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, Lc);
         else
-          epilogue_role<SRD_ACT_NONE, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx);
+          epilogue_role<SRD_ACT_NONE, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, Lc);
         cx.it_base += (pid.pair < a.n_items) ? (uint32_t)((a.n_items - 1 - pid.pair) / pid.n_pairs + 1) : 0u;
       }
     }
@@ -2010,6 +2092,7 @@ int tc_supported(const SrdConvDesc& d, const char** why) {
 static int tc_set_func_attrs(int dev);
 
 struct TcPlan {
+  TcMaps maps;
   TcArgs args;
   int grid, smem;
   unsigned* counter = nullptr;           // ticket counter of the dynamic item scheduler (device memory)
@@ -2022,7 +2105,9 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   EncodeTiledFn enc = get_encode_fn();
   SRD_CHECK(enc != nullptr, "conv_tc: cuTensorMapEncodeTiled not available (no CUDA driver?)");
   TcArgs& a = plan->args;
+  TcMaps& mp = plan->maps;
   memset(&a, 0, sizeof(a));
+  memset(&mp, 0, sizeof(mp));
   const int Hp = d.H_in + 2, Wp = d.W_in + 2;
   a.n_src = d.n_src;
   a.stride = d.stride; a.nky = d.nky; a.nkx = d.nkx; a.ky0 = d.ky0; a.kx0 = d.kx0; a.up = d.up;
@@ -2186,7 +2271,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
       cuuint64_t strides[2] = {16, (cuuint64_t)Wp * 16};
       cuuint32_t box[3] = {64, (cuuint32_t)HALO_W, BOX_ROWS};
       cuuint32_t es[3] = {1, 1, 1};
-      r = enc(&a.tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)s.ptr, dims, strides, box, es,
+      r = enc(&mp.tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, (void*)s.ptr, dims, strides, box, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else if (d.stride == 1) {
@@ -2194,7 +2279,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
       cuuint64_t strides[2] = {(cuuint64_t)s.ct * 2, (cuuint64_t)Wp * s.ct * 2};
       cuuint32_t box[3] = {64, (cuuint32_t)(a.a_mode ? HALO_W : TILE_W), BOX_ROWS};
       cuuint32_t es[3] = {1, 1, 1};
-      r = enc(&a.tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, es,
+      r = enc(&mp.tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, base, dims, strides, box, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     } else {
@@ -2204,7 +2289,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
                                (cuuint64_t)2 * Wp * s.ct * 2};
       cuuint32_t box[5] = {64, 1, TILE_W, 1, BOX_ROWS};
       cuuint32_t es[5] = {1, 1, 1, 1, 1};
-      r = enc(&a.tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es,
+      r = enc(&mp.tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     }
@@ -2215,7 +2300,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
     cuuint64_t strides[1] = {128};
     cuuint32_t box[2] = {64, (cuuint32_t)(a.Npad / cg)};
     cuuint32_t es[2] = {1, 1};
-    CUresult r = enc(&a.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d.w_tc, dims, strides, box, es,
+    CUresult r = enc(&mp.tmB, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void*)d.w_tc, dims, strides, box, es,
                      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(B) failed with %d", (int)r);
@@ -2247,17 +2332,17 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
                  CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     };
     SRD_CHECK(((uintptr_t)d.out % 16) == 0, "conv_tc: out must be 16-byte aligned");
-    CUresult r = (d.up == 2) ? enc_out5(&a.tmO, d.out, d.out_ct, d.out_coff, 4) : enc_out(&a.tmO, d.out, d.out_ct, d.out_coff, 4);
+    CUresult r = (d.up == 2) ? enc_out5(&mp.tmO, d.out, d.out_ct, d.out_coff, 4) : enc_out(&mp.tmO, d.out, d.out_ct, d.out_coff, 4);
     SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(out) failed with %d", (int)r);
-    r = (d.up == 2) ? enc_out5(&a.tmOrow, d.out, d.out_ct, d.out_coff, 1) : enc_out(&a.tmOrow, d.out, d.out_ct, d.out_coff, 1);
+    r = (d.up == 2) ? enc_out5(&mp.tmOrow, d.out, d.out_ct, d.out_coff, 1) : enc_out(&mp.tmOrow, d.out, d.out_ct, d.out_coff, 1);
     SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(out row) failed with %d", (int)r);
     if (d.res1) {
-      r = enc_out(&a.tmR, d.res1, d.res1_ct, d.res1_coff, 4);
+      r = enc_out(&mp.tmR, d.res1, d.res1_ct, d.res1_coff, 4);
       SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(res1) failed with %d", (int)r);
     }
     if (d.N2) {
       SRD_CHECK(((uintptr_t)d.dst2 % 16) == 0, "conv_tc: dst2 must be 16-byte aligned");
-      r = enc_out(&a.tmO2, d.dst2, d.dst2_ct, d.dst2_coff, 4);
+      r = enc_out(&mp.tmO2, d.dst2, d.dst2_ct, d.dst2_coff, 4);
       SRD_CHECK(r == CUDA_SUCCESS, "conv_tc: cuTensorMapEncodeTiled(dst2) failed with %d", (int)r);
     }
   }
@@ -2282,7 +2367,10 @@ TcPlan* tc_plan_new() { return new (std::nothrow) TcPlan; }
 void tc_plan_delete(TcPlan* p) { delete p; }
 
 int launch_conv_tc(const TcPlan& plan, const float* temb, cudaStream_t stream) {
-  TcArgs a = plan.args;
+  TcLaunch lp;
+  lp.m = plan.maps;
+  lp.a = plan.args;
+  TcArgs& a = lp.a;
   if (temb) a.ep.temb = temb;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)plan.grid);
@@ -2303,19 +2391,20 @@ int launch_conv_tc(const TcPlan& plan, const float* temb, cudaStream_t stream) {
   }
   cfg.attrs = at;
   cfg.numAttrs = (unsigned)n_at;
-  if (a.cg == 1) SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, a));
-  else SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, a));
+  if (a.cg == 1) SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<1>, lp));
+  else SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_tc_kernel<2>, lp));
   return 0;
 }
 
 // ------------------------------------------------------------------------------------------ layer chain: host
 struct TcChain {
-  ChainLayer* d_layers = nullptr;
+  ChainParams params;      // host copy; temb_row is filled in per launch
+  TcMaps* d_maps = nullptr;
   unsigned* d_counters = nullptr;
   size_t counter_bytes = 0;
   int n_layers = 0, n_segments = 0, grid = 0, smem = 0, cg = 2;
   ~TcChain() {
-    if (d_layers) cudaFree(d_layers);
+    if (d_maps) cudaFree(d_maps);
     if (d_counters) cudaFree(d_counters);
   }
 };
@@ -2340,9 +2429,11 @@ struct TcChainLink {
 };
 
 int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, TcChain* chain, int g_single_segments) {
-  SRD_CHECK(n >= 1 && n <= 4096, "conv_chain: bad layer count %d", n);
-  std::vector<ChainLayer> L((size_t)n);
-  memset(L.data(), 0, sizeof(ChainLayer) * (size_t)n);
+  SRD_CHECK(n >= 1 && n <= CHAIN_MAX_LAYERS, "conv_chain: %d layers (at most %d fit the kernel parameter space)", n,
+            CHAIN_MAX_LAYERS);
+  memset(&chain->params, 0, sizeof(chain->params));
+  ChainLayer* L = chain->params.layers;
+  std::vector<TcMaps> maps((size_t)n);
   // counters: one array per (layer, output) that has a reader inside the chain
   std::vector<long long> cnt_off((size_t)n * 2, -1);
   std::vector<int> n_rowblk((size_t)n);
@@ -2356,6 +2447,7 @@ int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, 
     SRD_CHECK(a.cg == cg, "conv_chain: layers disagree on the CTA-pair mode");
     SRD_CHECK(!a.dyn_sched && !a.dbg, "conv_chain: layer %d uses the dynamic scheduler / debug stamps", i);
     SRD_CHECK(a.up == 1 || a.up == 2, "conv_chain: layer %d has up = %d (only 1 and 2 can be chained)", i, a.up);
+    SRD_CHECK(!(a.head_w || a.lin_w) || a.Npad <= 128, "conv_chain: layer %d: fused head / linear residual need N <= 128", i);
     n_rowblk[i] = (a.n_vrows - a.vstart + TILE_H - 1) / TILE_H;
     const int layer_smem = plans[i]->smem - (BAR_BYTES + VEC_BYTES) + CHAIN_FIXED_BYTES;
     if (layer_smem > smem) smem = layer_smem;
@@ -2395,6 +2487,7 @@ int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, 
     const TcArgs& a = plans[i]->args;
     const TcChainLink& k = links[i];
     L[i].a = a;
+    maps[(size_t)i] = plans[i]->maps;
     L[i].temb_off = k.temb_off;
     SRD_CHECK(k.temb_off < 0 || (a.fast && a.ep.temb_bstride == 0), "conv_chain: layer %d cannot take a per-launch temb row", i);
     for (int s = 0; s < a.n_src; ++s)
@@ -2411,8 +2504,10 @@ int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, 
     L[i].seg_first = (i == 0 || g_single_segments || !same_segment(plans[i - 1]->args, a)) ? 1 : 0;
     n_seg += L[i].seg_first;
   }
-  SRD_CUDA(cudaMalloc((void**)&chain->d_layers, sizeof(ChainLayer) * (size_t)n));
-  SRD_CUDA(cudaMemcpy(chain->d_layers, L.data(), sizeof(ChainLayer) * (size_t)n, cudaMemcpyHostToDevice));
+  SRD_CUDA(cudaMalloc((void**)&chain->d_maps, sizeof(TcMaps) * (size_t)n));
+  SRD_CUDA(cudaMemcpy(chain->d_maps, maps.data(), sizeof(TcMaps) * (size_t)n, cudaMemcpyHostToDevice));
+  chain->params.maps = chain->d_maps;
+  chain->params.n_layers = n;
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
@@ -2425,6 +2520,7 @@ int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, 
 TcChain* tc_chain_new() { return new (std::nothrow) TcChain; }
 void tc_chain_delete(TcChain* c) { delete c; }
 int tc_chain_segments(const TcChain* c) { return c->n_segments; }
+int tc_chain_max_layers() { return CHAIN_MAX_LAYERS; }
 
 int launch_chain(const TcChain& c, const float* temb_row, cudaStream_t stream) {
   SRD_CUDA(cudaMemsetAsync(c.d_counters, 0, c.counter_bytes, stream));
@@ -2447,10 +2543,10 @@ int launch_chain(const TcChain& c, const float* temb_row, cudaStream_t stream) {
   }
   cfg.attrs = at;
   cfg.numAttrs = (unsigned)n_at;
-  const ChainLayer* layers = c.d_layers;
-  int n = c.n_layers;
-  if (c.cg == 1) SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel<1>, layers, n, temb_row));
-  else SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel<2>, layers, n, temb_row));
+  ChainParams P = c.params;
+  P.temb_row = temb_row;
+  if (c.cg == 1) SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel<1>, P));
+  else SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel<2>, P));
   return 0;
 }
 

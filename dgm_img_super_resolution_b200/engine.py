@@ -17,9 +17,11 @@ PRECISIONS = ("bf16", "fp32", "bf16_direct")
 FUSE_RES_CONV = os.environ.get("SRD_NO_FUSED_RES") != "1"
 REVERSE_ORDER = os.environ.get("SRD_NO_REVERSE", "0") != "1"   # alternate the tile order of consecutive conv launches
 FOLD_COND = os.environ.get("SRD_NO_FOLD_COND", "0") != "1"     # add cond after the first Downsample (see CondProgram)
-# Unet.forward as ONE persistent launch (srd_chain_*): SRD_CHAIN=0 falls back to one launch per layer,
-# SRD_CHAIN_SINGLE=1 keeps the single launch but drains the CTA pair after every layer (debug)
-USE_CHAIN = os.environ.get("SRD_CHAIN", "1") != "0"
+# Unet.forward as ONE persistent launch (srd_chain_*), opt-in with SRD_CHAIN=1: bit-identical to the per-layer
+# launches but measured SLOWER on B200 (its role loops lose the constant-bank / uniform-datapath operands
+# of the single-layer kernel), so one launch per layer stays the default.  SRD_CHAIN_SINGLE=1 additionally drains the
+# CTA pair after every layer (debug).
+USE_CHAIN = os.environ.get("SRD_CHAIN", "0") == "1"
 CHAIN_SINGLE_SEGMENTS = os.environ.get("SRD_CHAIN_SINGLE", "0") == "1"
 
 
@@ -287,7 +289,7 @@ class ChainOp:
                 return False
             read.update(ins)
             written.update(outs)
-        return len(ops) >= 2
+        return 2 <= len(ops) <= L.lib().srd_chain_max_layers()
 
     def run(self, ctx):
         L.check(L.lib().srd_chain_run(self.handle, C.c_void_p(ctx.temb_ptr) if ctx.temb_ptr else None, _stream()),

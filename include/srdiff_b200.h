@@ -149,6 +149,8 @@ typedef struct {
 int srd_chain_create(SrdConvPlan* const* plans, const SrdChainLink* links, int32_t n, int32_t flags, SrdChain** out);
 int srd_chain_run(const SrdChain* chain, const float* temb_row, void* stream);
 int srd_chain_destroy(SrdChain* chain);
+/* most layers one chain can hold (their scalar arguments travel in the 32 KB kernel parameter space) */
+int srd_chain_max_layers(void);
 /* number of segments (runs of layers the roles cross without a CTA-level drain) the planner found */
 int srd_chain_segments(const SrdChain* chain);
 

@@ -1,7 +1,7 @@
-"""Layer chain (include/srdiff_b200.h: srd_chain_*): the whole Unet.forward as ONE persistent launch whose layers are
-ordered by completion counters instead of kernel boundaries.  It must be bit-identical to the same plans launched one
-by one -- same tiles, same arithmetic -- on every run (a missed dependency shows up as a mismatch or as run-to-run
-differences), at small / ragged shapes and at the bench shape."""
+"""Layer chain (include/srdiff_b200.h: srd_chain_*; opt-in, SRD_CHAIN=1): the whole Unet.forward as ONE persistent
+launch whose layers are ordered by completion counters instead of kernel boundaries.  It must be bit-identical to the
+same plans launched one by one -- same tiles, same arithmetic -- on every run (a missed dependency shows up as a
+mismatch or as run-to-run differences), at small / ragged shapes and at the bench shape."""
 import pytest
 import torch
 
@@ -10,6 +10,14 @@ from dgm_img_super_resolution_b200 import engine as E
 
 DEV = "cuda:0"
 pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _chain_on():
+    old = E.USE_CHAIN
+    E.USE_CHAIN = True
+    yield
+    E.USE_CHAIN = old
 
 
 def _plan(hp, B, h, w, seed, timesteps=4):
