@@ -99,6 +99,8 @@ SYMBOLS = {
     "srd_chain_destroy": (C.c_int, [_vp]),
     "srd_chain_segments": (C.c_int, [_vp]),
     "srd_chain_max_layers": (C.c_int, []),
+    "srd_chain_fused_max_layers": (C.c_int, []),
+    "srd_conv_plans_share_segment": (C.c_int, [_vp, _vp]),
     "srd_tc_set_mode": (C.c_int, [_i32, _i32]),
     "srd_tc_set_debug": (C.c_int, [_vp]),
     "srd_time_table": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),

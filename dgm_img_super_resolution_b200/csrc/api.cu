@@ -37,6 +37,8 @@ void tc_chain_delete(TcChain*);
 int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, TcChain* chain, int single_segments);
 int tc_chain_segments(const TcChain* c);
 int tc_chain_max_layers();
+int tc_same_segment(const TcPlan* x, const TcPlan* y);
+int tc_seg_k();
 int launch_chain(const TcChain& c, const float* temb_row, cudaStream_t stream);
 void tc_set_debug(unsigned long long* p);
 
@@ -193,7 +195,7 @@ int srd_chain_create(SrdConvPlan* const* plans, const SrdChainLink* links, int32
   }
   srd::TcChain* c = tc_chain_new();
   SRD_CHECK(c != nullptr, "srd_chain_create: out of memory");
-  if (tc_chain_build(tcs.data(), reinterpret_cast<const srd::TcChainLink*>(links), n, c, flags & 1)) {
+  if (tc_chain_build(tcs.data(), reinterpret_cast<const srd::TcChainLink*>(links), n, c, flags)) {
     tc_chain_delete(c);
     return 1;
   }
@@ -212,6 +214,13 @@ int srd_chain_destroy(SrdChain* chain) {
 }
 
 int srd_chain_max_layers(void) { return tc_chain_max_layers(); }
+
+int srd_chain_fused_max_layers(void) { return tc_seg_k(); }
+
+int srd_conv_plans_share_segment(const SrdConvPlan* x, const SrdConvPlan* y) {
+  if (!x || !y || x->kernel != SRD_KERNEL_TC || y->kernel != SRD_KERNEL_TC) return 0;
+  return tc_same_segment(x->tc, y->tc);
+}
 
 int srd_chain_segments(const SrdChain* chain) {
   return chain ? tc_chain_segments(reinterpret_cast<const srd::TcChain*>(chain)) : -1;

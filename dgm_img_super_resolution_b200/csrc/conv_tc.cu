@@ -180,6 +180,8 @@ struct ChainRt {
   uint32_t it_base;        // items this pair has processed in the segment's earlier layers (TMEM stage / parity continuity)
   Ring ra, rb, rt;
   uint32_t k;              // epilogue staging-buffer counter
+  uint32_t exp_mult;       // completion counters are compared with expect * exp_mult (1, or launch epoch + 1 when the
+                           // counters are never reset: conv_seg_kernel)
   const float* temb_row;
 };
 
@@ -251,12 +253,12 @@ __device__ __forceinline__ int dep_rowblk(const ChainDep& d, int R) {
 }
 __device__ __noinline__ void dep_poll(const unsigned* p, unsigned expect, int* err_flag) {
   unsigned v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
   if (v >= expect) return;
   const unsigned long long t0 = global_ns();
   for (;;) {
     __nanosleep(40);
-    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
     if (v >= expect) return;
     if (global_ns() - t0 > WATCHDOG_NS) {
       if (err_flag) atomicExch(err_flag, 11);
@@ -269,23 +271,27 @@ __device__ __noinline__ void dep_poll(const unsigned* p, unsigned expect, int* e
 __device__ __forceinline__ bool dep_cached(const ChainDep& d, int Ra, int Rb, int vlo, int vhi) {
   return dep_rowblk(d, Ra - 2) >= vlo && dep_rowblk(d, Rb + 1) <= vhi;
 }
-__device__ __forceinline__ void dep_wait(const ChainDep& d, int Ra, int Rb, int& vlo, int& vhi, int* err_flag) {
+__device__ __forceinline__ void dep_wait(const ChainDep& d, int Ra, int Rb, int& vlo, int& vhi, int* err_flag,
+                                         uint32_t exp_mult) {
   const int lo = dep_rowblk(d, Ra - 2), hi = dep_rowblk(d, Rb + 1);
   if (lo >= vlo && hi <= vhi) return;
   for (int r = lo; r <= hi; ++r)
-    if (r < vlo || r > vhi) dep_poll(d.cnt + r, d.expect, err_flag);
+    if (r < vlo || r > vhi) dep_poll(d.cnt + r, d.expect * exp_mult, err_flag);
   if (vhi >= vlo && lo <= vhi + 1 && hi >= vlo - 1) { vlo = lo < vlo ? lo : vlo; vhi = hi > vhi ? hi : vhi; }
   else { vlo = lo; vhi = hi; }
-  // acquire: the counters were read relaxed; order them before the (async-proxy) loads that follow
-  asm volatile("fence.acq_rel.gpu;" ::: "memory");
+  // the counters were read with acquire loads; the loads that follow belong to the async proxy
   asm volatile("fence.proxy.async;" ::: "memory");
 }
 // One epilogue warp has finished a sub-tile: its bulk stores are COMPLETE (not merely read), the per-thread ring
 // stores of the other lanes are ordered before this by the preceding __syncwarp.  Lane 0 only.
+// The bump itself is a RELAXED reduction: a gpu-scope release would make lane 0 (and with it the warp) wait for a
+// full memory round trip per sub-tile, which the 64-channel layers' epilogue cannot afford.  What it has to be ordered
+// after is (a) the warp's bulk stores -- complete, i.e. performed at the L2, once wait_group returns -- and (b) the
+// few per-thread ring-column stores of edge tiles, whose lanes fence them themselves before the __syncwarp.
 __device__ __forceinline__ void dep_publish(unsigned* cnt) {
   asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
   asm volatile("fence.proxy.async;" ::: "memory");
-  asm volatile("red.release.gpu.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(1u) : "memory");
+  asm volatile("red.relaxed.gpu.global.add.u32 [%0], %1;" ::"l"(cnt), "r"(1u) : "memory");
 }
 
 // In a CTA pair (CG == 2) the shared::cluster address of a CTA-local object carries the CTA rank in
@@ -776,7 +782,7 @@ __device__ __forceinline__ void epilogue_role(const TcArgs& a, const EpiSmem& es
       float head[4] = {0.f, 0.f, 0.f, 0.f};
       const bool last_tile = (mt == a.MT - 1);
       if (CHAIN && a.ep.res1 && L->dep_res1.cnt) {       // residual written inside the chain (epi_geo == 0 only)
-        if (lane == 0) dep_wait(L->dep_res1, tg.V0 + quarter * 4, tg.V0 + quarter * 4 + 4, r_vlo, r_vhi, a.err_flag);
+        if (lane == 0) dep_wait(L->dep_res1, tg.V0 + quarter * 4, tg.V0 + quarter * 4 + 4, r_vlo, r_vhi, a.err_flag, cx->exp_mult);
         __syncwarp();
       }
       if (a.fast) {
@@ -903,9 +909,13 @@ template <int ACT, int CG, bool CHAIN = false>
 __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, const EpiSmem& es, const StageSmem& sg,
                                              const Sched& sc, uint32_t tmem_base, uint32_t t_full0, uint32_t t_empty0,
                                              int warp, int lane, ChainRt* cx = nullptr, const ChainLayer* L = nullptr) {
+#ifndef SRD_CHAIN_EPI_MIN
+#define SRD_CHAIN_EPI_MIN 0       // experiment: chain epilogue without dependency / publishing code (1-layer timing only)
+#endif
+  constexpr bool PUB = CHAIN && !SRD_CHAIN_EPI_MIN;
   const uint32_t it_base = CHAIN ? cx->it_base : 0u;
-  unsigned* const out_cnt = CHAIN ? L->out_cnt : nullptr;
-  unsigned* const out2_cnt = CHAIN ? L->out2_cnt : nullptr;
+  unsigned* const out_cnt = PUB ? L->out_cnt : nullptr;
+  unsigned* const out2_cnt = PUB ? L->out2_cnt : nullptr;
   int r_vlo = 0, r_vhi = -1;                      // residual producer's row blocks already seen complete (lane 0)
   // Layer chain: the counter of the sub-tile this warp stored last, not yet bumped (lane 0).  Waiting for the bulk
   // stores to COMPLETE right after issuing them would stall the warp for a DRAM / L2 round trip per sub-tile, so
@@ -913,7 +923,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
   // ready, a dependency has to be polled) or is about to issue the next store (the old one has long completed).
   // It is always flushed before a wait that another CTA's progress could depend on.
   unsigned* pend = nullptr;
-  auto flush = [&]() { if (CHAIN && pend) { dep_publish(pend); pend = nullptr; } };
+  auto flush = [&]() { if (PUB && pend) { dep_publish(pend); pend = nullptr; } };
   const PairId pid = pair_id<CG>();
   const int S = a.up;
   const int quarter = warp & 3, group = (warp - WARP_EPI0) >> 2;
@@ -953,9 +963,9 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
     const uint32_t bar = sg.r_full0 + 8u * buf;
     if (has_r1) {
       const int Vr = rowblk * TILE_H + a.vstart + g0;
-      if (CHAIN && L->dep_res1.cnt && !dep_cached(L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi)) {
+      if (PUB && L->dep_res1.cnt && !dep_cached(L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi)) {
         flush();
-        dep_wait(L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi, a.err_flag);
+        dep_wait(L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi, a.err_flag, cx->exp_mult);
       }
       mbar_expect_tx(bar, 4096u);
       tma_load_3d(sg.base + buf * 4096u, &m_.tmR, bar, j * 64, colblk * TILE_W + 1, Vr);
@@ -978,7 +988,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
     if (S > 1) { pr = fdiv(phase, a.fd_up); ps = phase - pr * S; }
     const bool stamp = (quarter == 0 && lane == 0);
     if (stamp) epi_stamp(a, it, 0);
-    if (CHAIN) {
+    if (PUB) {
       if (!mbar_try(t_full, round & 1u)) {           // would idle: publish the last sub-tile meanwhile
         if (lane == 0) flush();
         mbar_wait(t_full, round & 1u, a.err_flag, 6);
@@ -1135,6 +1145,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
             if (bot && lef) *(p + (2 * dn - 2 * ct) / 8) = val;
             if (bot && rig) *(p + (2 * dn + 2 * ct) / 8) = val;
           }
+          if (PUB) __threadfence();                              // see dep_publish
         }
         if (stamp && last_sub) epi_stamp(a, it, 3);
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic smem writes -> async proxy
@@ -1205,7 +1216,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
           // the buffer of sub-tile k+1 was last read by the store of sub-tile k+1-nbuf
           if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
-          if (CHAIN) {       // layer chain: the readers of this tensor learn about these rows at the next flush()
+          if (PUB) {         // layer chain: the readers of this tensor learn about these rows at the next flush()
             unsigned* const cnt = which ? out2_cnt : out_cnt;
             if (cnt && (t0 + mt * CG) < a.tiles_per_phase) pend = cnt + ((tg.V0 - a.vstart) >> 4);
           }
@@ -1306,8 +1317,8 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, const TcMaps& m_,
       for (int s = 0; s < SRD_MAX_SRC; ++s) {
         if (s < n_src && L->dep_src[s].cnt) {
           for (int mt = 0; mt < MT; ++mt) {
-            if (stride == 1) dep_wait(L->dep_src[s], V0[mt] - 1, V0[mt] + TILE_H + 1, d_vlo[s], d_vhi[s], err);
-            else dep_wait(L->dep_src[s], 2 * V0[mt], 2 * V0[mt] + 2 * BOX_ROWS, d_vlo[s], d_vhi[s], err);
+            if (stride == 1) dep_wait(L->dep_src[s], V0[mt] - 1, V0[mt] + TILE_H + 1, d_vlo[s], d_vhi[s], err, cx->exp_mult);
+            else dep_wait(L->dep_src[s], 2 * V0[mt], 2 * V0[mt] + 2 * BOX_ROWS, d_vlo[s], d_vhi[s], err, cx->exp_mult);
           }
         }
       }
@@ -1848,6 +1859,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const __grid_
   const PairId pid = pair_id<CG>();
   ChainRt cx;
   cx.temb_row = temb_row;
+  cx.exp_mult = 1u;
   uint32_t tmem_base = 0;
   bool first = true;
   int l0 = 0;
@@ -2017,6 +2029,201 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const __grid_
       asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
     else
       asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+}
+
+// ------------------------------------------------------------------------------------------ fused segment kernel
+// conv_seg_kernel<CG, K>: up to K consecutive layers that share one shared-memory / TMEM / barrier plan (one
+// "segment" of the chain planner) in ONE launch.  Same role code and the same completion-counter protocol as
+// conv_chain_kernel, but the layer loop is unrolled at compile time, so every layer's arguments sit at a fixed offset
+// of the kernel parameter block: the role loops keep their constant-bank operands and uniform-datapath control flow
+// (what the run-time-indexed chain kernel loses).  The counters are never reset: a device-side launch epoch scales the
+// expected values instead, so no memset node sits in front of the launch and programmatic dependent launch still
+// overlaps its prologue with the previous layer's tail.
+constexpr unsigned SEG_EPOCH_MAX = 1u << 20;
+#ifndef SRD_SEG_K
+#define SRD_SEG_K 3
+#endif
+constexpr int SEG_K = SRD_SEG_K;       // layers one fused-segment launch can hold (the role code is instantiated K times)
+template <int K>
+struct SegParams {
+  const TcMaps* maps;      // [n] in global memory
+  const float* temb_row;
+  unsigned* epoch;         // completed launches of this segment since the counters were last zeroed
+  unsigned* done;          // CTAs that have finished the current launch
+  unsigned* counters;
+  int n_counters, n;
+  ChainLayer layers[K];
+};
+
+template <int CG, int K>
+__global__ void __launch_bounds__(TC_THREADS, 1) conv_seg_kernel(const __grid_constant__ SegParams<K> P) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  uint8_t* const gen0 = smem_raw + (smem_base - smem_u32(smem_raw));
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t bar_base = smem_base;
+  const Bars bars{bar_base};
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen0 + 8 * (4 * MAX_STAGES + 8));
+  float* const bt0 = reinterpret_cast<float*>(gen0 + CHAIN_BT_OFF);
+  float* const s_head = reinterpret_cast<float*>(gen0 + CHAIN_HEAD_OFF);
+  const TcArgs& a0 = P.layers[0].a;
+  const uint32_t a_base = smem_base + CHAIN_FIXED_BYTES;
+  const uint32_t b_base = a_base + (uint32_t)a0.a_stages * a0.MT * a0.a_stage_bytes;
+  const uint32_t stg_base = b_base + (uint32_t)a0.b_region_bytes;
+  const int n = P.n;
+
+  if (warp == WARP_TMA && lane == 0) {
+    for (int s = 0; s < a0.a_stages; ++s) { mbar_init(bars.A_full(s), 1); mbar_init(bars.A_empty(s), 1); }
+    for (int s = 0; s < a0.b_stages; ++s) { mbar_init(bars.B_full(s), 1); mbar_init(bars.B_empty(s), 1); }
+    for (int s = 0; s < 4; ++s) { mbar_init(bars.T_full(s), 1); mbar_init(bars.T_empty(s), (uint32_t)(4 * a0.n_share * CG)); }
+    mbar_init(bars.B_res(), 1);
+    mbar_init(bars.M_done(), 1);
+    for (int s = 0; s < 2 * EPI_WARPS; ++s) mbar_init(bars.R_full0() + 8u * s, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (j < n) {
+        for (int s = 0; s < P.layers[j].a.n_src; ++s) asm volatile("prefetch.tensormap [%0];" ::"l"(&P.maps[j].tmA[s]) : "memory");
+        asm volatile("prefetch.tensormap [%0];" ::"l"(&P.maps[j].tmB) : "memory");
+      }
+    }
+  }
+  if (warp == WARP_MMA) {
+    if (CG == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars.tmem_slot()), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(bars.tmem_slot()), "r"(512u) : "memory");
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+  }
+  // the vectors of layer 0; the per-launch time-embedding row is a kernel parameter (launch constant)
+  chain_stage_vecs(P.layers[0], P.temb_row, bt0, s_head, (int)threadIdx.x, TC_THREADS);
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+  if (warp != WARP_TMB) asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  const PairId pid = pair_id<CG>();
+  ChainRt cx;
+  cx.temb_row = P.temb_row;
+  cx.it_base = 0; cx.k = 0; cx.n_seg = n; cx.j = 0;
+  cx.ra = Ring{0, 0, a0.a_stages}; cx.rb = Ring{0, 0, a0.b_stages}; cx.rt = Ring{0, 0, a0.n_stages};
+  unsigned ep = 0;
+  if (warp != WARP_TMB) {          // (the previous launch of this segment finished at least one kernel boundary ago)
+    asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(ep) : "l"(P.epoch) : "memory");
+  }
+  cx.exp_mult = ep + 1u;
+
+  if (warp == WARP_TMA) {
+    if (elect_one_sync()) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (j < n) {
+          cx.j = j;
+          producer_role<CG, true>(P.layers[j].a, P.maps[j], a_base, bar_base, &cx, &P.layers[j]);
+        }
+      }
+    }
+  } else if (warp == WARP_TMB) {
+    if (elect_one_sync()) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (j < n) {
+          cx.j = j;
+          weight_producer_role<CG, true>(P.layers[j].a, P.maps[j], b_base, bar_base, &cx);
+        }
+      }
+    }
+  } else if (warp == WARP_MMA) {
+    if ((CG == 1 || pid.rank == 0) && elect_one_sync()) {
+#pragma unroll
+      for (int j = 0; j < K; ++j) {
+        if (j < n) {
+          const TcArgs& a = P.layers[j].a;
+          cx.j = j;
+          const int taps = a.a_mode ? a.nkx * a.nky : 0;
+#define SRD_MMA_CASE(T, D)                                                                                             \
+  do {                                                                                                                 \
+    if (a.b_resident && a.MT == 2) mma_role<T, 2, true, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);  \
+    else if (a.b_resident) mma_role<T, 1, true, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);          \
+    else if (a.MT == 2) mma_role<T, 2, false, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);            \
+    else mma_role<T, 1, false, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);                           \
+  } while (0)
+          if (a.dual) SRD_MMA_CASE(9, true);
+          else if (taps == 9 && a.nkx == 3) SRD_MMA_CASE(9, false);
+          else if (taps == 4 && a.nkx == 2) SRD_MMA_CASE(4, false);
+          else if (taps == 1) SRD_MMA_CASE(1, false);
+          else SRD_MMA_CASE(0, false);
+#undef SRD_MMA_CASE
+        }
+      }
+    }
+  } else if (warp >= WARP_EPI0 && warp < WARP_EPI0 + EPI_WARPS) {
+    const int etid = (int)threadIdx.x - WARP_EPI0 * 32;
+    const int ew = warp - WARP_EPI0;
+#pragma unroll
+    for (int j = 0; j < K; ++j) {
+      if (j < n) {
+        const TcArgs& a = P.layers[j].a;
+        const TcMaps& m_ = P.maps[j];
+        cx.j = j;
+        asm volatile("bar.sync 1, %0;" ::"r"(EPI_WARPS * 32) : "memory");
+        if (j + 1 < K && j + 1 < n)
+          chain_stage_vecs(P.layers[j + 1 < K ? j + 1 : j], P.temb_row, bt0 + ((j + 1) & 1) * 512, s_head, etid, EPI_WARPS * 32);
+        EpiSmem es;
+        const Sched sc = make_sched<CG>(a, bar_base);
+        es.bias = bt0 + (j & 1) * 512; es.temb = es.bias + 256;
+        es.head_w = a.head_w ? s_head : nullptr; es.head_b = s_head + CHAIN_HEAD_FLOATS; es.hpart = nullptr;
+        es.lin_w = a.lin_w ? s_head : nullptr;
+        if (a.epi_tma) {
+          StageSmem sg;
+          sg.base = stg_base + (uint32_t)(ew * a.epi_nbuf) * 4096u;
+          sg.gen = smem_raw + (sg.base - smem_u32(smem_raw));
+          sg.r_full0 = bars.R_full0() + 8u * (uint32_t)(ew * 2);
+          if (a.ep.act == SRD_ACT_MISH)
+            epilogue_tma<SRD_ACT_MISH, CG, true>(a, m_, es, sg, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
+          else
+            epilogue_tma<SRD_ACT_NONE, CG, true>(a, m_, es, sg, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
+        } else if (a.ep.act == SRD_ACT_MISH)
+          epilogue_role<SRD_ACT_MISH, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
+        else if (a.ep.act == SRD_ACT_LRELU02)
+          epilogue_role<SRD_ACT_LRELU02, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
+        else
+          epilogue_role<SRD_ACT_NONE, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
+        cx.it_base += (pid.pair < a.n_items) ? (uint32_t)((a.n_items - 1 - pid.pair) / pid.n_pairs + 1) : 0u;
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (CG == 2) cluster_sync_all();
+  if (warp == WARP_MMA) {
+    tc_fence_after();
+    if (CG == 1)
+      asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+    else
+      asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512u) : "memory");
+  }
+  // launch epoch: the CTA that finishes last advances it (every CTA has read it by then); long before the 32-bit
+  // counters could wrap it zeroes them and starts over
+  if (threadIdx.x == 0) {
+    __threadfence();
+    const unsigned t = atomicAdd(P.done, 1u);
+    if (t == gridDim.x - 1) {
+      *P.done = 0u;
+      if (ep + 1u >= SEG_EPOCH_MAX) {
+        for (int i = 0; i < P.n_counters; ++i) P.counters[i] = 0u;
+        *P.epoch = 0u;
+      } else {
+        *P.epoch = ep + 1u;
+      }
+      __threadfence();
+    }
   }
 }
 
@@ -2357,7 +2564,9 @@ static int tc_set_func_attrs(int dev) {
   if (cudaFuncSetAttribute(conv_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(conv_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
       cudaFuncSetAttribute(conv_chain_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
-      cudaFuncSetAttribute(conv_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      cudaFuncSetAttribute(conv_chain_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(conv_seg_kernel<1, SEG_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess ||
+      cudaFuncSetAttribute(conv_seg_kernel<2, SEG_K>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
     return 1;
   done[dev] = true;
   return 0;
@@ -2399,9 +2608,11 @@ int launch_conv_tc(const TcPlan& plan, const float* temb, cudaStream_t stream) {
 // ------------------------------------------------------------------------------------------ layer chain: host
 struct TcChain {
   ChainParams params;      // host copy; temb_row is filled in per launch
+  int fused = 0;           // 1: conv_seg_kernel (<= SEG_K layers of one segment, epoch-scaled counters, no memset)
   TcMaps* d_maps = nullptr;
-  unsigned* d_counters = nullptr;
+  unsigned* d_counters = nullptr;  // counters, then (fused) the epoch and done words
   size_t counter_bytes = 0;
+  long long n_counters = 0;
   int n_layers = 0, n_segments = 0, grid = 0, smem = 0, cg = 2;
   ~TcChain() {
     if (d_maps) cudaFree(d_maps);
@@ -2428,9 +2639,12 @@ struct TcChainLink {
   int temb_off;
 };
 
-int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, TcChain* chain, int g_single_segments) {
+int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, TcChain* chain, int flags) {
+  const int g_single_segments = flags & 1;
+  chain->fused = (flags & 2) ? 1 : 0;
   SRD_CHECK(n >= 1 && n <= CHAIN_MAX_LAYERS, "conv_chain: %d layers (at most %d fit the kernel parameter space)", n,
             CHAIN_MAX_LAYERS);
+  SRD_CHECK(!chain->fused || n <= SEG_K, "conv_chain: a fused segment holds at most %d layers (got %d)", SEG_K, n);
   memset(&chain->params, 0, sizeof(chain->params));
   ChainLayer* L = chain->params.layers;
   std::vector<TcMaps> maps((size_t)n);
@@ -2466,7 +2680,9 @@ int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, 
     }
   }
   if (total == 0) total = 1;
-  SRD_CUDA(cudaMalloc((void**)&chain->d_counters, (size_t)total * sizeof(unsigned)));
+  chain->n_counters = total;
+  SRD_CUDA(cudaMalloc((void**)&chain->d_counters, (size_t)(total + 2) * sizeof(unsigned)));
+  SRD_CUDA(cudaMemset(chain->d_counters, 0, (size_t)(total + 2) * sizeof(unsigned)));
   chain->counter_bytes = (size_t)total * sizeof(unsigned);
   auto make_dep = [&](int p, int which, ChainDep* d) {
     const TcArgs& pa = plans[p]->args;
@@ -2502,6 +2718,7 @@ int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, 
       L[i].out2_cnt = chain->d_counters + cnt_off[(size_t)i * 2 + 1];
     }
     L[i].seg_first = (i == 0 || g_single_segments || !same_segment(plans[i - 1]->args, a)) ? 1 : 0;
+    SRD_CHECK(!chain->fused || i == 0 || !L[i].seg_first, "conv_chain: layer %d does not share the segment plan of layer 0", i);
     n_seg += L[i].seg_first;
   }
   SRD_CUDA(cudaMalloc((void**)&chain->d_maps, sizeof(TcMaps) * (size_t)n));
@@ -2522,8 +2739,11 @@ void tc_chain_delete(TcChain* c) { delete c; }
 int tc_chain_segments(const TcChain* c) { return c->n_segments; }
 int tc_chain_max_layers() { return CHAIN_MAX_LAYERS; }
 
+int tc_same_segment(const TcPlan* x, const TcPlan* y) { return same_segment(x->args, y->args) ? 1 : 0; }
+int tc_seg_k() { return SEG_K; }
+
 int launch_chain(const TcChain& c, const float* temb_row, cudaStream_t stream) {
-  SRD_CUDA(cudaMemsetAsync(c.d_counters, 0, c.counter_bytes, stream));
+  if (!c.fused) SRD_CUDA(cudaMemsetAsync(c.d_counters, 0, c.counter_bytes, stream));
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)c.grid);
   cfg.blockDim = dim3(TC_THREADS);
@@ -2543,6 +2763,18 @@ int launch_chain(const TcChain& c, const float* temb_row, cudaStream_t stream) {
   }
   cfg.attrs = at;
   cfg.numAttrs = (unsigned)n_at;
+  if (c.fused) {
+    SegParams<SEG_K> S;
+    memset(&S, 0, sizeof(S));
+    S.maps = c.d_maps; S.temb_row = temb_row;
+    S.counters = c.d_counters; S.n_counters = (int)c.n_counters;
+    S.epoch = c.d_counters + c.n_counters; S.done = c.d_counters + c.n_counters + 1;
+    S.n = c.n_layers;
+    for (int i = 0; i < c.n_layers; ++i) S.layers[i] = c.params.layers[i];
+    if (c.cg == 1) SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_seg_kernel<1, SEG_K>, S));
+    else SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_seg_kernel<2, SEG_K>, S));
+    return 0;
+  }
   ChainParams P = c.params;
   P.temb_row = temb_row;
   if (c.cg == 1) SRD_CUDA(cudaLaunchKernelEx(&cfg, conv_chain_kernel<1>, P));

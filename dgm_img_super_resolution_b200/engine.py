@@ -22,6 +22,12 @@ FOLD_COND = os.environ.get("SRD_NO_FOLD_COND", "0") != "1"     # add cond after 
 # of the single-layer kernel), so one launch per layer stays the default.  SRD_CHAIN_SINGLE=1 additionally drains the
 # CTA pair after every layer (debug).
 USE_CHAIN = os.environ.get("SRD_CHAIN", "0") == "1"
+# Runs of consecutive layers with the same kernel plan (ResnetBlock pairs, the 20x20 level ...) as ONE fused-segment
+# launch each (srd_chain_create flags bit 1: compile-time unrolled layer loop, constant-bank arguments kept), opt-in
+# with SRD_FUSE=1: bit-identical, 42 -> 27 launches per pass, but each fused layer runs 5-20 % slower than its own
+# launch (the dependency / publishing state costs the register-capped epilogue its software pipelining), which is more
+# than the ~7 us per saved launch boundary -- measured 3.08 vs 2.83 ms per pass.
+FUSE_SEGMENTS = os.environ.get("SRD_FUSE", "0") == "1"
 CHAIN_SINGLE_SEGMENTS = os.environ.get("SRD_CHAIN_SINGLE", "0") == "1"
 
 
@@ -232,6 +238,13 @@ class ConvOp:
             temb = C.c_void_p(ctx.temb_ptr + 4 * self.temb_off)
         L.check(L.lib().srd_conv_run(self.handle, temb, _stream()), "srd_conv_run")
 
+    def rebuild(self):
+        """Re-plan after a change of the descriptor (e.g. the tile order)."""
+        h = C.c_void_p()
+        L.check(L.lib().srd_conv_plan_create(C.byref(self.desc), C.byref(h)), "srd_conv_plan_create")
+        L.lib().srd_conv_plan_destroy(self.handle)
+        self.handle = h
+
     def __del__(self):
         try:
             if self.handle:
@@ -245,8 +258,9 @@ class ChainOp:
     """A run of tcgen05 conv launches executed as ONE persistent kernel (include/srdiff_b200.h: srd_chain_*).
     Dependencies between the layers are derived from the activation buffers they read and write."""
 
-    def __init__(self, ops):
+    def __init__(self, ops, fused=False):
         self.ops = ops
+        self.fused = fused
         n = len(ops)
         writer = {}                                    # id(Act) -> (layer, which output)
         links = (L.SrdChainLink * n)()
@@ -264,8 +278,8 @@ class ChainOp:
         self.links = links
         handles = (C.c_void_p * n)(*[op.handle for op in ops])
         h = C.c_void_p()
-        L.check(L.lib().srd_chain_create(handles, links, n, 1 if CHAIN_SINGLE_SEGMENTS else 0, C.byref(h)),
-                "srd_chain_create")
+        flags = 2 if fused else (1 if CHAIN_SINGLE_SEGMENTS else 0)
+        L.check(L.lib().srd_chain_create(handles, links, n, flags, C.byref(h)), "srd_chain_create")
         self.handle = h
         self.n_segments = L.lib().srd_chain_segments(h)
 
@@ -326,6 +340,7 @@ class Builder:
         self.device = device
         self.prec = precision if isinstance(precision, Precision) else Precision(precision)
         self.ops = []
+        self.exec = None        # launch list after fuse_segments(): ConvOps and fused ChainOps
         self.chain = None       # ChainOp over all of `ops` (make_chain)
         self.chain_error = None
         self._dir = {}          # id(Act) -> 1 if its last writer walked the tiles in reverse order
@@ -339,8 +354,58 @@ class Builder:
         if self.chain is not None:
             self.chain.run(ctx)
             return
-        for op in self.ops:
+        for op in (self.exec if self.exec is not None else self.ops):
             op.run(ctx)
+
+    def fuse_segments(self):
+        """Group runs of consecutive tcgen05 layers that share one kernel plan into fused-segment launches of at most
+        srd_chain_fused_max_layers() layers (`self.exec` = what run() launches).  Inside a group every layer walks its
+        tiles in the direction of the group's first layer: a consumer then needs the row blocks its producer finished
+        FIRST, so it never waits for the producer's tail (across launches the serpentine order stays)."""
+        self.exec = None
+        if not FUSE_SEGMENTS or self.prec.name != "bf16":
+            return
+        lib, K = L.lib(), L.lib().srd_chain_fused_max_layers()
+        ops, runs, cur = self.ops, [], []
+
+        def plain(op):
+            return (isinstance(op, ConvOp) and op.kernel == L.KERNEL_TC and op.desc.temb_bstride == 0 and
+                    op.io.get("out2") is None and op.desc.up in (1, 2))
+        for op in ops:
+            if cur and plain(op) and lib.srd_conv_plans_share_segment(cur[-1].handle, op.handle) and \
+                    ChainOp.chainable(cur + [op]):
+                cur.append(op)
+            else:
+                if cur:
+                    runs.append(cur)
+                cur = [op] if plain(op) else []
+                if not plain(op):
+                    runs.append([op])
+        if cur:
+            runs.append(cur)
+        groups = []
+        for r in runs:
+            m = _ceil(len(r), K)
+            base, rem, pos = len(r) // m, len(r) % m, 0
+            for g in range(m):                       # balanced split: 4 -> 2 + 2, not 3 + 1
+                size = base + (1 if g < rem else 0)
+                groups.append(r[pos:pos + size])
+                pos += size
+        # tile-order pass (see above), re-planning the layers whose direction changes
+        if REVERSE_ORDER:
+            dirs = {}
+            for g in groups:
+                for i, op in enumerate(g):
+                    if not isinstance(op, ConvOp) or op.kernel != L.KERNEL_TC:
+                        continue
+                    d = (1 - dirs.get(id(op.io["srcs"][0]), 0)) if i == 0 else g[0].desc.reverse_items
+                    if d != op.desc.reverse_items:
+                        op.desc.reverse_items = d
+                        op.rebuild()
+                    for key in ("out", "out2", "dst2"):
+                        if op.io.get(key) is not None:
+                            dirs[id(op.io[key])] = d
+        self.exec = [ChainOp(g, fused=True) if len(g) > 1 else g[0] for g in groups]
 
     def make_chain(self):
         """Fuse the whole launch list into one persistent launch when every op qualifies (ChainOp.chainable)."""
@@ -354,7 +419,9 @@ class Builder:
     def count_kernels(self):
         """(launches per run, tcgen05 conv layers among the ops)"""
         n_tc = sum(1 for o in self.ops if isinstance(o, ConvOp) and o.kernel == L.KERNEL_TC)
-        return (1 if self.chain is not None else len(self.ops)), n_tc
+        if self.chain is not None:
+            return 2, n_tc                      # counter memset + the chain kernel
+        return len(self.exec if self.exec is not None else self.ops), n_tc
 
     # ---- generic conv ----------------------------------------------------------------------
     def conv(self, pw, srcs, out=None, out_coff=0, out2=None, out2_coff=0, act=L.ACT_NONE, alpha=1.0,
@@ -722,6 +789,8 @@ class UnetProgram:
             bld.conv(_pc(fc1), [(f, 0, xd_)], planar=self.eps, planar_c=od)
         if not per_sample_temb:
             bld.make_chain()
+            if bld.chain is None:
+                bld.fuse_segments()
 
     def run(self, temb_ptr):
         self.bld.run(RunCtx(temb_ptr))

@@ -139,7 +139,12 @@ int srd_conv_run(const SrdConvPlan* plan, const float* temb, void* stream);
  * output dst2); res2, lin_src, temb and the weights must not be produced inside the chain.  temb_off >= 0: the
  * layer's time-embedding vector is temb_row + temb_off of the per-launch row handed to srd_chain_run (replaces the
  * per-launch `temb` of srd_conv_run).  flags bit 0: every layer its own segment (debug).  The buffers must all be
- * distinct (no in-place layers). */
+ * distinct (no in-place layers).
+ * flags bit 1: FUSED SEGMENT -- at most srd_chain_fused_max_layers() layers that all share one segment plan
+ * (srd_conv_plans_share_segment): the layer loop is unrolled at compile time so every layer's arguments stay
+ * constant-bank operands (as fast per item as the single-layer kernel), the counters are scaled by a device-side
+ * launch epoch instead of being cleared, and programmatic dependent launch is kept.  This is the mode the engine
+ * uses for runs of same-shaped layers (ResnetBlock pairs, the 20x20 level). */
 typedef struct SrdChain SrdChain;
 typedef struct {
   int32_t src_layer[SRD_MAX_SRC], src_which[SRD_MAX_SRC];
@@ -149,6 +154,9 @@ typedef struct {
 int srd_chain_create(SrdConvPlan* const* plans, const SrdChainLink* links, int32_t n, int32_t flags, SrdChain** out);
 int srd_chain_run(const SrdChain* chain, const float* temb_row, void* stream);
 int srd_chain_destroy(SrdChain* chain);
+int srd_chain_fused_max_layers(void);
+/* 1 if two tcgen05 plans have the same shared-memory / TMEM / barrier plan, i.e. may sit in one segment */
+int srd_conv_plans_share_segment(const SrdConvPlan* x, const SrdConvPlan* y);
 /* most layers one chain can hold (their scalar arguments travel in the 32 KB kernel parameter space) */
 int srd_chain_max_layers(void);
 /* number of segments (runs of layers the roles cross without a CTA-level drain) the planner found */

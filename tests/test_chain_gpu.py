@@ -1,4 +1,4 @@
-"""Layer chain (include/srdiff_b200.h: srd_chain_*; opt-in, SRD_CHAIN=1): the whole Unet.forward as ONE persistent
+"""Layer chain and fused segments (include/srdiff_b200.h: srd_chain_*; both opt-in, SRD_CHAIN=1 / SRD_FUSE=1): the whole Unet.forward as ONE persistent
 launch whose layers are ordered by completion counters instead of kernel boundaries.  It must be bit-identical to the
 same plans launched one by one -- same tiles, same arithmetic -- on every run (a missed dependency shows up as a
 mismatch or as run-to-run differences), at small / ragged shapes and at the bench shape."""
@@ -100,3 +100,42 @@ def test_chain_inside_the_sampler_graph(hp):
         assert torch.equal(a, b)
     finally:
         M.runtime.noise, M.runtime.seed_override = "torch", None
+
+
+# ------------------------------------------------------------------------------------------ fused segments (default)
+def _run_exec(plan, t, fused):
+    bld = plan.unet_prog.bld
+    saved = bld.exec
+    if not fused:
+        bld.exec = None
+    try:
+        plan.unet_prog.eps.fill_(float("nan"))
+        plan.unet_prog.run(plan.temb.data_ptr() + 4 * t * plan.temb.shape[1])
+        torch.cuda.synchronize()
+        return plan.unet_prog.eps.clone()
+    finally:
+        bld.exec = saved
+
+
+@pytest.mark.parametrize("B,h,w", [(2, 8, 8), (3, 6, 10), (5, 16, 12), (64, 40, 40)])
+def test_fused_segments_equal_layer_by_layer(hp, B, h, w):
+    """The engine's default: runs of same-plan layers as fused-segment launches (compile-time unrolled layer loop,
+    epoch-scaled completion counters that are never cleared).  Bit-identical to one launch per layer, on every one of
+    several consecutive launches (each advances the device-side epoch), also at the bench shape."""
+    E.USE_CHAIN = False
+    old_fuse, E.FUSE_SEGMENTS = E.FUSE_SEGMENTS, True
+    try:
+        M, diff, plan = _plan(hp, B, h, w, 51, timesteps=100 if B == 64 else 4)
+    finally:
+        E.FUSE_SEGMENTS = old_fuse
+    bld = plan.unet_prog.bld
+    assert bld.chain is None and bld.exec is not None
+    fused = [op for op in bld.exec if isinstance(op, E.ChainOp)]
+    assert fused and all(op.fused and 2 <= len(op.ops) <= 3 for op in fused)
+    assert sum(len(op.ops) if isinstance(op, E.ChainOp) else 1 for op in bld.exec) == len(bld.ops)
+    ref = _run_exec(plan, 2, fused=False)
+    assert torch.isfinite(ref).all()
+    for _ in range(4):
+        assert torch.equal(_run_exec(plan, 2, fused=True), ref)
+    if B == 64:
+        assert len(bld.exec) <= 28, len(bld.exec)          # 42 layers -> 27 launches

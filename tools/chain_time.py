@@ -47,6 +47,35 @@ def run_ops(lo, hi):
     for op in ops[lo:hi]:
         op.run(ctx)
 
+if specs and specs[0] == "one":
+    for i in [int(v) for v in specs[1:]] or [2, 6, 12, 18, 37]:
+        op = ops[i]
+        c1 = E.ChainOp([op], fused=True)
+        ta = timed(lambda: op.run(ctx), reps=5)
+        tb = timed(lambda: c1.run(ctx), reps=5)
+        print("%2d %-24s plain %7.1f us | 1-layer fused segment %7.1f us (%+.1f)" % (i, name(op), ta, tb, tb - ta), flush=True)
+    sys.exit(0)
+if specs and specs[0] == "fused":
+    # per fused group of the engine's default grouping: its launches one by one vs the fused-segment launch
+    bld = plan.unet_prog.bld
+    bld.fuse_segments()
+    pos = 0
+    for op in bld.exec:
+        if isinstance(op, E.ChainOp):
+            n = len(op.ops)
+            ta = timed(lambda: [o.run(ctx) for o in op.ops], reps=3)
+            tb = timed(lambda: op.run(ctx), reps=3)
+            one = []
+            if len(specs) > 1:
+                for o in op.ops[:1]:
+                    c1 = E.ChainOp([o], fused=True)
+                    one.append(("plain %.1f" % timed(lambda: o.run(ctx), reps=5), "fused-1 %.1f" % timed(lambda: c1.run(ctx), reps=5)))
+            print("ops[%d:%d] %-22s x%d: launches %.1f us | fused %.1f us (%+.1f) dir=%s %s" % (
+                pos, pos + n, name(op.ops[0]), n, ta, tb, tb - ta, [o.desc.reverse_items for o in op.ops], one), flush=True)
+            pos += n
+        else:
+            pos += 1
+    sys.exit(0)
 if not specs:
     tot_a = tot_b = 0.0
     for i, op in enumerate(ops):

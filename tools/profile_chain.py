@@ -24,13 +24,19 @@ plan.encode(); plan.load_x()
 ops = plan.unet_prog.bld.ops
 ctx = E.RunCtx(plan.temb.data_ptr())
 plan.unet_prog.bld.run(ctx); torch.cuda.synchronize()
-torch.cuda.profiler.start()
-if mode == "chain":
+if mode == "fused":
+    ch = E.ChainOp(ops[Li:Li + 1], fused=True)
+    torch.cuda.profiler.start()
+    for _ in range(reps):
+        ch.run(ctx)
+elif mode == "chain":
+    torch.cuda.profiler.start()
     lo, hi = (Li, Li + 1) if len(sys.argv) <= 4 else (Li, int(sys.argv[4]))
     ch = E.ChainOp(ops[lo:hi])
     for _ in range(reps):
         ch.run(ctx)
 else:
+    torch.cuda.profiler.start()
     for _ in range(reps):
         ops[Li].run(ctx)
 torch.cuda.synchronize()
