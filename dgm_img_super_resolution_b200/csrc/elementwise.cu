@@ -33,7 +33,8 @@ __device__ __forceinline__ void normal4(uint64_t seed, uint32_t quad, uint32_t i
   for (int i = 0; i < 2; ++i) {
     const float u1 = ((float)r[2 * i] + 1.0f) * k;        // (0, 1]
     const float u2 = (float)r[2 * i + 1] * k;             // [0, 1]
-    const float rad = sqrtf(-1.3862943611198906f * __log2f(fminf(u1, 1.0f)));   // sqrt(-2 ln u1)
+    float rad;                                                                  // sqrt(-2 ln u1), MUFU sqrt
+    asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(rad) : "f"(-1.3862943611198906f * __log2f(fminf(u1, 1.0f))));
     float s, c;
     __sincosf(6.283185307179586f * u2, &s, &c);
     z[2 * i] = rad * c;
@@ -66,8 +67,11 @@ __global__ void randn_kernel(float* out, int B, int chw, uint64_t seed, uint32_t
 // Algorithmic HBM traffic: 16 B/element with a noise tensor (x, eps, z in; x' out), 12 B with
 // in-kernel Philox (+ the small NHWC copy of x' when requested).
 // ------------------------------------------------------------------------------------------
+#ifndef SRD_PS_MINBLOCKS
+#define SRD_PS_MINBLOCKS 3      // 4 (64 registers, spills) and 2 measured the same 24 us: the kernel is issue-bound
+#endif
 template <int V, typename T, bool SMALLC>
-__global__ void __launch_bounds__(256, 3) p_sample_kernel(const SrdPSampleArgs a) {
+__global__ void __launch_bounds__(256, SRD_PS_MINBLOCKS) p_sample_kernel(const SrdPSampleArgs a) {
   const int HW = a.H * a.W;
   const int nq = HW / V;                       // V divides W (checked on the host)
   const uint64_t seed = a.seed_ptr ? __ldg(reinterpret_cast<const unsigned long long*>(a.seed_ptr)) : a.seed;
@@ -173,13 +177,24 @@ __global__ void __launch_bounds__(256, 3) p_sample_kernel(const SrdPSampleArgs a
       }
     }
     if (a.nhwc_out) {
+      // interior pixel groups (all but the two outermost rows / columns, whose pixels also own mirrored ring
+      // copies): the V pixels are V consecutive 8-channel slots -- plain vector stores, no ring logic
+      const bool interior = SMALLC && sizeof(T) == 2 && y > 1 && y < a.H - 2 && x0p > 1 && x0p + V < a.W - 2;
+      if (interior) {
+        uint4* dst = reinterpret_cast<uint4*>(static_cast<T*>(a.nhwc_out) +
+                                              ((size_t)(b * (a.H + 2) + y + 1) * (a.W + 2) + x0p + 1) * 8);
 #pragma unroll
-      for (int v = 0; v < V; ++v) {
-        float o8[8];
+        for (int v = 0; v < V; ++v)
+          dst[v] = make_uint4(pack_bf16x2(nh[v][0], nh[v][1]), pack_bf16x2(nh[v][2], NHC > 3 ? nh[v][NHC > 3 ? 3 : 0] : 0.f), 0u, 0u);
+      } else {
 #pragma unroll
-        for (int c = 0; c < 8; ++c) o8[c] = c < NHC ? nh[v][c < NHC ? c : 0] : 0.f;
-        store_nhwc<T, 8, (sizeof(T) == 2 ? 8 : 4)>(static_cast<T*>(a.nhwc_out), a.nhwc_ct, 0, b, y,
-                                                   x0p + v, a.H, a.W, 0, 8, SRD_BORDER_REFLECT, o8);
+        for (int v = 0; v < V; ++v) {
+          float o8[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) o8[c] = c < NHC ? nh[v][c < NHC ? c : 0] : 0.f;
+          store_nhwc<T, 8, (sizeof(T) == 2 ? 8 : 4)>(static_cast<T*>(a.nhwc_out), a.nhwc_ct, 0, b, y,
+                                                     x0p + v, a.H, a.W, 0, 8, SRD_BORDER_REFLECT, o8);
+        }
       }
     }
   }

@@ -157,7 +157,7 @@ def time_embedding(sd, time, dim, prefix="denoise_fn."):
     """`SinusoidalPosEmb` :412-419 followed by `Unet.mlp` :764-768."""
     half = dim // 2
     e = math.log(10000) / (half - 1)
-    e = torch.exp(torch.arange(half) * -e)
+    e = torch.exp(torch.arange(half, device=time.device) * -e)     # on the input's device, like :415-416
     e = time[:, None] * e[None, :]
     e = torch.cat((e.sin(), e.cos()), dim=-1)
     h = F.linear(e, sd[prefix + "mlp.0.weight"], sd[prefix + "mlp.0.bias"])
