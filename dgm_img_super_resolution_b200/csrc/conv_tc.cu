@@ -63,7 +63,8 @@ constexpr int A_HALO_STAGE = (A_HALO_BYTES + 1023) / 1024 * 1024;
 constexpr int MAX_STAGES = 8;
 constexpr int DBG_ITEMS = 64;
 constexpr int BAR_BYTES = 1024;          // mbarriers + TMEM slot
-constexpr int VEC_BYTES = (512 + 1024 + 4 + 2 * 128 * 4) * 4;   // epilogue vectors (see conv_tc_kernel)
+constexpr int VEC_BYTES = (512 + 1024 + 4 + 2 * 128 * 4) * 4;   // epilogue vectors (see conv_tc_kernel); the layout uses
+                                                                // 512 + 512 + 1024 + 4 floats of it
 
 // Exact n / d for n < 2^24 as one 32x32->64 multiply and a shift (the single-thread roles and the
 // per-tile epilogue decode must not run ~40-instruction integer divisions).
@@ -1611,11 +1612,11 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
   uint8_t* gen_base = smem_raw + (bar_base - smem_u32(smem_raw));       // generic pointer to bar_base
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(gen_base + 8 * (4 * MAX_STAGES + 8));
   float* vec = reinterpret_cast<float*>(gen_base + BAR_BYTES);
-  float* s_bias = vec;                 // [256]
-  float* s_temb = vec + 256;           // [256]
-  float* s_head = vec + 512;           // [4][256]
-  float* s_headb = vec + 512 + 1024;   // [4]
-  float* s_hpart = vec + 512 + 1024 + 4;   // [2][128][4]
+  float* s_bias = vec;                 // [512]: bias, then (second output) bias2 at [Npad, 2 Npad)
+  float* s_temb = vec + 512;           // [512]
+  float* s_head = vec + 1024;          // [4][256]
+  float* s_headb = vec + 1024 + 1024;  // [4]
+  float* s_hpart = nullptr;
 
   if (warp == WARP_TMA && lane == 0) {
     for (int s = 0; s < a.a_stages; ++s) { mbar_init(A_full(s), 1); mbar_init(A_empty(s), 1); }
@@ -2276,10 +2277,10 @@ int tc_supported(const SrdConvDesc& d, const char** why) {
   else if (d.stride != 1 && d.stride != 2) w = "stride";
   else if (d.head_w && (d.planar_c > 4 || !d.planar)) w = "head needs planar_c <= 4";
   else if (d.head_w && d.lin_src) w = "fused head and linear residual are exclusive";
-  else if (d.N2 && (d.N2 != d.N || (d.N % 64) || d.N > 128 || d.stride != 1 || d.up != 1 || d.nky != 3 || d.nkx != 3 ||
+  else if (d.N2 && (d.N2 != d.N || (d.N % 64) || d.N > 256 || d.stride != 1 || d.up != 1 || d.nky != 3 || d.nkx != 3 ||
                     d.res1 || d.res2 || d.lin_src || d.head_w || d.out2 || d.planar || !d.out || (d.dst2_ct % 8) ||
                     (d.dst2_coff % 8)))
-    w = "second output needs a plain 3x3 stride-1 conv with N2 == N in {64, 128}, one NHWC output, no residuals";
+    w = "second output needs a plain 3x3 stride-1 conv with N2 == N in {64, 128, 192, 256}, one NHWC output, no residuals";
   else {
     for (int i = 0; i < d.n_src; ++i) {
       const SrdSrc& s = d.src[i];
@@ -2662,6 +2663,7 @@ int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, 
     SRD_CHECK(!a.dyn_sched && !a.dbg, "conv_chain: layer %d uses the dynamic scheduler / debug stamps", i);
     SRD_CHECK(a.up == 1 || a.up == 2, "conv_chain: layer %d has up = %d (only 1 and 2 can be chained)", i, a.up);
     SRD_CHECK(!(a.head_w || a.lin_w) || a.Npad <= 128, "conv_chain: layer %d: fused head / linear residual need N <= 128", i);
+    SRD_CHECK(!a.dual || a.Npad <= 128, "conv_chain: layer %d: a second output needs N <= 128 inside a chain", i);
     n_rowblk[i] = (a.n_vrows - a.vstart + TILE_H - 1) / TILE_H;
     const int layer_smem = plans[i]->smem - (BAR_BYTES + VEC_BYTES) + CHAIN_FIXED_BYTES;
     if (layer_smem > smem) smem = layer_smem;

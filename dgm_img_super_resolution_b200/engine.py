@@ -15,6 +15,10 @@ from . import _lib as L
 PRECISIONS = ("bf16", "fp32", "bf16_direct")
 # developer switch for A/B measurements: res_conv as a second output of block1's launch (SrdConvDesc.N2)
 FUSE_RES_CONV = os.environ.get("SRD_NO_FUSED_RES") != "1"
+# widest block whose res_conv rides on block1's launch: 128 keeps two TMEM accumulator stages (2 x 2 x 128 columns);
+# 192 / 256 outputs fit too (2 x N <= 512 columns, SRD_FUSE_RES_MAX_N=256: 42 -> 39 launches) but leave ONE stage, i.e.
+# no MMA / epilogue overlap inside the launch -- measured 2.664 vs 2.677 ms per pass, inside the noise, so off
+FUSE_RES_MAX_N = int(os.environ.get("SRD_FUSE_RES_MAX_N", "128"))
 REVERSE_ORDER = os.environ.get("SRD_NO_REVERSE", "0") != "1"   # alternate the tile order of consecutive conv launches
 FOLD_COND = os.environ.get("SRD_NO_FOLD_COND", "0") != "1"     # add cond after the first Downsample (see CondProgram)
 # Unet.forward as ONE persistent launch (srd_chain_*), opt-in with SRD_CHAIN=1: bit-identical to the per-layer
@@ -77,6 +81,13 @@ class Act:
 # --------------------------------------------------------------------------------------------
 # weight packing (one-time re-layout; see include/srdiff_b200.h for the layouts)
 # --------------------------------------------------------------------------------------------
+def _host(weight):
+    """fp32 host copy of a (small) parameter: the one-time re-layout runs as CPU tensor ops followed by ONE
+    host->device copy per packed tensor, so building a plan launches no GPU kernels of its own (the first kernels
+    of a fresh process are then the conv launches themselves, not hundreds of ATen slice copies)."""
+    return weight.detach().to(device="cpu", dtype=torch.float32)
+
+
 def _chunked(wp, nch):
     """[rows][nch*64][...] -> [rows][nch][64][...]"""
     return wp.reshape(wp.shape[0], nch, 64, *wp.shape[2:])
@@ -88,7 +99,7 @@ def _pack_conv_blocks(w, src_cins, ky_order):
     whole-tensor ops per source (pad, gather, permute) -- not one copy per (chunk, tap)."""
     O, I, kh, kw = w.shape
     npad = _ceil(O, 16) * 16
-    ky_idx = torch.tensor(ky_order, device=w.device)
+    ky_idx = torch.tensor(ky_order)
     out, a = [], 0
     for cin in src_cins:
         nch = _ceil(cin, 64)
@@ -104,7 +115,8 @@ def _pack_conv(weight, src_cins, stride):
     O, I, kh, kw = weight.shape
     assert sum(src_cins) == I, (src_cins, I)
     npad = _ceil(O, 16) * 16
-    w = weight.detach().float()
+    dev = weight.device
+    w = _host(weight)
     ky_order = [0, 2, 1] if stride == 2 else list(range(kh))
     parts, a = [], 0
     for cin in src_cins:
@@ -113,7 +125,7 @@ def _pack_conv(weight, src_cins, stride):
     w_direct = torch.cat(parts, 0)[None].contiguous()
     blocks = [b.reshape(-1, npad, 64) for b in _pack_conv_blocks(w, src_cins, ky_order)]
     w_tc = torch.cat(blocks, 0).to(torch.bfloat16).contiguous()
-    return w_direct, w_tc
+    return w_direct.to(dev), w_tc.to(dev)
 
 
 def _pack_convT(weight, src_cins, S):
@@ -124,9 +136,10 @@ def _pack_convT(weight, src_cins, S):
     I, O, k, _ = weight.shape
     assert k == 2 * S and sum(src_cins) == I
     npad = _ceil(O, 16) * 16
-    w = weight.detach().float()
+    dev = weight.device
+    w = _host(weight)
     taps = torch.tensor([[r + S // 2 - ((1 if r >= S // 2 else 0) + d - 1) * S for d in range(2)] for r in range(S)],
-                        device=w.device)                                   # [S][2]: kernel index of tap d in phase r
+                        )                                                  # [S][2]: kernel index of tap d in phase r
     directs, tcs, a = [], [], 0
     for cin in src_cins:
         ws = w[a:a + cin]                                                  # [cin][O][k][k]
@@ -139,7 +152,7 @@ def _pack_convT(weight, src_cins, S):
         a += cin
     w_direct = torch.cat(directs, 1).contiguous()
     w_tc = torch.cat(tcs, 1).to(torch.bfloat16).contiguous()
-    return w_direct, w_tc
+    return w_direct.to(dev), w_tc.to(dev)
 
 
 def _pack_conv_dual(w3, w1, src_cins):
@@ -148,11 +161,11 @@ def _pack_conv_dual(w3, w1, src_cins):
     O, I, kh, kw = w3.shape
     assert (kh, kw) == (3, 3) and tuple(w1.shape) == (O, I, 1, 1) and sum(src_cins) == I
     npad = _ceil(O, 16) * 16
-    b3 = _pack_conv_blocks(w3.detach().float(), src_cins, [0, 1, 2])
-    b1 = _pack_conv_blocks(w1.detach().float(), src_cins, [0])
+    b3 = _pack_conv_blocks(_host(w3), src_cins, [0, 1, 2])
+    b1 = _pack_conv_blocks(_host(w1), src_cins, [0])
     blocks = [torch.cat([x.reshape(x.shape[0], 9, npad, 64), y.reshape(y.shape[0], 1, npad, 64)], 1)
               for x, y in zip(b3, b1)]
-    return torch.cat([b.reshape(-1, npad, 64) for b in blocks], 0).to(torch.bfloat16).contiguous()
+    return torch.cat([b.reshape(-1, npad, 64) for b in blocks], 0).to(torch.bfloat16).contiguous().to(w3.device)
 
 
 def _pack_conv_win8(weight):
@@ -161,10 +174,10 @@ def _pack_conv_win8(weight):
     O, I, kh, kw = weight.shape
     assert kh == 3 and kw == 3 and I <= 8
     npad = _ceil(O, 16) * 16
-    w = weight.detach().float()
-    blk = torch.zeros((kh, npad, 8, 8), dtype=torch.float32, device=w.device)      # [ky][n][dx][c]
+    w = _host(weight)
+    blk = torch.zeros((kh, npad, 8, 8), dtype=torch.float32)                          # [ky][n][dx][c]
     blk[:, :O, :kw, :I] = w.permute(2, 0, 3, 1)                                       # [ky][O][kx][I]
-    return blk.reshape(kh, npad, 64).to(torch.bfloat16).contiguous()
+    return blk.reshape(kh, npad, 64).to(torch.bfloat16).contiguous().to(weight.device)
 
 
 class PackedConv:
@@ -663,7 +676,7 @@ def build_resnet(bld, blk, srcs, dim_out, out, border, temb_off, temb_bstride=0,
         return out
     # channel-changing block on the tcgen05 path: the 1x1 res_conv is a second output of block1's launch
     # (same activation tiles; SrdConvDesc.N2) when the doubled accumulator still leaves two TMEM stages
-    fused_res = (cin != dim_out and FUSE_RES_CONV and mid_res is None and bld.prec.name == "bf16" and dim_out % 64 == 0 and dim_out <= 128 and H >= 4 and
+    fused_res = (cin != dim_out and FUSE_RES_CONV and mid_res is None and bld.prec.name == "bf16" and dim_out % 64 == 0 and dim_out <= FUSE_RES_MAX_N and H >= 4 and
                  (temb_bstride == 0 or not use_temb) and all(s[0].ct % 8 == 0 and s[1] % 8 == 0 for s in srcs))
     r = bld.act(B, H, W, dim_out) if cin != dim_out else None
     bld.conv(_pc(blk.block1.block[1]), srcs, out=h1, act=L.ACT_MISH, temb_off=temb_off,
