@@ -135,6 +135,7 @@ def imresize(I, scale=None, method='bicubic', sizes=None, mode="vec"):
     flag2d = B.dim() == 2
     if flag2d:
         B = B.unsqueeze(2)
+    keep = []                                           # tap tables stay referenced until the stream has used them
     for dim in np.argsort(np.array(sc)):
         dim = int(dim)
         w, ind = contributions(I.shape[dim], osz[dim], sc[dim], kernel, 4.0)
@@ -146,7 +147,7 @@ def imresize(I, scale=None, method='bicubic', sizes=None, mode="vec"):
         L.check(L.lib().srd_resize_dim(B.data_ptr(), 1 if B.dtype == torch.uint8 else 0, H, W, C_, dim, osz[dim],
                                        wd.data_ptr(), idd.data_ptr(), w.shape[1], out.data_ptr(), E._stream()),
                 "srd_resize_dim")
-        torch.cuda.current_stream().synchronize()       # wd / idd are temporaries
+        keep.append((wd, idd, B))      # (the caching allocator is stream-ordered: freeing them later is safe, no host sync)
         B = out
     return B.squeeze(2) if flag2d else B
 

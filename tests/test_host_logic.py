@@ -175,12 +175,14 @@ def test_committed_profile_evidence_is_consistent(tmp_path):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    csv_path = os.path.join(root, "profiles", "r01", "ncu_launch_list_bench_warmL2.csv")
-    out = str(tmp_path / "pass.json")
-    subprocess.check_call([sys.executable, os.path.join(root, "tools", "ncu_summary.py"), csv_path, "--pass-json", out],
-                          stdout=subprocess.DEVNULL)
-    got, committed = json.load(open(out)), json.load(open(os.path.join(root, "profiles", "r01", "unet_pass_traffic.json")))
-    assert got["conv_launches_per_unet_pass"] == committed["conv_launches_per_unet_pass"] == 42
-    for k in ("dram_bytes_read", "dram_bytes_write", "serialized_cold_us"):
-        assert got[k] == pytest.approx(committed[k], rel=1e-9)
-    assert 4.5e9 < committed["dram_bytes_read"] + committed["dram_bytes_write"] < 6.5e9
+    for rnd in ("r01", "r02"):
+        csv_path = os.path.join(root, "profiles", rnd, "ncu_launch_list_bench_warmL2.csv")
+        out = str(tmp_path / ("pass_%s.json" % rnd))
+        subprocess.check_call([sys.executable, os.path.join(root, "tools", "ncu_summary.py"), csv_path, "--pass-json", out],
+                              stdout=subprocess.DEVNULL)
+        got = json.load(open(out))
+        committed = json.load(open(os.path.join(root, "profiles", rnd, "unet_pass_traffic.json")))
+        assert got["conv_launches_per_unet_pass"] == committed["conv_launches_per_unet_pass"] == 42
+        for k in ("dram_bytes_read", "dram_bytes_write", "serialized_cold_us"):
+            assert got[k] == pytest.approx(committed[k], rel=1e-9)
+        assert 4.5e9 < committed["dram_bytes_read"] + committed["dram_bytes_write"] < 6.5e9

@@ -93,8 +93,8 @@ def pass_traffic(path, out_json):
            "dram_bytes_read": sum(c.get("rd", 0.0) for c in convs), "dram_bytes_write": sum(c.get("wr", 0.0) for c in convs),
            "per_launch": [{"us": round(c["us"], 2), "rd_MB": round(c.get("rd", 0.0) / 1e6, 2),
                            "wr_MB": round(c.get("wr", 0.0) / 1e6, 2)} for c in convs],
-           "source": "profiles/r01/" + os.path.basename(path) + " (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
-                     "dram__bytes_write.sum --clock-control none, python bench.py --steps 1 --warmup 1 --no-cpu)"}
+           "source": os.path.join(os.path.basename(os.path.dirname(os.path.abspath(out_json))), os.path.basename(path)) + " (ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,"
+                     "dram__bytes_write.sum --clock-control none, --cache-control none, python bench.py --steps 1 --warmup 1 --no-cpu --no-cudnn)"}
     json.dump(res, open(out_json, "w"), indent=1)
     print("pass: %d launches, %.1f us serialized, %.2f GB read + %.2f GB written -> %s" % (
         res["conv_launches_per_unet_pass"], res["serialized_cold_us"], res["dram_bytes_read"] / 1e9,
