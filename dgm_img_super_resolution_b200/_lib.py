@@ -43,7 +43,7 @@ class SrdConvDesc(C.Structure):
         ("lin_src", C.c_void_p), ("lin_ct", C.c_int32), ("lin_c", C.c_int32), ("lin_w", C.c_void_p),
         ("N2", C.c_int32), ("dst2_ct", C.c_int32), ("dst2_coff", C.c_int32), ("reserved2", C.c_int32),
         ("bias2", C.c_void_p), ("dst2", C.c_void_p),
-        ("reverse_items", C.c_int32), ("reserved3", C.c_int32),
+        ("reverse_items", C.c_int32), ("n_split", C.c_int32),
     ]
 
 

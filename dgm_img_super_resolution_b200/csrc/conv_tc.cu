@@ -139,6 +139,10 @@ struct TcArgs {
   unsigned* sched_counter; // dynamic item scheduler (see Sched): per-plan ticket counter, 0 between launches
   int dyn_sched;           // 1: items beyond each pair's first are handed out by tickets, not round-robin
   int reverse_items;       // static deal only: item order reversed (see SrdConvDesc.reverse_items)
+  int nsplit;              // 1 | 2: the N output channels are computed as `nsplit` groups of Npad channels, each group a
+                           // "phase" of its own (own weight k-blocks, own items): N = 256 runs as two 128-column halves
+                           // with TWO tile pairs per weight block (MT = 2) in the TMEM space one 256-column tile needs,
+                           // which halves the weight bytes streamed from L2 per MMA (SrdConvDesc.n_split)
 };
 
 // ------------------------------------------------------------------------------------------ layer chain
@@ -969,7 +973,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
         dep_wait(L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi, a.err_flag, cx->exp_mult);
       }
       mbar_expect_tx(bar, 4096u);
-      tma_load_3d(sg.base + buf * 4096u, &m_.tmR, bar, j * 64, colblk * TILE_W + 1, Vr);
+      tma_load_3d(sg.base + buf * 4096u, &m_.tmR, bar, j * 64 + (a.nsplit > 1 ? ph * a.Npad : 0), colblk * TILE_W + 1, Vr);
     } else {
       mbar_arrive(bar);
     }
@@ -987,6 +991,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
     const int t0 = (item - phase * a.items_per_phase) * (a.MT * CG) + pid.rank;
     int pr = 0, ps = 0;                                          // sub-pixel phase of a transposed conv
     if (S > 1) { pr = fdiv(phase, a.fd_up); ps = phase - pr * S; }
+    const int choff = a.nsplit > 1 ? phase * a.Npad : 0;         // first output channel of this item's channel group
     const bool stamp = (quarter == 0 && lane == 0);
     if (stamp) epi_stamp(a, it, 0);
     if (PUB) {
@@ -1023,8 +1028,8 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
           edge = 0;
           if (valid && reflect)
             edge = (oy == 1 ? 1u : 0u) | (oy == Ho - 2 ? 2u : 0u) | (ox == 1 ? 4u : 0u) | (ox == Wo - 2 ? 8u : 0u);
-          outp = static_cast<__nv_bfloat16*>(a.ep.out) + pix * a.ep.out_ct + a.ep.out_coff;
-          r2p = (a.ep.res2 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff : nullptr;
+          outp = static_cast<__nv_bfloat16*>(a.ep.out) + pix * a.ep.out_ct + a.ep.out_coff + choff;
+          r2p = (a.ep.res2 && valid) ? static_cast<const __nv_bfloat16*>(a.ep.res2) + pix * a.ep.res2_ct + a.ep.res2_coff + choff : nullptr;
           tbase = tmem_base + ((uint32_t)(quarter * 32) << 16) +
                   (uint32_t)(stage * stage_cols + which * n_sub1 * 64 + mt * a.Npad);
           if (which) { edge = 0; r2p = nullptr; mt_cur = -1; }     // plain output: no ring mirrors, no residuals
@@ -1045,7 +1050,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
 #pragma unroll 1
         for (int cc = 0; cc < 4; ++cc) {
           const int c0 = j * 64 + cc * 16;
-          const int cb = c0 + which * a.Npad;                    // bias2 / zero temb are staged after bias / temb
+          const int cb = c0 + which * a.Npad + choff;            // bias2 / zero temb are staged after bias / temb
           uint32_t r[16];
           tc_ld16(tbase + (uint32_t)c0, r);
           uint4* s0 = reinterpret_cast<uint4*>(row + (((uint32_t)(2 * cc) ^ swz) << 4));
@@ -1156,8 +1161,9 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
           flush();                                                 // (the previous sub-tile's stores have long completed)
           const uint32_t src = sg.base + buf * 4096u;
           const int V0 = tg.V0 + g0, xc = tg.x0 + 1;               // this warp's 4 rows
+          const int jc = j * 64 + choff;                           // first channel of the sub-tile in the tensor
           if (which) {                                             // second output: zero ring, one 4-row box
-            tma_store_3d(&m_.tmO2, src, j * 64, xc, V0);
+            tma_store_3d(&m_.tmO2, src, jc, xc, V0);
           } else if (a.epi_geo == 0) {
             bool whole = !reflect;
             int yp0 = 0;
@@ -1167,7 +1173,7 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
               whole = (yp0 >= 3) && (yp0 + 3 <= Ho - 2) && (V0 + 4 <= a.n_vrows);
             }
             if (whole) {
-              tma_store_3d(&m_.tmO, src, j * 64, xc, V0);
+              tma_store_3d(&m_.tmO, src, jc, xc, V0);
             } else {
               int yp = yp0;
               for (int gg = 0; gg < 4; ++gg, ++yp) {
@@ -1176,9 +1182,9 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
                 if (V >= a.n_vrows) break;
                 if (yp < 1 || yp > Ho) continue;                     // ring row: written by its mirror source
                 const uint32_t rs = src + (uint32_t)gg * 1024u;
-                tma_store_3d(&m_.tmOrow, rs, j * 64, xc, V);
-                if (yp == 2) tma_store_3d(&m_.tmOrow, rs, j * 64, xc, V - 2);          // oy == 1 -> ring row 0
-                if (yp == Ho - 1) tma_store_3d(&m_.tmOrow, rs, j * 64, xc, V + 2);     // oy == H-2 -> ring row H+1
+                tma_store_3d(&m_.tmOrow, rs, jc, xc, V);
+                if (yp == 2) tma_store_3d(&m_.tmOrow, rs, jc, xc, V - 2);          // oy == 1 -> ring row 0
+                if (yp == Ho - 1) tma_store_3d(&m_.tmOrow, rs, jc, xc, V + 2);     // oy == H-2 -> ring row H+1
               }
             }
           } else {
@@ -1190,8 +1196,8 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
             const int bb0 = fdiv(V0, a.fd_period), y0 = V0 - bb0 * a.period - a.voff;
             const int oy0 = y0 * S + pr, oy3 = (y0 + 3) * S + pr;
             if (y0 >= 0 && y0 + 3 < a.H_m && V0 + 3 < a.n_vrows && (!reflect || (oy0 > 1 && oy3 < Ho - 2))) {
-              if (S == 1) tma_store_3d(&m_.tmO, src, j * 64, xc, bb0 * (Ho + 2) + oy0 + 1);
-              else tma_store_5d(&m_.tmO, src, j * 64, Cc & 1, Cc >> 1, (oy0 + 1) & 1, bb0 * hp2 + ((oy0 + 1) >> 1));
+              if (S == 1) tma_store_3d(&m_.tmO, src, jc, xc, bb0 * (Ho + 2) + oy0 + 1);
+              else tma_store_5d(&m_.tmO, src, jc, Cc & 1, Cc >> 1, (oy0 + 1) & 1, bb0 * hp2 + ((oy0 + 1) >> 1));
             } else
             for (int gg = 0; gg < 4; ++gg) {
               const int V = V0 + gg;
@@ -1202,8 +1208,8 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
               const int oy = y * S + pr;
               const uint32_t rs = src + (uint32_t)gg * 1024u;
               auto put = [&](int Rl) {                               // Rl: padded row inside image bb
-                if (S == 1) tma_store_3d(&m_.tmOrow, rs, j * 64, xc, bb * (Ho + 2) + Rl);
-                else tma_store_5d(&m_.tmOrow, rs, j * 64, Cc & 1, Cc >> 1, Rl & 1, bb * hp2 + (Rl >> 1));
+                if (S == 1) tma_store_3d(&m_.tmOrow, rs, jc, xc, bb * (Ho + 2) + Rl);
+                else tma_store_5d(&m_.tmOrow, rs, jc, Cc & 1, Cc >> 1, Rl & 1, bb * hp2 + (Rl >> 1));
               };
               put(oy + 1);
               if (reflect) {
@@ -1398,7 +1404,7 @@ __device__ __forceinline__ void weight_producer_role(const TcArgs& a, const TcMa
   for (int il = 0;; ++il) {
     const int item = sc.get(il);
     if (item < 0) break;
-    int kb = (a.up > 1) ? fdiv(item, a.fd_ipp) * kb_per_phase : 0;
+    int kb = (a.up > 1 || a.nsplit > 1) ? fdiv(item, a.fd_ipp) * kb_per_phase : 0;
     for (int j = 0; j < kb_per_phase; ++j, ++kb) {
       mbar_wait(bars.B_empty(rb.stage), rb.phase ^ 1, err, 2);
       if (leader) mbar_expect_tx(bars.B_full(rb.stage), B_BYTES * CG);
@@ -1458,6 +1464,8 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
       ky0 = (pr >= S / 2) ? 1 : 0;
       kx0 = (ps >= S / 2) ? 1 : 0;
       b_cur += (uint32_t)phase * kbpp16;
+    } else if (a.nsplit > 1) {
+      b_cur += (uint32_t)fdiv(item, a.fd_ipp) * kbpp16;      // resident weights: the item's channel group
     }
     dbg_stamp(a, mma_il, 1);
     mbar_wait(bars.T_empty(rt.stage), rt.phase ^ 1, err, 3);
@@ -1648,7 +1656,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     }
   }
   // stage the per-channel epilogue vectors
-  for (int i = threadIdx.x; i < a.Npad; i += TC_THREADS) {
+  for (int i = threadIdx.x; i < a.Npad * a.nsplit; i += TC_THREADS) {
     s_bias[i] = (i < a.ep.N) ? __ldg(a.ep.bias + i) : 0.f;
     s_temb[i] = (a.ep.temb && a.ep.temb_bstride == 0 && i < a.ep.N) ? __ldg(a.ep.temb + i) : 0.f;
   }
@@ -1795,7 +1803,7 @@ __device__ __forceinline__ void chain_stage_vecs(const ChainLayer& L, const floa
   float* s_temb = bt + 256;
   const float* temb = L.temb_off >= 0 ? temb_row + L.temb_off : a.ep.temb;
   const int Npad = a.Npad, N = a.ep.N;
-  for (int i = tid; i < Npad; i += nthr) {
+  for (int i = tid; i < Npad * a.nsplit; i += nthr) {
     s_bias[i] = (i < N) ? __ldg(a.ep.bias + i) : 0.f;
     s_temb[i] = (temb && a.ep.temb_bstride == 0 && i < N) ? __ldg(temb + i) : 0.f;
   }
@@ -2281,6 +2289,10 @@ int tc_supported(const SrdConvDesc& d, const char** why) {
                     d.res1 || d.res2 || d.lin_src || d.head_w || d.out2 || d.planar || !d.out || (d.dst2_ct % 8) ||
                     (d.dst2_coff % 8)))
     w = "second output needs a plain 3x3 stride-1 conv with N2 == N in {64, 128, 192, 256}, one NHWC output, no residuals";
+  else if (d.n_split != 0 && d.n_split != 1 &&
+           (d.n_split != 2 || (d.N % 128) || d.stride != 1 || d.up != 1 || d.N2 || d.head_w || d.lin_src || d.planar || d.out2 ||
+            !d.out || d.H_out < 4 || d.temb_bstride != 0 || (d.out_ct % 8) || (d.out_coff % 8) || d.act == SRD_ACT_LRELU02))
+    w = "n_split = 2 needs a stride-1 conv with N % 128 == 0, one NHWC output through the TMA-staged epilogue";
   else {
     for (int i = 0; i < d.n_src; ++i) {
       const SrdSrc& s = d.src[i];
@@ -2320,7 +2332,8 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   a.n_src = d.n_src;
   a.stride = d.stride; a.nky = d.nky; a.nkx = d.nkx; a.ky0 = d.ky0; a.kx0 = d.kx0; a.up = d.up;
   a.H_m = d.H_in / d.stride; a.W_m = d.W_in / d.stride;
-  a.Npad = (d.N + 15) / 16 * 16;
+  a.nsplit = d.n_split == 2 ? 2 : 1;
+  a.Npad = (d.N / a.nsplit + 15) / 16 * 16;        // output channels (padded) of ONE channel group
   if (d.stride == 1) { a.period = Hp; a.voff = 1; a.vstart = 1; }
   else { a.period = Hp / 2; a.voff = 0; a.vstart = 0; }
   a.n_vrows = d.B * a.period;
@@ -2330,7 +2343,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   int dev = 0, n_sm = 148;
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, dev);
-  const int n_phase = d.up * d.up;
+  const int n_phase = d.up * d.up * a.nsplit;      // sub-pixel phases x channel groups: "phases" of the item space
   int kb = 0;
   const int taps = d.nky * d.nkx;
   a.dual = d.N2 ? 1 : 0;
@@ -2453,6 +2466,8 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   SRD_CHECK(!d.head_w || a.n_share == 1, "conv_tc: fused head needs N * MT <= 128");
   SRD_CHECK(!d.N2 || (a.epi_tma && a.a_mode == 1 && a.epi_geo == 0),
             "conv_tc: the second output needs the halo A mode and the TMA-staged epilogue");
+  SRD_CHECK(a.nsplit == 1 || (a.epi_tma && a.a_mode == 1 && a.epi_geo == 0),
+            "conv_tc: n_split needs the halo A mode and the TMA-staged epilogue");
   SRD_CHECK(!d.lin_src || a.epi_tma, "conv_tc: the linear residual needs the TMA-staged epilogue "
             "(stride-1 conv, N %% 64 == 0, NHWC output, batch-uniform temb)");
   plan->smem = a.a_stages * stage_bytes + b_bytes_total + stg_total + BAR_BYTES + VEC_BYTES + 1024;
@@ -2690,7 +2705,7 @@ int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, 
     const TcArgs& pa = plans[p]->args;
     const int Ho = pa.ep.H_out;
     d->cnt = chain->d_counters + cnt_off[(size_t)p * 2 + which];
-    const int n_phase = pa.up * pa.up;
+    const int n_phase = pa.up * pa.up * pa.nsplit;
     d->expect = pa.epi_tma ? (unsigned)(pa.n_colblk * (pa.Npad / 64) * 4 * n_phase)
                            : (unsigned)(pa.n_colblk * 4 * pa.n_share * n_phase);
     d->n_rowblk = n_rowblk[p];

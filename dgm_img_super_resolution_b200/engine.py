@@ -19,6 +19,11 @@ FUSE_RES_CONV = os.environ.get("SRD_NO_FUSED_RES") != "1"
 # 192 / 256 outputs fit too (2 x N <= 512 columns, SRD_FUSE_RES_MAX_N=256: 42 -> 39 launches) but leave ONE stage, i.e.
 # no MMA / epilogue overlap inside the launch -- measured 2.664 vs 2.677 ms per pass, inside the noise, so off
 FUSE_RES_MAX_N = int(os.environ.get("SRD_FUSE_RES_MAX_N", "128"))
+# 256-channel stride-1 convs as two 128-channel groups sharing each weight block between two tile pairs
+# (SrdConvDesc.n_split, SRD_NSPLIT=1): halves the weight bytes streamed from L2 per MMA, doubles the activation boxes;
+# measured neutral on B200 (layers 16-24 of the Unet: 300-326 us vs 285-322 us, run-to-run spread larger than the
+# difference), so off by default
+NSPLIT = os.environ.get("SRD_NSPLIT", "0") == "1"
 REVERSE_ORDER = os.environ.get("SRD_NO_REVERSE", "0") != "1"   # alternate the tile order of consecutive conv launches
 FOLD_COND = os.environ.get("SRD_NO_FOLD_COND", "0") != "1"     # add cond after the first Downsample (see CondProgram)
 # Unet.forward as ONE persistent launch (srd_chain_*), opt-in with SRD_CHAIN=1: bit-identical to the per-layer
@@ -218,18 +223,25 @@ class PackedConv:
             hit = self._cache["w8"]
         return hit[1], hit[2], hit[3]
 
-    def get(self, src_cins):
-        key = (tuple(src_cins), self.weight.data_ptr(), self.weight._version,
+    def get(self, src_cins, n_split=1):
+        key = (tuple(src_cins), n_split, self.weight.data_ptr(), self.weight._version,
                self.bias_p.data_ptr(), self.bias_p._version)
-        hit = self._cache.get("k")
+        slot = "k%d" % n_split
+        hit = self._cache.get(slot)
         if hit is None or hit[0] != key:
             if self.transposed:
                 wd, wt = _pack_convT(self.weight, src_cins, self.ksize // 2)
             else:
                 wd, wt = _pack_conv(self.weight, src_cins, self.stride)
+                if n_split > 1:       # w_tc per output-channel group: [group][KB][N / n_split][64]
+                    O = self.weight.shape[0]
+                    assert O % (64 * n_split) == 0
+                    h = O // n_split
+                    wt = torch.stack([_pack_conv(self.weight[g * h:(g + 1) * h], src_cins, self.stride)[1]
+                                      for g in range(n_split)]).contiguous()
             b = self.bias_p.detach().float().contiguous()
-            self._cache["k"] = (key, wd, wt, b)
-            hit = self._cache["k"]
+            self._cache[slot] = (key, wd, wt, b)
+            hit = self._cache[slot]
         return hit[1], hit[2], hit[3]
 
 
@@ -468,7 +480,16 @@ class Builder:
             d.dst2, d.dst2_ct, d.dst2_coff = dual[1].ptr, dual[1].ct, 0
             d.kernel = L.KERNEL_TC
         else:
-            wd, wt, bias = pw.get([s[2] for s in srcs])
+            # 256-wide stride-1 convs on the tcgen05 path: two channel groups of 128 (see SrdConvDesc.n_split)
+            n_split = 2 if (NSPLIT and self.prec.name == "bf16" and kernel is None and not pw.transposed and
+                            pw.stride == 1 and pw.N == 256 and out is not None and out2 is None and planar is None and
+                            head is None and lin is None and temb_bstride == 0 and act != L.ACT_LRELU02 and alpha == 1.0 and
+                            a0.H >= 4 and out.ct % 8 == 0 and out_coff % 8 == 0 and
+                            all(a.ct % 8 == 0 and coff % 8 == 0 for a, coff, _ in srcs) and
+                            (res1 is None or (res1[0].ct % 8 == 0 and res1[1] % 8 == 0)) and
+                            (res2 is None or (res2[0].ct % 8 == 0 and res2[1] % 8 == 0))) else 1
+            d.n_split = n_split
+            wd, wt, bias = pw.get([s[2] for s in srcs], n_split)
         if win8:
             d.stride, d.nky, d.nkx, d.ky0, d.kx0, d.up = 1, 3, 1, 0, 0, 1
         elif pw.transposed:

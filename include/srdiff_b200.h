@@ -111,7 +111,13 @@ typedef struct {
   /* tc kernel: walk the output tiles from the last to the first.  A consumer that starts where its producer
    * just finished finds the freshest part of its input still in the 126 MB L2 (layers are launched back to back
    * and every 160x160 / 80x80 tensor of a 64-image batch is larger than L2), so consecutive layers alternate. */
-  int32_t reverse_items, reserved3;
+  int32_t reverse_items;
+  /* tc kernel, 0 | 1 | 2.  2: compute the N output channels as two groups of N/2 (N % 128 == 0; stride-1 conv, one
+   * NHWC output, no second output / head / planar): w_tc then holds the k-blocks of group 0 (output channels
+   * [0, N/2), each block [N/2][64]) followed by those of group 1.  Every weight block is then shared by TWO tile
+   * pairs within the TMEM space one N-wide tile would need, halving the weight bytes streamed from L2 per MMA --
+   * what bounds the 256-channel layers of the 20x20 Unet level. */
+  int32_t n_split;
 } SrdConvDesc;
 
 typedef struct SrdConvPlan SrdConvPlan;

@@ -345,3 +345,28 @@ def test_sample_sharded_is_shard_invariant_with_real_diffusion(hp):
         M.runtime.noise, M.runtime.seed_override, M.runtime.image_offset = "torch", None, 0
         if created:
             dist.destroy_process_group()
+
+
+def test_n_split_channel_groups_match_oracle(hp):
+    """SrdConvDesc.n_split = 2 (opt-in, SRD_NSPLIT=1): a 256-channel Block computed as two 128-channel groups that
+    share every weight block between two tile pairs -- against the oracle, and bit-equal to the unsplit launch."""
+    from dgm_img_super_resolution_b200 import engine as E
+    import dgm_img_super_resolution_b200.model as M
+    M.hparams.clear()
+    M.hparams.update(hp)
+    torch.manual_seed(7)
+    blk = M.Block(192, 256, groups=0).to(DEV)
+    x = torch.randn((3, 192, 20, 12), generator=torch.Generator().manual_seed(8))
+    want = O._block({"block.1.weight": blk.block[1].weight.detach().cpu(), "block.1.bias": blk.block[1].bias.detach().cpu()},
+                    "", x)
+    M.runtime.precision = "bf16"
+    old = E.NSPLIT
+    try:
+        E.NSPLIT = False
+        plain = blk(x.to(DEV)).cpu()
+        E.NSPLIT = True
+        split = blk(x.to(DEV)).cpu()
+    finally:
+        E.NSPLIT = old
+    assert O.rel_l2(split, want) < 1e-2
+    assert torch.equal(split, plain)
