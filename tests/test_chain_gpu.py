@@ -131,11 +131,11 @@ def test_fused_segments_equal_layer_by_layer(hp, B, h, w):
     bld = plan.unet_prog.bld
     assert bld.chain is None and bld.exec is not None
     fused = [op for op in bld.exec if isinstance(op, E.ChainOp)]
-    assert fused and all(op.fused and 2 <= len(op.ops) <= 3 for op in fused)
+    assert fused and all(op.fused and 2 <= len(op.ops) <= 3 for op in fused)       # K = 2 (default build) or 3
     assert sum(len(op.ops) if isinstance(op, E.ChainOp) else 1 for op in bld.exec) == len(bld.ops)
     ref = _run_exec(plan, 2, fused=False)
     assert torch.isfinite(ref).all()
     for _ in range(4):
         assert torch.equal(_run_exec(plan, 2, fused=True), ref)
     if B == 64:
-        assert len(bld.exec) <= 28, len(bld.exec)          # 42 layers -> 27 launches
+        assert len(bld.exec) <= 32, len(bld.exec)          # 42 layers -> 27 launches with K = 3, 30 with K = 2
