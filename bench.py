@@ -362,15 +362,23 @@ def run_ours(args, hp, wl):
             img, _ = sample_call(img_lr, img_lr_up)
         return img
 
+    # end to end: every rank uploads ITS OWN images from pinned host memory, rank 0 reads the gathered result back
+    sh_start, sh_count = D.shard_range(Bcall_global, world, rank) if world > 1 else (0, Bcall_global)
+    lr_sl, up_sl = img_lr_h[sh_start:sh_start + sh_count], img_lr_up_h[sh_start:sh_start + sh_count]
+
     def one_pass_e2e():
         for _ in range(calls):
-            a = img_lr_h.to(dev, non_blocking=True)
-            b = img_lr_up_h.to(dev, non_blocking=True)
-            img, _ = sample_call(a, b)
-            if not tile:
-                out_h.copy_(img, non_blocking=True)           # stream-ordered D2H; synchronised by timed()
+            a = lr_sl.to(dev, non_blocking=True)
+            b = up_sl.to(dev, non_blocking=True)
+            if tile:
+                P.enhance(diff, a, tile=(tile, tile)).cpu()
+                continue
+            if world > 1:
+                img, _ = D.sample_sharded(diff, a, b, total=Bcall_global)
             else:
-                img.cpu()
+                img, _ = diff.sample(a, b, tuple(b.shape))
+            if rank == 0:
+                out_h.copy_(img, non_blocking=True)           # stream-ordered D2H; synchronised by timed()
         return out_h
 
     def barrier():
@@ -504,8 +512,8 @@ def run_ours(args, hp, wl):
             cud = {"error": str(e).splitlines()[0][:200]}
 
     if rank == 0:
-        h2d = int(calls * (img_lr_h.numel() + img_lr_up_h.numel()) * 4)
-        d2h = int(calls * out_h.numel() * 4)
+        h2d = int(calls * (img_lr_h.numel() + img_lr_up_h.numel()) * 4)      # summed over ranks: each uploads its shard
+        d2h = int(calls * out_h.numel() * 4)                                  # rank 0 reads the gathered batch
         n_launch = calls * diff.last_stats.get("gpu_launches", 0) if not tile else diff.last_stats.get("gpu_launches", 0)
         line = {
             "metric": METRIC, "value": value, "unit": "images/s",

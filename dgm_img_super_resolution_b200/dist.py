@@ -34,11 +34,12 @@ def gather_outputs(local, total, group=None):
     return torch.cat(parts, 0)
 
 
-def sample_sharded(diffusion, img_lr, img_lr_up, sample_fn=None, group=None):
+def sample_sharded(diffusion, img_lr, img_lr_up, sample_fn=None, group=None, total=None):
     """Run `GaussianDiffusion.sample` on this rank's slice of the global batch and gather.
 
-    img_lr / img_lr_up are the GLOBAL batch (same on every rank).  Returns (img, rrdb_out) for the
-    global batch on every rank.  Noise is ALWAYS the in-kernel Philox stream here (`runtime.noise` is
+    img_lr / img_lr_up are the GLOBAL batch (same on every rank) -- or, when `total` is given, only THIS RANK'S
+    slice `shard_range(total, world, rank)` of a global batch of `total` images (a host that feeds each GPU its own
+    images need not ship the whole batch to every rank).  Returns (img, rrdb_out) for the global batch on every rank.  Noise is ALWAYS the in-kernel Philox stream here (`runtime.noise` is
     forced to "philox" for the call) keyed by the global image index (`runtime.image_offset` = slice
     start) and by ONE seed agreed on by all ranks (rank 0's, broadcast), so the result does not depend on
     how the batch is sharded: N ranks produce bit for bit what one GPU produces for the whole batch.
@@ -46,9 +47,15 @@ def sample_sharded(diffusion, img_lr, img_lr_up, sample_fn=None, group=None):
     """
     from . import model as M
     world, rank = dist.get_world_size(group), dist.get_rank(group)
-    total = img_lr.shape[0]
-    start, count = shard_range(total, world, rank)
-    lr, up = img_lr[start:start + count], img_lr_up[start:start + count]
+    if total is None:
+        total = img_lr.shape[0]
+        start, count = shard_range(total, world, rank)
+        lr, up = img_lr[start:start + count], img_lr_up[start:start + count]
+    else:
+        start, count = shard_range(total, world, rank)
+        if img_lr.shape[0] != count:
+            raise ValueError("rank %d owns %d of %d images but was given %d" % (rank, count, total, img_lr.shape[0]))
+        lr, up = img_lr, img_lr_up
     old = (M.runtime.image_offset, M.runtime.noise, M.runtime.seed_counter, M.runtime.seed_override)
     # one seed for the whole job: rank 0 draws it, everybody uses it
     seed = torch.tensor([M.next_seed(img_lr.device) if rank == 0 else 0], dtype=torch.int64, device=img_lr.device)
