@@ -545,7 +545,11 @@ int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, 
   for (int i = 0; i < n; ++i) {
     const TcArgs& a = plans[i]->args;
     SRD_CHECK(a.cg == cg, "conv_chain: layers disagree on the CTA-pair mode");
+#if defined(SRD_TC_DEBUG)
+    SRD_CHECK(!a.dyn_sched, "conv_chain: layer %d uses the dynamic scheduler", i);      // debug builds keep the stamps
+#else
     SRD_CHECK(!a.dyn_sched && !a.dbg, "conv_chain: layer %d uses the dynamic scheduler / debug stamps", i);
+#endif
     SRD_CHECK(a.up == 1 || a.up == 2, "conv_chain: layer %d has up = %d (only 1 and 2 can be chained)", i, a.up);
     SRD_CHECK(!(a.head_w || a.lin_w) || a.Npad <= 128, "conv_chain: layer %d: fused head / linear residual need N <= 128", i);
     SRD_CHECK(!a.dual || a.Npad <= 128, "conv_chain: layer %d: a second output needs N <= 128 inside a chain", i);

@@ -1025,6 +1025,10 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
         uint8_t* row = my_row + buf * 4096u;
         mbar_wait(sg.r_full0 + 8u * buf, (k >> nbuf_sh) & 1u, a.err_flag, 8);   // buffer free / residual landed
         if (stamp && qq == share) epi_stamp(a, it, 2);
+        // Layer chain: the previous sub-tile's stores were issued a T_full / buffer wait ago -- publish them NOW, before
+        // this sub-tile's arithmetic: waiting for the next store point instead delays the consumer layer's first
+        // items by a whole sub-tile (measured: a 10 us bubble per layer at 20x20, profiles/r02)
+        if (PUB && lane == 0) flush();
         const bool last_sub = (qq + a.n_share >= n_sub);
         // Compact hot loop (one 16-channel chunk per iteration, NOT unrolled: the body must stay
         // resident in the instruction cache; rare ring / second-residual work lives outside).

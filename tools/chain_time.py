@@ -58,6 +58,7 @@ if specs and specs[0] == "one":
 if specs and specs[0] == "fused":
     # per fused group of the engine's default grouping: its launches one by one vs the fused-segment launch
     bld = plan.unet_prog.bld
+    E.FUSE_SEGMENTS = True
     bld.fuse_segments()
     pos = 0
     for op in bld.exec:

@@ -1,0 +1,1 @@
+timeout 1500 python -m pytest tests -m gpu -q 2>&1 | tail -3
