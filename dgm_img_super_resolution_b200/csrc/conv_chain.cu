@@ -308,8 +308,13 @@ struct SegParams {
   ChainLayer layers[K];
 };
 
+#ifndef SRD_SEG_PLAIN_ROLES
+#define SRD_SEG_PLAIN_ROLES 0     // diagnosis (single-layer segments only): bit 0 producer, 1 weights, 2 MMA, 3 epilogue
+#endif                            // run the NON-chain instantiation of that role inside the fused-segment kernel
 template <int CG, int K>
 __global__ void __launch_bounds__(TC_THREADS, 1) conv_seg_kernel(const __grid_constant__ SegParams<K> P) {
+  constexpr bool CH_P = !(SRD_SEG_PLAIN_ROLES & 1), CH_W = !(SRD_SEG_PLAIN_ROLES & 2), CH_M = !(SRD_SEG_PLAIN_ROLES & 4),
+                 CH_E = !(SRD_SEG_PLAIN_ROLES & 8);
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
   uint8_t* const gen0 = smem_raw + (smem_base - smem_u32(smem_raw));
@@ -377,7 +382,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_seg_kernel(const __grid_co
       for (int j = 0; j < K; ++j) {
         if (j < n) {
           cx.j = j;
-          producer_role<CG, true>(P.layers[j].a, P.maps[j], a_base, bar_base, &cx, &P.layers[j]);
+          producer_role<CG, CH_P>(P.layers[j].a, P.maps[j], a_base, bar_base, &cx, &P.layers[j]);
         }
       }
     }
@@ -387,7 +392,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_seg_kernel(const __grid_co
       for (int j = 0; j < K; ++j) {
         if (j < n) {
           cx.j = j;
-          weight_producer_role<CG, true>(P.layers[j].a, P.maps[j], b_base, bar_base, &cx);
+          weight_producer_role<CG, CH_W>(P.layers[j].a, P.maps[j], b_base, bar_base, &cx);
         }
       }
     }
@@ -401,10 +406,10 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_seg_kernel(const __grid_co
           const int taps = a.a_mode ? a.nkx * a.nky : 0;
 #define SRD_MMA_CASE(T, D)                                                                                             \
   do {                                                                                                                 \
-    if (a.b_resident && a.MT == 2) mma_role<T, 2, true, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);  \
-    else if (a.b_resident) mma_role<T, 1, true, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);          \
-    else if (a.MT == 2) mma_role<T, 2, false, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);            \
-    else mma_role<T, 1, false, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);                           \
+    if (a.b_resident && a.MT == 2) mma_role<T, 2, true, CG, D, CH_M>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);  \
+    else if (a.b_resident) mma_role<T, 1, true, CG, D, CH_M>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);          \
+    else if (a.MT == 2) mma_role<T, 2, false, CG, D, CH_M>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);            \
+    else mma_role<T, 1, false, CG, D, CH_M>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);                           \
   } while (0)
           if (a.dual) SRD_MMA_CASE(9, true);
           else if (taps == 9 && a.nkx == 3) SRD_MMA_CASE(9, false);
@@ -438,15 +443,15 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_seg_kernel(const __grid_co
           sg.gen = smem_raw + (sg.base - smem_u32(smem_raw));
           sg.r_full0 = bars.R_full0() + 8u * (uint32_t)(ew * 2);
           if (a.ep.act == SRD_ACT_MISH)
-            epilogue_tma<SRD_ACT_MISH, CG, true>(a, m_, es, sg, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
+            epilogue_tma<SRD_ACT_MISH, CG, CH_E>(a, m_, es, sg, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
           else
-            epilogue_tma<SRD_ACT_NONE, CG, true>(a, m_, es, sg, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
+            epilogue_tma<SRD_ACT_NONE, CG, CH_E>(a, m_, es, sg, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
         } else if (a.ep.act == SRD_ACT_MISH)
-          epilogue_role<SRD_ACT_MISH, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
+          epilogue_role<SRD_ACT_MISH, CG, CH_E>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
         else if (a.ep.act == SRD_ACT_LRELU02)
-          epilogue_role<SRD_ACT_LRELU02, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
+          epilogue_role<SRD_ACT_LRELU02, CG, CH_E>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
         else
-          epilogue_role<SRD_ACT_NONE, CG, true>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
+          epilogue_role<SRD_ACT_NONE, CG, CH_E>(a, es, sc, tmem_base, bars.T_full(0), bars.T_empty(0), warp, lane, &cx, &P.layers[j]);
         cx.it_base += (pid.pair < a.n_items) ? (uint32_t)((a.n_items - 1 - pid.pair) / pid.n_pairs + 1) : 0u;
       }
     }
@@ -554,6 +559,7 @@ int tc_chain_build(const TcPlan* const* plans, const TcChainLink* links, int n, 
     SRD_CHECK(!(a.head_w || a.lin_w) || a.Npad <= 128, "conv_chain: layer %d: fused head / linear residual need N <= 128", i);
     SRD_CHECK(!a.dual || a.Npad <= 128, "conv_chain: layer %d: a second output needs N <= 128 inside a chain", i);
     n_rowblk[i] = (a.n_vrows - a.vstart + TILE_H - 1) / TILE_H;
+    SRD_CHECK(n_rowblk[i] < 65535, "conv_chain: layer %d has too many row blocks for the packed dependency cache", i);
     const int layer_smem = plans[i]->smem - (BAR_BYTES + VEC_BYTES) + CHAIN_FIXED_BYTES;
     if (layer_smem > smem) smem = layer_smem;
   }

@@ -900,16 +900,23 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
 #endif
   constexpr bool PUB = CHAIN && !SRD_CHAIN_EPI_MIN;
   const uint32_t it_base = CHAIN ? cx->it_base : 0u;
-  unsigned* const out_cnt = PUB ? L->out_cnt : nullptr;
-  unsigned* const out2_cnt = PUB ? L->out2_cnt : nullptr;
-  int r_vlo = 0, r_vhi = -1;                      // residual producer's row blocks already seen complete (lane 0)
-  // Layer chain: the counter of the sub-tile this warp stored last, not yet bumped (lane 0).  Waiting for the bulk
-  // stores to COMPLETE right after issuing them would stall the warp for a DRAM / L2 round trip per sub-tile, so
-  // the bump is deferred to the next point where the warp either would idle anyway (its next accumulator is not
-  // ready, a dependency has to be polled) or is about to issue the next store (the old one has long completed).
-  // It is always flushed before a wait that another CTA's progress could depend on.
-  unsigned* pend = nullptr;
-  auto flush = [&]() { if (PUB && pend) { dep_publish(pend); pend = nullptr; } };
+  // Chain state is kept to TWO registers across the hot chunk loop (the epilogue sits at the kernel's register cap):
+  // `pend` = row block + 1 of the sub-tile this warp stored last and has not published yet (bit 30: second output;
+  // 0 = nothing pending) -- the counter arrays are re-read from the layer arguments when the bump happens -- and the
+  // [lo, hi] interval of residual row blocks already seen complete, packed into one word (lane 0 only).
+  // Waiting for the bulk stores to COMPLETE right after issuing them would stall the warp for a DRAM / L2 round trip
+  // per sub-tile, so the bump is deferred to the next point where the warp either would idle anyway (its next
+  // accumulator is not ready, a dependency has to be polled) or starts its next sub-tile.  It is always flushed
+  // before a wait that another CTA's progress could depend on.
+  uint32_t pend = 0u;
+  uint32_t r_seen = 0x0000FFFFu;                  // (hi << 16) | lo; lo = 0xFFFF marks the empty interval
+  auto flush = [&]() {
+    if (PUB && pend) {
+      unsigned* const base = (pend & 0x40000000u) ? L->out2_cnt : L->out_cnt;
+      dep_publish(base + ((pend & 0x3FFFFFFFu) - 1u));
+      pend = 0u;
+    }
+  };
   const PairId pid = pair_id<CG>();
   const int S = a.up;
   const int quarter = warp & 3, group = (warp - WARP_EPI0) >> 2;
@@ -949,9 +956,14 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
     const uint32_t bar = sg.r_full0 + 8u * buf;
     if (has_r1) {
       const int Vr = rowblk * TILE_H + a.vstart + g0;
-      if (PUB && L->dep_res1.cnt && !dep_cached(L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi)) {
-        flush();
-        dep_wait(L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi, a.err_flag, cx->exp_mult);
+      if (PUB && L->dep_res1.cnt) {
+        int r_vlo = (int)(r_seen & 0xFFFFu), r_vhi = (int)(r_seen >> 16);
+        if (r_vlo == 0xFFFF) { r_vlo = 0; r_vhi = -1; }
+        if (!dep_cached(L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi)) {
+          flush();
+          dep_wait(L->dep_res1, Vr, Vr + 4, r_vlo, r_vhi, a.err_flag, cx->exp_mult);
+          r_seen = ((uint32_t)r_vhi << 16) | (uint32_t)r_vlo;
+        }
       }
       mbar_expect_tx(bar, 4096u);
       tma_load_3d(sg.base + buf * 4096u, &m_.tmR, bar, j * 64 + (a.nsplit > 1 ? ph * a.Npad : 0), colblk * TILE_W + 1, Vr);
@@ -1209,8 +1221,8 @@ __device__ __forceinline__ void epilogue_tma(const TcArgs& a, const TcMaps& m_, 
           if (nbuf == 2) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
           else asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
           if (PUB) {         // layer chain: the readers of this tensor learn about these rows at the next flush()
-            unsigned* const cnt = which ? out2_cnt : out_cnt;
-            if (cnt && (t0 + mt * CG) < a.tiles_per_phase) pend = cnt + ((tg.V0 - a.vstart) >> 4);
+            if ((which ? L->out2_cnt : L->out_cnt) && (t0 + mt * CG) < a.tiles_per_phase)
+              pend = (uint32_t)(((tg.V0 - a.vstart) >> 4) + 1) | (which ? 0x40000000u : 0u);
           }
           if (stamp && last_sub) epi_stamp(a, it, 6);
           prepare(k + 1, it, qq + a.n_share);
