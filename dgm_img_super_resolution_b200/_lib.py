@@ -102,6 +102,7 @@ SYMBOLS = {
     "srd_chain_fused_max_layers": (C.c_int, []),
     "srd_conv_plans_share_segment": (C.c_int, [_vp, _vp]),
     "srd_tc_set_mode": (C.c_int, [_i32, _i32]),
+    "srd_tc_s2_halo": (C.c_int, []),
     "srd_tc_set_debug": (C.c_int, [_vp]),
     "srd_time_table": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp, _vp, _vp, _vp, _vp, _i32, _vp, _vp]),
     "srd_sinusoidal_emb": (C.c_int, [_vp, _i32, _i32, _vp, _vp, _vp]),

@@ -26,6 +26,7 @@ void tc_plan_delete(TcPlan*);
 int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag);
 int launch_conv_tc(const TcPlan& plan, const float* temb, cudaStream_t stream);
 void tc_set_mode(int a_mode, int b_resident);
+int tc_s2_halo();
 struct TcChain;
 struct TcChainLink {
   int src_layer[SRD_MAX_SRC], src_which[SRD_MAX_SRC];
@@ -178,6 +179,8 @@ int srd_tc_set_mode(int32_t a_mode, int32_t b_resident) {
   tc_set_mode(a_mode, b_resident ? 1 : 0);
   return 0;
 }
+
+int srd_tc_s2_halo(void) { return tc_s2_halo(); }
 
 int srd_tc_set_debug(void* buf) {
   tc_set_debug((unsigned long long*)buf);

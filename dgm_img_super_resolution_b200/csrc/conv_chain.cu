@@ -210,7 +210,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const __grid_
         if ((CG == 1 || pid.rank == 0) && elect_one_sync()) {
           const TcArgs& a = mine->a;
           cx.j = l - l0;
-          const int taps = a.a_mode ? a.nkx * a.nky : 0;
+          const int taps = a.a_mode == 2 ? TAPS_S2 : (a.a_mode ? a.nkx * a.nky : 0);
 #define SRD_MMA_CASE(T, D)                                                                                             \
   do {                                                                                                                 \
     if (a.b_resident && a.MT == 2) mma_role<T, 2, true, CG, D, true>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);  \
@@ -222,6 +222,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_chain_kernel(const __grid_
           else if (taps == 9 && a.nkx == 3) SRD_MMA_CASE(9, false);
           else if (taps == 4 && a.nkx == 2) SRD_MMA_CASE(4, false);
           else if (taps == 1) SRD_MMA_CASE(1, false);
+          else if (taps == TAPS_S2) SRD_MMA_CASE(TAPS_S2, false);
           else SRD_MMA_CASE(0, false);
 #undef SRD_MMA_CASE
         }
@@ -403,7 +404,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_seg_kernel(const __grid_co
         if (j < n) {
           const TcArgs& a = P.layers[j].a;
           cx.j = j;
-          const int taps = a.a_mode ? a.nkx * a.nky : 0;
+          const int taps = a.a_mode == 2 ? TAPS_S2 : (a.a_mode ? a.nkx * a.nky : 0);
 #define SRD_MMA_CASE(T, D)                                                                                             \
   do {                                                                                                                 \
     if (a.b_resident && a.MT == 2) mma_role<T, 2, true, CG, D, CH_M>(a, tmem_base, a_base, b_base, bar_base, 0, &cx);  \
@@ -415,6 +416,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_seg_kernel(const __grid_co
           else if (taps == 9 && a.nkx == 3) SRD_MMA_CASE(9, false);
           else if (taps == 4 && a.nkx == 2) SRD_MMA_CASE(4, false);
           else if (taps == 1) SRD_MMA_CASE(1, false);
+          else if (taps == TAPS_S2) SRD_MMA_CASE(TAPS_S2, false);
           else SRD_MMA_CASE(0, false);
 #undef SRD_MMA_CASE
         }

@@ -22,6 +22,7 @@
 // Two entry points share the role code: conv_tc_kernel (one layer per launch) and conv_chain_kernel (a list of
 // layers in ONE launch; CTAs move from layer to layer on their own, ordered by per-row-block completion counters
 // instead of kernel boundaries -- see the "layer chain" section).
+#include <stdlib.h>
 #include "conv_tc.cuh"
 
 namespace srd {
@@ -139,7 +140,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
     if ((CG == 1 || cluster_ctarank() == 0) && elect_one_sync()) {
       // specialised issue loops: taps unrolled (descriptor offsets become immediates), MT and the weight
       // mode resolved at compile time
-      const int taps = a.a_mode ? a.nkx * a.nky : 0;
+      const int taps = a.a_mode == 2 ? TAPS_S2 : (a.a_mode ? a.nkx * a.nky : 0);
 #define SRD_MMA_CASE(T)                                                                      \
   do {                                                                                       \
     if (a.b_resident && a.MT == 2) mma_role<T, 2, true, CG>(a, tmem_base, a_base, b_base, bar_base, issuer); \
@@ -155,6 +156,7 @@ __global__ void __launch_bounds__(TC_THREADS, 1) conv_tc_kernel(const __grid_con
       } else if (taps == 9 && a.nkx == 3) SRD_MMA_CASE(9);
       else if (taps == 4 && a.nkx == 2) SRD_MMA_CASE(4);
       else if (taps == 1) SRD_MMA_CASE(1);
+      else if (taps == TAPS_S2) SRD_MMA_CASE(TAPS_S2);
       else SRD_MMA_CASE(0);
 #undef SRD_MMA_CASE
     }
@@ -218,6 +220,12 @@ static EncodeTiledFn get_encode_fn() {
 
 // tuning / validation switches (srd_tc_set_mode): A-operand mode for stride-1 convs, resident weights
 static int g_a_mode = 1;
+// Stride-2 convs: halo boxes per (row parity, column parity) (1, default) or boxes per (kx, row parity) (0).  The two
+// modes consume the weight k-blocks in different tap orders; engine.py packs for the mode srd_tc_s2_halo() reports.
+int tc_s2_halo() {
+  static const int v = [] { const char* e = getenv("SRD_S2_HALO"); return e ? (atoi(e) ? 1 : 0) : 1; }();
+  return v;
+}
 static int g_b_resident = 1;
 static int g_epi_tma = 1;
 static int g_cg = 2;                     // CTAs per MMA: 2 = cta_group::2 pairs (default), 1 = single-CTA MMAs
@@ -330,8 +338,8 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
   // ---- shared-memory plan: A ring + weights (ring or resident) + staging + barriers + epilogue vectors
   const int B_BYTES = a.Npad * 128 / cg;      // per CTA: each CTA of a pair holds Npad / cg rows of a weight k-block
   const int budget = 227 * 1024 - BAR_BYTES - VEC_BYTES - 1024;
-  a.a_mode = (d.stride == 1) ? g_a_mode : 0;
-  a.a_stage_bytes = a.a_mode ? A_HALO_STAGE : A_BYTES;
+  a.a_mode = (d.stride == 1) ? g_a_mode : (tc_s2_halo() ? 2 : 0);
+  a.a_stage_bytes = a.a_mode == 2 ? A_S2_STAGE : (a.a_mode ? A_HALO_STAGE : A_BYTES);
   const long long res_bytes = (long long)a.kb_total * B_BYTES;
   const long long n_tiles_all = (long long)n_phase * a.tiles_per_phase;
   // MT = 2 halves the weight traffic of an item (two M tiles share every weight k-block).  Normally it needs
@@ -362,12 +370,13 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
         const long long left = (long long)budget - stg - res_bytes;
         if (left < 2LL * sb) continue;
         const int ast = (int)(left / sb);
-        a.a_stages = ast > 4 ? 4 : ast;
+        const int ast_max = a.a_mode == 2 ? 6 : 4;         // stride-2 halo: four boxes per chunk
+        a.a_stages = ast > ast_max ? ast_max : ast;
         a.b_stages = 1;
         b_bytes_total = (int)res_bytes;
       } else {
         // deepest A ring that still leaves >= 4 weight stages; at least 2 (halo) / 3 (per-kx) A stages and 3 weight stages
-        const int ast_min = a.a_mode ? 2 : 3;
+        const int ast_min = a.a_mode == 1 ? 2 : 3;
         int ast = 4;
         for (; ast > ast_min; --ast)
           if (budget - stg - ast * sb >= 4 * B_BYTES) break;
@@ -467,6 +476,7 @@ int tc_plan_build(const SrdConvDesc& d, TcPlan* plan, int* err_flag) {
       cuuint64_t strides[4] = {(cuuint64_t)s.ct * 2, (cuuint64_t)2 * s.ct * 2, (cuuint64_t)Wp * s.ct * 2,
                                (cuuint64_t)2 * Wp * s.ct * 2};
       cuuint32_t box[5] = {64, 1, TILE_W, 1, BOX_ROWS};
+      if (a.a_mode == 2) { box[2] = S2_W; box[4] = S2_ROWS; }
       cuuint32_t es[5] = {1, 1, 1, 1, 1};
       r = enc(&mp.tmA[i], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, base, dims, strides, box, es,
               CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,

@@ -41,6 +41,14 @@ constexpr int A_BYTES = BOX_ROWS * TILE_W * 128;   // 18432: one {64ch x 8px x 1
 constexpr int HALO_W = TILE_W + 2;
 constexpr int A_HALO_BYTES = BOX_ROWS * HALO_W * 128;      // 23040: one {64ch x 10px x 18rows} box (all 9 taps)
 constexpr int A_HALO_STAGE = (A_HALO_BYTES + 1023) / 1024 * 1024;
+// stride-2 convs (a_mode 2): one halo box per (input row parity, input column parity) of the parity-split view --
+// {64ch x 9 half-columns x 17 half-rows}; tap (ky, kx) reads box (ky & 1, kx & 1) at half-row / half-column offset
+// (ky >> 1, kx >> 1).  Four boxes (78 KB) per 64-channel chunk and M tile instead of six (kx, row parity) boxes
+// (110 KB).
+constexpr int S2_W = TILE_W + 1, S2_ROWS = TILE_H + 1;
+constexpr int A_S2_BYTES = S2_ROWS * S2_W * 128;           // 19584
+constexpr int A_S2_STAGE = (A_S2_BYTES + 1023) / 1024 * 1024;
+constexpr int TAPS_S2 = 18;                                // mma_role<TAPS> code of this mode
 constexpr int MAX_STAGES = 8;
 constexpr int DBG_ITEMS = 64;
 constexpr int BAR_BYTES = 1024;          // mbarriers + TMEM slot
@@ -101,7 +109,8 @@ struct TcArgs {
   int lin_ct, lin_c;
   int* err_flag;
   int fast;                // epilogue fast path eligible (N % 16 == 0, uniform temb, aligned windows)
-  int a_mode;              // 0: one box per (chunk, kx), ky by 1024 B row offsets (always-aligned descriptors)
+  int a_mode;              // 2: stride-2 halo boxes per (row parity, column parity), see A_S2_BYTES;
+                           // 0: one box per (chunk, kx), ky by 1024 B row offsets (always-aligned descriptors)
                            // 1|2: ONE halo box per chunk, (ky,kx) by 128 B-granular descriptor start offsets
                            //      (2: descriptor base_offset = (addr >> 7) & 7)
   int a_stage_bytes;       // bytes of one A tile slot inside a stage
@@ -389,6 +398,7 @@ __device__ __forceinline__ uint64_t umma_desc_sw128_ex(uint32_t saddr, uint32_t 
 // | SWIZZLE_128B (bits 61-63).  Advancing the start address is an add on the low word.
 constexpr uint32_t DESC_HI_1024 = (1024u >> 4) | (1u << 14) | (2u << 29);
 constexpr uint32_t DESC_HI_HALO = ((uint32_t)(TILE_W + 2) * 128u >> 4) | (1u << 14) | (2u << 29);
+constexpr uint32_t DESC_HI_S2 = ((uint32_t)(TILE_W + 1) * 128u >> 4) | (1u << 14) | (2u << 29);
 __device__ __forceinline__ uint64_t mk_desc(uint32_t lo, uint32_t hi) {
   uint64_t d;
   asm("mov.b64 %0, {%1, %2};" : "=l"(d) : "r"(lo), "r"(hi));
@@ -1324,18 +1334,21 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, const TcMaps& m_,
       item = sc.get(il);
       if (item < 0) break;
     }
-    const int phase = fdiv(item, a.fd_ipp);
-    const int t0 = (item - phase * ipp) * (MT * CG) + pid.rank;
-    int kx0 = a.kx0;
-    if (S > 1) { const int pr = fdiv(phase, a.fd_up); kx0 = (phase - pr * S >= S / 2) ? 1 : 0; }
-    // tile origins of this item
-    int V0[2], X0[2];
-    for (int mt = 0; mt < MT; ++mt) {
-      const int tt = t0 + mt * CG;
-      const int rowblk = fdiv(tt, a.fd_colblk);
-      V0[mt] = rowblk * TILE_H + vstart;
-      X0[mt] = (tt - rowblk * n_colblk) * TILE_W;
-    }
+    // tile origins (and first kx) of an item
+    auto origins = [&](int it_, int (&V0_)[2], int (&X0_)[2], int& kx0_) {
+      const int phase = fdiv(it_, a.fd_ipp);
+      const int t0 = (it_ - phase * ipp) * (MT * CG) + pid.rank;
+      kx0_ = a.kx0;
+      if (S > 1) { const int pr = fdiv(phase, a.fd_up); kx0_ = (phase - pr * S >= S / 2) ? 1 : 0; }
+      for (int mt = 0; mt < MT; ++mt) {
+        const int tt = t0 + mt * CG;
+        const int rowblk = fdiv(tt, a.fd_colblk);
+        V0_[mt] = rowblk * TILE_H + vstart;
+        X0_[mt] = (tt - rowblk * n_colblk) * TILE_W;
+      }
+    };
+    int V0[2], X0[2], kx0;
+    origins(item, V0, X0, kx0);
     if (CHAIN) {
       // the rows this item's boxes cover must have been written by the layers that produce them
 #pragma unroll
@@ -1352,6 +1365,18 @@ __device__ __forceinline__ void producer_role(const TcArgs& a, const TcMaps& m_,
       const CUtensorMap* tm = &m_.tmA[s];
       const int nch = a.nchunk[s];
       for (int ch = 0; ch < nch; ++ch) {
+        if (a_mode == 2) {
+          for (int p = 0; p < 4; ++p) {                      // (row parity, column parity) = (p >> 1, p & 1)
+            mbar_wait(bars.A_empty(ra.stage), ra.phase ^ 1, err, 1);
+            if (s == 0 && ch == 0 && p == 0) dbg_stamp(a, il, 0);
+            if (leader) mbar_expect_tx(bars.A_full(ra.stage), (uint32_t)(CG * MT * A_S2_BYTES));
+            for (int mt = 0; mt < MT; ++mt)
+              tma_load_5d<CG>(a_base + (uint32_t)(ra.stage * MT + mt) * a_stage_bytes, tm, bars.A_full(ra.stage),
+                              ch * 64, p & 1, X0[mt], p >> 1, V0[mt]);
+            ra.next();
+          }
+          continue;
+        }
         if (a_mode) {
           mbar_wait(bars.A_empty(ra.stage), ra.phase ^ 1, err, 1);
           if (s == 0 && ch == 0) dbg_stamp(a, il, 0);
@@ -1546,7 +1571,27 @@ __device__ __forceinline__ void mma_role(const TcArgs& a, uint32_t tmem_base, ui
       }
       kcount = 1u;
     };
-    if (TAPS > 0) {
+    if (TAPS == TAPS_S2) {
+      // stride-2 halo boxes; tap order == weight k-block order (engine._S2_TAPS):
+      // box (even rows, even cols): (0,0) (0,2) (2,0) (2,2); (even, odd): (0,1) (2,1); (odd, even): (1,0) (1,2); (odd, odd): (1,1)
+#pragma unroll 1
+      for (int c = 0; c < n_chunks; ++c) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          mbar_wait(bars.A_full(ra.stage), ra.phase, err, 4);
+          tc_fence_after();
+          if (c == 0 && p == 0) dbg_stamp(a, mma_il, 4);
+          const uint32_t st_lo = a_lo_base + (uint32_t)(ra.stage * MT) * aS16;
+#pragma unroll
+          for (int hy = 0; hy < ((p >> 1) ? 1 : 2); ++hy)
+#pragma unroll
+            for (int hx = 0; hx < ((p & 1) ? 1 : 2); ++hx)
+              issue_tap(st_lo + (uint32_t)(hy * S2_W + hx) * 8u, DESC_HI_S2);
+          tc_commit<CG>(bars.A_empty(ra.stage));
+          ra.next();
+        }
+      }
+    } else if (TAPS > 0) {
       constexpr int NK = TAPS == 9 ? 3 : (TAPS == 4 ? 2 : 1);
       const uint32_t tap0 = (uint32_t)(ky0 * HALO_W + kx0) * 8u;
 #pragma unroll 1
@@ -1616,6 +1661,7 @@ struct TcPlan {
   ~TcPlan() { if (counter) cudaFree(counter); }
 };
 
+int tc_s2_halo();              // conv_tc.cu: stride-2 A-operand mode (SRD_S2_HALO, default 1)
 int tc_pdl_enabled();          // conv_tc.cu: programmatic dependent launch switch (srd_tc_set_mode bit 3)
 
 }  // namespace srd

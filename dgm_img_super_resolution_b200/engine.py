@@ -115,6 +115,26 @@ def _pack_conv_blocks(w, src_cins, ky_order):
     return out
 
 
+# tap order of a stride-2 conv's k-blocks when the kernel reads halo boxes per (row parity, column parity)
+# (srd_tc_s2_halo(), csrc/conv_tc.cuh mma_role<TAPS_S2>): boxes (even, even), (even, odd), (odd, even), (odd, odd)
+_S2_TAPS = [(0, 0), (0, 2), (2, 0), (2, 2), (0, 1), (2, 1), (1, 0), (1, 2), (1, 1)]
+
+
+def _pack_conv_blocks_taps(w, src_cins, taps):
+    """Like _pack_conv_blocks with an explicit (ky, kx) list: per source [nch][tap][Npad][64]."""
+    O, I, kh, kw = w.shape
+    npad = _ceil(O, 16) * 16
+    idx = torch.tensor([ky * kw + kx for ky, kx in taps])
+    out, a = [], 0
+    for cin in src_cins:
+        nch = _ceil(cin, 64)
+        wp = torch.nn.functional.pad(w[:, a:a + cin], (0, 0, 0, 0, 0, nch * 64 - cin, 0, npad - O))
+        blk = _chunked(wp, nch).reshape(npad, nch, 64, kh * kw).index_select(3, idx).permute(1, 3, 0, 2)
+        out.append(blk)
+        a += cin
+    return out
+
+
 def _pack_conv(weight, src_cins, stride):
     """nn.Conv2d weight [O][I][kh][kw] -> (w_direct fp32 [1][K][O], w_tc bf16 [KB][Npad][64])."""
     O, I, kh, kw = weight.shape
@@ -128,7 +148,10 @@ def _pack_conv(weight, src_cins, stride):
         parts.append(w[:, a:a + cin].permute(2, 3, 1, 0).reshape(kh * kw * cin, O))
         a += cin
     w_direct = torch.cat(parts, 0)[None].contiguous()
-    blocks = [b.reshape(-1, npad, 64) for b in _pack_conv_blocks(w, src_cins, ky_order)]
+    if stride == 2 and L.lib().srd_tc_s2_halo():
+        blocks = [b.reshape(-1, npad, 64) for b in _pack_conv_blocks_taps(w, src_cins, _S2_TAPS)]
+    else:
+        blocks = [b.reshape(-1, npad, 64) for b in _pack_conv_blocks(w, src_cins, ky_order)]
     w_tc = torch.cat(blocks, 0).to(torch.bfloat16).contiguous()
     return w_direct.to(dev), w_tc.to(dev)
 

@@ -77,7 +77,9 @@ typedef struct {
   int32_t up;             /* S: 1 = plain conv; 2|4 = ConvTranspose2d(k=2S, stride=S, pad=S/2)   */
   int32_t N;              /* output channels                                                     */
   const float* w_direct;  /* fp32 [up*up][K][N], K order (src, ky, kx, c)                        */
-  const void* w_tc;       /* bf16 [up*up][KB][Npad][64] K-blocks in order (src, chunk, kx, ky*)  */
+  const void* w_tc;       /* bf16 [up*up][KB][Npad][64] K-blocks in order (src, chunk, kx, ky*);
+                           * stride 2 with srd_tc_s2_halo(): (src, chunk, tap) over the taps (ky, kx) =
+                           * (0,0) (0,2) (2,0) (2,2) (0,1) (2,1) (1,0) (1,2) (1,1)               */
   const float* bias;      /* [N]                                                                 */
   int32_t act;
   float alpha;
@@ -179,6 +181,10 @@ int srd_chain_segments(const SrdChain* chain);
  *        bit 6: hand work items to CTA pairs through a ticket counter instead of round-robin (measured slower).
  * b_resident: keep all weight k-blocks in shared memory when they fit. */
 int srd_tc_set_mode(int32_t a_mode, int32_t b_resident);
+/* 1 when stride-2 convs read halo boxes per (row parity, column parity) -- the default; SRD_S2_HALO=0 in the
+ * environment selects boxes per (kx, row parity).  Decides the tap order of a stride-2 conv's w_tc k-blocks
+ * (see SrdConvDesc.w_tc). */
+int srd_tc_s2_halo(void);
 /* Debug: plans created afterwards record per-item clock64 stamps into buf [grid][64][8] (NULL = off). */
 int srd_tc_set_debug(void* buf);
 /* Non-zero after the tcgen05 pipeline watchdog fired (value = which wait timed out). */
