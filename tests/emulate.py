@@ -36,7 +36,10 @@ def emulate_direct(srcs, cins, w_direct, N, stride, nk, k0, up):
 
 
 def emulate_tc(srcs, cins, w_tc, N, stride, nk, k0, up):
-    """w_tc [P][KB][Npad][64] bf16 with K-block order (src, chunk, kx, ky*), ky* = [0,2,1] for stride 2."""
+    """w_tc [P][KB][Npad][64] bf16 with K-block order (src, chunk, kx, ky*); stride 2: per (src, chunk) the nine taps in
+    the order of the (row parity, column parity) halo boxes (include/srdiff_b200.h, SrdConvDesc.w_tc), or -- with
+    SRD_S2_HALO=0 -- (kx, ky*) with ky* = [0,2,1]."""
+    from dgm_img_super_resolution_b200 import _lib
     B, Hp, Wp, _ = srcs[0].shape
     H, W = Hp - 2, Wp - 2
     Hm, Wm = H // stride, W // stride
@@ -55,14 +58,16 @@ def emulate_tc(srcs, cins, w_tc, N, stride, nk, k0, up):
         for src, cin in zip(srcs, cins):
             for ch in range((cin + 63) // 64):
                 c0, c1 = ch * 64, min(cin, ch * 64 + 64)
-                for kx in range(nk):
-                    for ky in ky_order:
-                        ys = torch.arange(Hm) * stride + ky0 + ky
-                        xs = torch.arange(Wm) * stride + kx0 + kx
-                        a = torch.zeros((B, Hm, Wm, 64))
-                        a[..., :c1 - c0] = src[:, ys][:, :, xs][..., c0:c1]     # TMA zero-fills c >= cin
-                        acc += a @ w[ph, kb].t()
-                        kb += 1
+                taps = [(ky, kx) for kx in range(nk) for ky in ky_order]
+                if stride == 2 and _lib.lib().srd_tc_s2_halo():
+                    taps = [(0, 0), (0, 2), (2, 0), (2, 2), (0, 1), (2, 1), (1, 0), (1, 2), (1, 1)]
+                for ky, kx in taps:
+                    ys = torch.arange(Hm) * stride + ky0 + ky
+                    xs = torch.arange(Wm) * stride + kx0 + kx
+                    a = torch.zeros((B, Hm, Wm, 64))
+                    a[..., :c1 - c0] = src[:, ys][:, :, xs][..., c0:c1]     # TMA zero-fills c >= cin
+                    acc += a @ w[ph, kb].t()
+                    kb += 1
         assert kb == w.shape[1]
         out[:, r::up, s::up] = acc[..., :N]
     return out
