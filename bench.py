@@ -91,9 +91,18 @@ class ClockSampler:
          "clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        self.index, self.rows, self.proc = index, [], None
+        self.index, self.rows, self.proc, self.limit = index, [], None, None
+
+    def _limit(self):
+        try:
+            out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=power.limit",
+                                  "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=10).stdout
+            return float(out.strip().splitlines()[0])
+        except Exception:
+            return None
 
     def start(self):
+        self.limit = self._limit()
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
                                           "--format=csv,noheader,nounits", "-lms", "200"],
@@ -115,7 +124,7 @@ class ClockSampler:
             self.proc.wait(timeout=2)
         except Exception:
             self.proc.kill()
-        sm, mx, reasons = [], None, set()
+        sm, mx, reasons, pw = [], None, set(), []
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for r in self.rows:
             if len(r) < 7:
@@ -125,13 +134,19 @@ class ClockSampler:
                 mx = float(r[1])
             except ValueError:
                 continue
+            try:
+                pw.append(float(r[2]))
+            except ValueError:
+                pass
             for n, v in zip(names, r[3:7]):
                 if v.lower().startswith("active"):
                     reasons.add(n)
         # "under load": drop idle samples (clock below half of the median of the top half)
         sm_load = sorted(sm)[len(sm) // 2:] if sm else []
+        pw_load = sorted(pw)[len(pw) // 2:] if pw else []
         return {"sm_mhz": statistics.median(sm_load) if sm_load else None, "sm_max_mhz": mx,
-                "reasons": sorted(reasons), "samples": len(sm)}
+                "reasons": sorted(reasons), "samples": len(sm),
+                "power_w": statistics.median(pw_load) if pw_load else None, "power_limit_w": self.limit}
 
 
 def synth_inputs(torch, B, lr, s, seed):
