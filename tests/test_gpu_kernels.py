@@ -151,13 +151,16 @@ def test_resnet_block_without_time(ours, precision, prec, cin, cout, H, W):
 
 
 @pytest.mark.parametrize("prec", ["fp32", "bf16_direct", "bf16"])
-@pytest.mark.parametrize("c,H,W", [(64, 16, 16), (128, 20, 12), (192, 40, 40)])
-def test_downsample_stride2(ours, precision, prec, c, H, W):
+@pytest.mark.parametrize("c,H,W,B", [(64, 16, 16, 2), (128, 20, 12, 2), (192, 40, 40, 2),
+                                     # many item rounds with two tiles per item (resident weights), tiles that straddle
+                                     # images, ragged column tiles on both sides of the halo box
+                                     (64, 96, 104, 5), (256, 12, 20, 3)])
+def test_downsample_stride2(ours, precision, prec, c, H, W, B):
     M, _ = ours
     precision.precision = prec
     m = _mk(M, M.Downsample, c)
     g = torch.Generator().manual_seed(8)
-    x = torch.randn((2, c, H, W), generator=g)
+    x = torch.randn((B, c, H, W), generator=g)
     sd = {k: v.cpu() for k, v in m.state_dict().items()}
     want = O._conv(sd, "conv.1", O._rpad(x), stride=2)
     got = m(x.to(DEV)).cpu()
