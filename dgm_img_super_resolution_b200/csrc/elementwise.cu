@@ -78,13 +78,14 @@ __global__ void __launch_bounds__(256, SRD_PS_MINBLOCKS) p_sample_kernel(const S
   const long long total = (long long)a.B * nq;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
-    const int b = (int)(i / nq), q = (int)(i % nq);
+    const int b = (int)((unsigned)i / (unsigned)nq), q = (int)((unsigned)i - (unsigned)b * (unsigned)nq);   // total < 2^31 (host check)
     const int t = a.t[b];
     const float* cf = a.coef + (size_t)t * 5;
     const float cA = __ldg(cf), cB = __ldg(cf + 1), c1 = __ldg(cf + 2), c2 = __ldg(cf + 3);
     const float sigma = (t == 0) ? 0.f : expf(0.5f * __ldg(cf + 4));   // nonzero_mask * exp(.5 logvar)
     const int pix = q * V;
     const int y = pix / a.W, x0p = pix % a.W;
+    const size_t off0 = (size_t)b * a.C * HW + pix;        // channel c of this pixel group: off0 + c * HW
     constexpr int NHC = SMALLC ? 4 : 8;         // channels kept for the NHWC copy (the rest of the 8 are zero)
     float nh[V][NHC];
     if (a.nhwc_out) {
@@ -101,7 +102,7 @@ __global__ void __launch_bounds__(256, SRD_PS_MINBLOCKS) p_sample_kernel(const S
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         if (c < a.C) {
-          const size_t off = ((size_t)b * a.C + c) * HW + pix;
+          const size_t off = off0 + (size_t)c * HW;
           // plain (coherent) loads: x_out may alias x, and ld.global.nc on memory this kernel writes is undefined
           px4[c] = *reinterpret_cast<const float4*>(a.x + off);
           pe4[c] = *reinterpret_cast<const float4*>(a.eps + off);
@@ -113,7 +114,7 @@ __global__ void __launch_bounds__(256, SRD_PS_MINBLOCKS) p_sample_kernel(const S
 #pragma unroll
     for (int cu = 0; cu < (SMALLC ? 4 : 1); ++cu)
     for (int c = SMALLC ? cu : 0; c < (SMALLC ? (cu < a.C ? cu + 1 : 0) : a.C); ++c) {
-      const size_t off = ((size_t)b * a.C + c) * HW + pix;
+      const size_t off = off0 + (size_t)c * HW;
       float xv[V], ev[V], zv[V], ov[V], x0v[V];
       if (SMALLC) {
         const float4 t0 = px4[cu], t1 = pe4[cu];
@@ -179,13 +180,29 @@ __global__ void __launch_bounds__(256, SRD_PS_MINBLOCKS) p_sample_kernel(const S
     if (a.nhwc_out) {
       // interior pixel groups (all but the two outermost rows / columns, whose pixels also own mirrored ring
       // copies): the V pixels are V consecutive 8-channel slots -- plain vector stores, no ring logic
-      const bool interior = SMALLC && sizeof(T) == 2 && y > 1 && y < a.H - 2 && x0p > 1 && x0p + V < a.W - 2;
-      if (interior) {
-        uint4* dst = reinterpret_cast<uint4*>(static_cast<T*>(a.nhwc_out) +
-                                              ((size_t)(b * (a.H + 2) + y + 1) * (a.W + 2) + x0p + 1) * 8);
+      // bf16, <= 4 channels, V == 4 (quads never straddle a row): the V pixels are V consecutive 8-channel slots.
+      // The mirrored ring copies (pad row 0 <- row 1, pad row H+1 <- row H-2, same for columns, corners follow) are
+      // straight-line predicated stores: nearly every warp holds a quad of the first / last column, so a generic
+      // per-pixel ring loop would run -- for a few active lanes -- in almost every warp.
+      if (SMALLC && sizeof(T) == 2 && V == 4 && a.H >= 4 && a.W >= 8) {
+        const int Wp = a.W + 2;
+        uint4* dst = reinterpret_cast<uint4*>(a.nhwc_out) + ((size_t)(b * (a.H + 2) + y + 1) * Wp + x0p + 1);
+        uint4 val[V];
 #pragma unroll
         for (int v = 0; v < V; ++v)
-          dst[v] = make_uint4(pack_bf16x2(nh[v][0], nh[v][1]), pack_bf16x2(nh[v][2], NHC > 3 ? nh[v][NHC > 3 ? 3 : 0] : 0.f), 0u, 0u);
+          val[v] = make_uint4(pack_bf16x2(nh[v][0], nh[v][1]), pack_bf16x2(nh[v][2], NHC > 3 ? nh[v][NHC > 3 ? 3 : 0] : 0.f), 0u, 0u);
+        const bool lef = (x0p == 0), rig = (x0p + V == a.W);     // ox == 1 is val[1], ox == W - 2 is val[V - 2]
+#pragma unroll
+        for (int v = 0; v < V; ++v) dst[v] = val[v];
+        if (lef) dst[-1] = val[1];
+        if (rig) dst[V] = val[V - 2];
+        if (y == 1 || y == a.H - 2) {
+          uint4* d2 = (y == 1) ? dst - 2 * Wp : dst + 2 * Wp;
+#pragma unroll
+          for (int v = 0; v < V; ++v) d2[v] = val[v];
+          if (lef) d2[-1] = val[1];
+          if (rig) d2[V] = val[V - 2];
+        }
       } else {
 #pragma unroll
         for (int v = 0; v < V; ++v) {
@@ -375,6 +392,7 @@ int srd_p_sample_step(const SrdPSampleArgs* a, void* stream) {
   SRD_CHECK(!a->nhwc_out || (a->nhwc_ct == 8 && a->C <= 8), "srd_p_sample_step: nhwc_out needs ct == 8, C <= 8");
   const bool v4 = (a->W % 4) == 0;
   const long long total = (long long)a->B * (a->H * a->W / (v4 ? 4 : 1));
+  SRD_CHECK(total < (1LL << 31), "srd_p_sample_step: more than 2^31 pixel groups");
   const int grid = grid_for(total);
   cudaStream_t s = (cudaStream_t)stream;
   if (a->act_dtype == SRD_BF16) {
